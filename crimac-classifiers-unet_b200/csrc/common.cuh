@@ -1,0 +1,71 @@
+// Shared host/device definitions for the echogram U-Net kernels (libcrimac_b200.so).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+// Spatial M-tile of every implicit-GEMM kernel: 8 range rows x 16 pings = 128 output pixels = the 128 TMEM lanes.
+// A 2x2 max-pool window therefore always lives inside one warp's 32 lanes (rows 2w, 2w+1).
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int TILE_M = 128;
+constexpr int KBLK = 64;  // bf16 channels per k-step = one 128-byte swizzle row
+
+// View of an NHWC bf16 activation tensor that may be a channel slice of a wider (concat) buffer.
+struct View {
+  bf16* ptr;    // first element of channel 0 of this view (slice offset already applied)
+  int N, H, W;  // batch, range rows, pings
+  int C;        // channels in the view
+  int pitch;    // elements between consecutive pixels (>= C)
+};
+
+// ---- epilogue modes of conv_igemm
+enum EpiMode : int {
+  EPI_STORE = 0,  // y = acc*scale+shift, optional ReLU, optional 2x2 max-pool copy, optional convT scatter
+  EPI_STATS = 1,  // raw = acc+shift stored as bf16 + per-tile per-channel sum / sum of squares (train-mode BN)
+  EPI_HEAD = 2,   // folded BN + ReLU, then the 1x1 head (+softmax) per pixel; BLOCK_N must be all 64 channels
+};
+
+struct ConvParams {
+  CUtensorMap a_map[4];  // activations; 3x3 / 1x1 use map 0, convT backward-data uses one map per (ky,kx)
+  CUtensorMap b_map;     // packed weights [N_total][taps*cin] bf16, K contiguous
+  int taps;              // 9, 1 or 4
+  int tap_mode;          // 0: tap -> (dy,dx) offsets on map 0 (3x3: tap=ky*3+kx; 1 tap: centre); 1: tap -> map index
+  int cin;               // channels per tap, multiple of 64
+  int NB, H, W;          // GEMM-M geometry: output pixels = NB*H*W
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  // epilogue
+  bf16* out;
+  int out_pitch;         // elements per output pixel
+  int relu;
+  int convt_cout;        // >0: convT scatter, N index = (ky*2+kx)*convt_cout + co, output is 2H x 2W
+  const float* scale;    // [N_total]
+  const float* shift;    // [N_total]
+  bf16* pool_out;        // optional (EPI_STORE): 2x2 max-pooled copy, H/2 x W/2
+  int pool_pitch;
+  float* stats;          // EPI_STATS: [m_tiles][2][N_total] partial sums
+  // EPI_HEAD
+  const float* head_w;   // [n_classes][64]
+  const float* head_b;   // [n_classes]
+  float* head_out;       // NCHW fp32 (NB, n_classes, H, W): probabilities (softmax=1) or logits
+  int n_classes;
+  int head_softmax;
+};
+
+struct WgradParams {
+  CUtensorMap a_map;     // "fixed" operand, rows of GEMM-M (conv: dY -> Cout; convT: X -> Cin)
+  CUtensorMap b_map[4];  // "tap" operand, rows of GEMM-N (conv: X shifted by tap; convT: dY sub-sampled per tap)
+  int taps, tap_mode;    // as ConvParams
+  int M_total, N_total;  // channels of the two operands
+  int NB, H, W;          // pixel geometry of the reduction dimension
+  int tiles_x, tiles_y;  // 4x16-pixel k-tiles per image
+  int k_tiles_total;     // NB*tiles_y*tiles_x
+  int splits;            // split-K factor (gridDim.z)
+  int m_tiles, n_tiles;
+  float* dw;             // fp32 gradient in PyTorch layout: index (m*N_total + n)*taps + tap ; accumulated with red.add
+};
+
+#define CRIMAC_MAX_CLASSES 8

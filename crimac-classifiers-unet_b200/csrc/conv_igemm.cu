@@ -1,0 +1,359 @@
+// Implicit-GEMM convolution for the echogram U-Net on sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM),
+// operands staged by TMA into 128B-swizzled shared memory, persistent warp-specialised CTAs.
+//
+//   GEMM view:  M = output pixels (8x16 spatial tile = 128 TMEM lanes),
+//                                  N = output channels, K = taps * Cin.
+//   A k-step = (tap, 64-channel block): ONE 4-D TMA box {64 ch, 16 pings, 8 rows, 1 patch} of the NHWC
+//   activation tensor at the tap-shifted coordinate; out-of-bounds rows/pings are zero-filled by TMA,
+//   which IS nn.Conv2d's zero padding (reference models/unet.py:35-44).  The same kernel serves
+//     - 3x3 conv forward + BN/ReLU epilogue            (unet.py:76-83, :135-136)
+//     - 3x3 conv backward-data (weights packed rotated, Cin<->Cout swapped)
+//     - ConvTranspose2d(k2,s2) forward as a 1-tap GEMM with a scatter epilogue into the concat buffer
+//       (unet.py:47-49, :130-132)
+//     - ConvTranspose2d backward-data as a 4-"tap" GEMM, one sub-sampled tensor map per (ky,kx)
+//     - the fused 1x1 head + softmax epilogue           (unet.py:284,342; pipeline.py:218)
+//
+// Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
+// w4..w7 = epilogue (thread t <-> TMEM lane <-> pixel t of the tile).  Two TMEM accumulator stages let
+// the epilogue of tile i overlap the main loop of tile i+1.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "devfn.cuh"
+
+namespace {
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int A_BYTES = TILE_M * KBLK * 2;
+  static constexpr int B_BYTES = BLOCK_N * KBLK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int AUX_BYTES = 256 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
+                                   (CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_affine = reinterpret_cast<float*>(aux + 256);  // [2 acc stages][scale BLOCK_N | shift BLOCK_N]
+  float* s_red = s_affine + 4 * BLOCK_N;                  // [4 warps][2][BLOCK_N]
+  float* s_head = s_red + 8 * BLOCK_N;                    // [ncls][64] + [ncls]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.a_map[0]);
+    ptx::prefetch_tmap(&p.b_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  if (EPI == EPI_HEAD && warp >= 4) {
+    const int e = threadIdx.x - 128;
+    for (int i = e; i < p.n_classes * 64; i += 128) s_head[i] = p.head_w[i];
+    if (e < p.n_classes) s_head[CRIMAC_MAX_CLASSES * 64 + e] = p.head_b[e];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int cblocks = p.cin / KBLK;
+  const int ksteps = p.taps * cblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int tx = m_tile % p.tiles_x;
+        m_tile /= p.tiles_x;
+        const int ty = m_tile % p.tiles_y;
+        const int img = m_tile / p.tiles_y;
+        const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BLOCK_N;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int dy = 0, dx = 0, mi = 0;
+          if (p.tap_mode == 0) {
+            if (p.taps == 9) {
+              dy = tap / 3 - 1;
+              dx = tap % 3 - 1;
+            }
+          } else {
+            mi = tap;
+          }
+          for (int cb = 0; cb < cblocks; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            ptx::tma_load_4d(sa, &p.a_map[mi], &full_bar[stage], cb * KBLK, x0 + dx, y0 + dy, img);
+            ptx::tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.cin + cb * KBLK, n0);
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = ptx::make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = ptx::make_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k) {
+            // +32 bytes (= 16 bf16) along K inside the 128-byte swizzle row: start-address field += 2
+            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = threadIdx.x - 128;  // 0..127
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;      // tile row <-> pixel
+    const int py = r >> 4, px = r & 15;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile_id = tile / p.n_tiles;
+      int m_tile = m_tile_id;
+      const int tx = m_tile % p.tiles_x;
+      m_tile /= p.tiles_x;
+      const int ty = m_tile % p.tiles_y;
+      const int img = m_tile / p.tiles_y;
+      const int n0 = n_tile * BLOCK_N;
+      const int y = ty * TILE_H + py, x = tx * TILE_W + px;
+      const bool valid = (y < p.H) && (x < p.W);
+
+      float* sc = s_affine + as * 2 * BLOCK_N;
+      float* sh = sc + BLOCK_N;
+      for (int i = e; i < BLOCK_N; i += 128) {
+        sc[i] = p.scale ? p.scale[n0 + i] : 1.0f;
+        // ConvTranspose scatter: N index = (ky,kx,co) and the bias is per co
+        sh[i] = p.shift ? p.shift[p.convt_cout > 0 ? (n0 + i) % p.convt_cout : n0 + i] : 0.0f;
+      }
+      epi_bar();
+
+      ptx::mbar_wait(&tmem_full[as], aphase);
+      ptx::tc_fence_after();
+
+      float logit[CRIMAC_MAX_CLASSES];
+      if (EPI == EPI_HEAD) {
+#pragma unroll
+        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] = (k < p.n_classes) ? s_head[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
+      }
+
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + chunk * 32, v);
+        ptx::tmem_ld_wait();
+        const int ng = n0 + chunk * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(v[j]) * sc[chunk * 32 + j] + sh[chunk * 32 + j];
+          if (EPI != EPI_STATS && p.relu) a = fmaxf(a, 0.f);
+          f[j] = a;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+
+        if (EPI == EPI_HEAD) {
+#pragma unroll
+          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) {
+            if (k < p.n_classes) {
+              float acc = logit[k];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc = fmaf(f[j], s_head[k * 64 + chunk * 32 + j], acc);
+              logit[k] = acc;
+            }
+          }
+        }
+
+        if (p.out != nullptr && valid) {
+          bf16* dst;
+          if (p.convt_cout > 0) {
+            const int kk = ng / p.convt_cout, co = ng - kk * p.convt_cout;
+            const long opix = (static_cast<long>(img) * (2 * p.H) + (2 * y + (kk >> 1))) * (2 * p.W) + (2 * x + (kk & 1));
+            dst = p.out + opix * p.out_pitch + co;
+          } else {
+            const long opix = (static_cast<long>(img) * p.H + y) * p.W + x;
+            dst = p.out + opix * p.out_pitch + ng;
+          }
+          store16(dst, pk);
+          store16(dst + 8, pk + 4);
+          store16(dst + 16, pk + 8);
+          store16(dst + 24, pk + 12);
+        }
+
+        if (EPI == EPI_STORE && p.pool_out != nullptr) {
+          uint32_t pm[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t m = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+            pm[j] = bf16x2_max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+          }
+          if (valid && !(px & 1) && !(py & 1)) {
+            const long ppix = (static_cast<long>(img) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+            bf16* dst = p.pool_out + ppix * p.pool_pitch + ng;
+            store16(dst, pm);
+            store16(dst + 8, pm + 4);
+            store16(dst + 16, pm + 8);
+            store16(dst + 24, pm + 12);
+          }
+        }
+
+        if (EPI == EPI_STATS) {
+          // statistics of the bf16-rounded values the BN-apply pass will read back
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 t = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]));
+            const float a = valid ? t.x : 0.f, b = valid ? t.y : 0.f;
+            s1[2 * j] = a;
+            s1[2 * j + 1] = b;
+            s2[2 * j] = a * a;
+            s2[2 * j + 1] = b * b;
+          }
+          xpose_reduce(s1, lane);
+          xpose_reduce(s2, lane);
+          s_red[(q * 2 + 0) * BLOCK_N + chunk * 32 + lane] = s1[0];
+          s_red[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = s2[0];
+        }
+      }
+
+      // accumulator fully read: hand the TMEM stage back to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[as]);
+
+      if (EPI == EPI_STATS) {
+        epi_bar();
+        const int n_total = p.n_tiles * BLOCK_N;
+        for (int c = e; c < BLOCK_N; c += 128) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            a += s_red[(w * 2 + 0) * BLOCK_N + c];
+            b += s_red[(w * 2 + 1) * BLOCK_N + c];
+          }
+          float* dst = p.stats + static_cast<long>(m_tile_id) * 2 * n_total;
+          dst[n0 + c] = a;
+          dst[n_total + n0 + c] = b;
+        }
+      }
+
+      if (EPI == EPI_HEAD && valid) {
+        if (p.head_softmax) {
+          float mx = logit[0];
+#pragma unroll
+          for (int k = 1; k < CRIMAC_MAX_CLASSES; ++k)
+            if (k < p.n_classes) mx = fmaxf(mx, logit[k]);
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+            if (k < p.n_classes) {
+              logit[k] = __expf(logit[k] - mx);
+              sum += logit[k];
+            }
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] *= inv;
+        }
+#pragma unroll
+        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+          if (k < p.n_classes)
+            p.head_out[((static_cast<long>(img) * p.n_classes + k) * p.H + y) * p.W + x] = logit[k];
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  auto kern = conv_igemm_kernel<BLOCK_N, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// BLOCK_N in {64,128,256}; p.n_tiles*BLOCK_N == N_total must hold.
+cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num_sms, cudaStream_t stream) {
+#define CASE(BN, EP) \
+  if (block_n == BN && epi == EP) return launch_one<BN, EP>(p, num_sms, stream);
+  CASE(64, EPI_STORE) CASE(128, EPI_STORE) CASE(256, EPI_STORE)
+  CASE(64, EPI_STATS) CASE(128, EPI_STATS) CASE(256, EPI_STATS)
+  CASE(64, EPI_HEAD)
+#undef CASE
+  return cudaErrorInvalidValue;
+}

@@ -1,0 +1,801 @@
+// CUDA-core kernels of the echogram U-Net path: everything that is HBM-bound rather than a dense contraction.
+//   first conv (Cin = #frequencies, K = 36/54: fp32 in, too thin for the tensor pipe)   unet.py:76 (down_convs.0.main.0)
+//   train-mode BatchNorm statistics finalize / apply (+ReLU, +2x2 max-pool, +concat write) unet.py:78-92
+//   1x1 head forward / backward, class-weighted cross-entropy                              unet.py:342, pipeline.py:135-138,176
+//   BatchNorm/ReLU backward (two-phase), max-pool backward + skip-gradient add             autograd of unet.py:76-93,130-136
+// All activation tensors are NHWC bf16 "views" (pointer, pitch) so that concat buffers are written/read in place.
+#include "host_util.h"
+#include "devfn.cuh"
+
+namespace {
+
+constexpr int kMaxBlocks = 148 * 8;
+
+// ============================================================================ first conv (fp32 NCHW in -> 64 ch)
+// One thread = one pixel of an 8x16 tile (same tile numbering as conv_igemm so the statistics buffers line up).
+template <int CIN>
+__global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, int relu, int NB, int H, int W,
+                                                         bf16* __restrict__ out, int out_pitch, float* stats) {
+  constexpr int K = CIN * 9;
+  __shared__ __align__(16) float ws[K * 64];  // [k][co]
+  __shared__ float s_sc[64], s_sh[64];
+  __shared__ float s_red[4][2][64];
+  for (int i = threadIdx.x; i < K * 64; i += 128) {
+    const int co = i & 63, k = i >> 6;
+    ws[i] = w[co * K + k];
+  }
+  if (threadIdx.x < 64) {
+    s_sc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f;
+    s_sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
+  const int total = NB * tiles_x * tiles_y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int img = t / tiles_y;
+    const int y = ty * TILE_H + py, xx = tx * TILE_W + px;
+    const bool valid = y < H && xx < W;
+    float in[K];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xq = xx + tap % 3 - 1;
+        const bool ok = valid && yy >= 0 && yy < H && xq >= 0 && xq < W;
+        in[ci * 9 + tap] = ok ? __ldg(&x[((static_cast<long>(img) * CIN + ci) * H + yy) * W + xq]) : 0.f;
+      }
+    bf16* dst = out + ((static_cast<long>(img) * H + y) * W + xx) * out_pitch;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(&ws[k * 64 + half * 32]);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 wv = wr[j4];
+          acc[4 * j4 + 0] = fmaf(in[k], wv.x, acc[4 * j4 + 0]);
+          acc[4 * j4 + 1] = fmaf(in[k], wv.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(in[k], wv.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(in[k], wv.w, acc[4 * j4 + 3]);
+        }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = acc[2 * j] * s_sc[half * 32 + 2 * j] + s_sh[half * 32 + 2 * j];
+        float b = acc[2 * j + 1] * s_sc[half * 32 + 2 * j + 1] + s_sh[half * 32 + 2 * j + 1];
+        if (relu) {
+          a = fmaxf(a, 0.f);
+          b = fmaxf(b, 0.f);
+        }
+        pk[j] = pack_bf16x2(a, b);
+      }
+      if (valid) {
+        store16(dst + half * 32, pk);
+        store16(dst + half * 32 + 8, pk + 4);
+        store16(dst + half * 32 + 16, pk + 8);
+        store16(dst + half * 32 + 24, pk + 12);
+      }
+      if (stats != nullptr) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 v = unpack_bf16x2(pk[j]);
+          const float a = valid ? v.x : 0.f, b = valid ? v.y : 0.f;
+          s1[2 * j] = a;
+          s1[2 * j + 1] = b;
+          s2[2 * j] = a * a;
+          s2[2 * j + 1] = b * b;
+        }
+        xpose_reduce(s1, lane);
+        xpose_reduce(s2, lane);
+        s_red[warp][0][half * 32 + lane] = s1[0];
+        s_red[warp][1][half * 32 + lane] = s2[0];
+      }
+    }
+    if (stats != nullptr) {
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 4; ++wv) {
+          a += s_red[wv][0][c];
+          b += s_red[wv][1][c];
+        }
+        stats[static_cast<long>(tile) * 128 + c] = a;
+        stats[static_cast<long>(tile) * 128 + 64 + c] = b;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ============================================================================ BN statistics -> scale/shift
+// partials [m_tiles][2][C] (sum, sum of squares) -> batch mean / biased var; running stats (momentum, unbiased var).
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int m_tiles, int C,
+                                                          double count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* running_mean,
+                                                          float* running_var, long long* num_batches_tracked,
+                                                          float momentum, float eps, float* scale, float* shift,
+                                                          float* save_mean, float* save_invstd) {
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C)
+    for (int t = tl; t < m_tiles; t += 8) {
+      s1 += partials[static_cast<long>(t) * 2 * C + c];
+      s2 += partials[static_cast<long>(t) * 2 * C + C + c];
+    }
+  sh[0][tl][cl] = s1;
+  sh[1][tl][cl] = s2;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    for (int t = 1; t < 8; ++t) {
+      s1 += sh[0][t][cl];
+      s2 += sh[1][t][cl];
+    }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - static_cast<float>(mean) * sc;
+    save_mean[c] = static_cast<float>(mean);
+    save_invstd[c] = invstd;
+    if (running_mean != nullptr) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+}
+
+// eval-mode folding: y = conv*scale + shift with scale = g/sqrt(rv+eps), shift = (bias - rm)*scale + beta
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                    const float* conv_bias, float eps, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+    scale[c] = sc;
+    shift[c] = (conv_bias[c] - rm[c]) * sc + beta[c];
+  }
+}
+
+// ============================================================================ BN apply + ReLU (+pool)
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_apply_kernel(View raw, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, View act, View pool) {
+  const int groups = raw.C >> 3;
+  const int Ho = POOL ? raw.H >> 1 : raw.H, Wo = POOL ? raw.W >> 1 : raw.W;
+  const long total = static_cast<long>(raw.N) * Ho * Wo * groups;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long pix = i / groups;
+    const int xo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int yo = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    float sc[8], sh[8];
+    ldg8f(scale + g * 8, sc);
+    ldg8f(shift + g * 8, sh);
+    if (!POOL) {
+      const long p = (static_cast<long>(n) * raw.H + yo) * raw.W + xo;
+      float v[8];
+      load8(raw.ptr + p * raw.pitch + g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+      store8(act.ptr + p * act.pitch + g * 8, v);
+    } else {
+      uint32_t mx[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long p = (static_cast<long>(n) * raw.H + 2 * yo + (q >> 1)) * raw.W + 2 * xo + (q & 1);
+        float v[8];
+        load8(raw.ptr + p * raw.pitch + g * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+        uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                          pack_bf16x2(v[6], v[7])};
+        store16(act.ptr + p * act.pitch + g * 8, pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx[j] = q == 0 ? pk[j] : bf16x2_max(mx[j], pk[j]);
+      }
+      const long pp = (static_cast<long>(n) * Ho + yo) * Wo + xo;
+      store16(pool.ptr + pp * pool.pitch + g * 8, mx);
+    }
+  }
+}
+
+// ============================================================================ 1x1 head forward (train path)
+// act (N,H,W,64) bf16 -> logits (N,ncls,H,W) fp32
+__global__ void __launch_bounds__(128) head_fwd_kernel(View act, const float* __restrict__ hw,
+                                                       const float* __restrict__ hb, int ncls, float* logits) {
+  __shared__ float s_w[CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES];
+  for (int i = threadIdx.x; i < ncls * 64; i += blockDim.x) s_w[i] = hw[i];
+  if (threadIdx.x < ncls) s_w[CRIMAC_MAX_CLASSES * 64 + threadIdx.x] = hb[threadIdx.x];
+  __syncthreads();
+  const long HW = static_cast<long>(act.H) * act.W;
+  const long total = act.N * HW;
+  for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long>(gridDim.x) * blockDim.x) {
+    float lg[CRIMAC_MAX_CLASSES];
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) lg[k] = k < ncls ? s_w[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float v[8];
+      load8(act.ptr + p * act.pitch + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+        if (k < ncls) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) lg[k] = fmaf(v[j], s_w[k * 64 + g * 8 + j], lg[k]);
+        }
+    }
+    const long n = p / HW, r = p - n * HW;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) logits[(n * ncls + k) * HW + r] = lg[k];
+  }
+}
+
+// ============================================================================ class-weighted cross-entropy
+// nn.CrossEntropyLoss(weight, ignore_index=-100, reduction='mean') (pipeline.py:135-138): per-pixel
+// w[y]*(lse - z[y]); writes the UNNORMALISED gradient w[y]*(softmax - onehot) and per-block partial sums.
+__global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict__ logits,
+                                                         const long long* __restrict__ labels,
+                                                         const float* __restrict__ cw, int ncls, long HW, long total,
+                                                         long long ignore_index, float* dlogits, double* partials) {
+  __shared__ double s_a[8], s_b[8];
+  double la = 0.0, lb = 0.0;
+  for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = p / HW, r = p - n * HW;
+    float z[CRIMAC_MAX_CLASSES];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) {
+        z[k] = logits[(n * ncls + k) * HW + r];
+        mx = fmaxf(mx, z[k]);
+      }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) sum += expf(z[k] - mx);
+    const float lse = mx + logf(sum);
+    const long long y = labels[p];
+    const bool use = (y != ignore_index) && y >= 0 && y < ncls;
+    const float wy = use ? cw[y] : 0.f;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) {
+        const float pk = expf(z[k] - lse);
+        if (dlogits) dlogits[(n * ncls + k) * HW + r] = wy * (pk - ((use && k == y) ? 1.f : 0.f));
+        if (use && k == y) la += static_cast<double>(wy) * static_cast<double>(lse - z[k]);
+      }
+    lb += wy;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    la += __shfl_xor_sync(0xffffffffu, la, o);
+    lb += __shfl_xor_sync(0xffffffffu, lb, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_a[threadIdx.x >> 5] = la;
+    s_b[threadIdx.x >> 5] = lb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      la += s_a[i];
+      lb += s_b[i];
+    }
+    partials[2 * blockIdx.x] = la;
+    partials[2 * blockIdx.x + 1] = lb;
+  }
+}
+// out[0] = loss, out[1] = 1/sum_w (gradient normaliser), out[2] = sum_w
+__global__ void ce_finalize_kernel(const double* partials, int nblocks, float* out) {
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblocks; ++i) {
+    a += partials[2 * i];
+    b += partials[2 * i + 1];
+  }
+  out[0] = static_cast<float>(a / b);  // all-ignored batch -> NaN, as the reference
+  out[1] = static_cast<float>(1.0 / b);
+  out[2] = static_cast<float>(b);
+}
+
+// ============================================================================ 1x1 head backward
+// dAct[p][c] = s * sum_k dl[k][p] W[k][c];  dW[k][c] = s * sum_p dl[k][p] act[p][c];  db[k] = s * sum_p dl[k][p]
+// (s = *gscale or 1).  One block = 128 pixels per iteration; partials per block, summed by head_bwd_finalize.
+__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dlogits, const float* gscale,
+                                                       View act, const float* __restrict__ hw, int ncls, View dact,
+                                                       float* partials) {
+  __shared__ float s_w[CRIMAC_MAX_CLASSES * 64];
+  __shared__ float s_dl[128][CRIMAC_MAX_CLASSES + 1];
+  __shared__ __align__(16) bf16 s_act[128][72];
+  for (int i = threadIdx.x; i < ncls * 64; i += 128) s_w[i] = hw[i];
+  const float s = gscale ? *gscale : 1.f;
+  const long HW = static_cast<long>(act.H) * act.W;
+  const long total = act.N * HW;
+  const int c = threadIdx.x & 63, half = threadIdx.x >> 6;
+  float accw[CRIMAC_MAX_CLASSES], accb[CRIMAC_MAX_CLASSES];
+#pragma unroll
+  for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) accw[k] = accb[k] = 0.f;
+  __syncthreads();
+  for (long base = static_cast<long>(blockIdx.x) * 128; base < total; base += static_cast<long>(gridDim.x) * 128) {
+    const long p = base + threadIdx.x;
+    const bool valid = p < total;
+    float dl[CRIMAC_MAX_CLASSES];
+    const long n = valid ? p / HW : 0, r = valid ? p - n * HW : 0;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) {
+      dl[k] = (valid && k < ncls) ? s * dlogits[(n * ncls + k) * HW + r] : 0.f;
+      if (k < ncls) s_dl[threadIdx.x][k] = dl[k];
+    }
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (valid) u = *reinterpret_cast<const uint4*>(act.ptr + p * act.pitch + g * 8);
+      *reinterpret_cast<uint4*>(&s_act[threadIdx.x][g * 8]) = u;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+          if (k < ncls) a = fmaf(dl[k], s_w[k * 64 + g * 8 + j], a);
+        o[j] = a;
+      }
+      if (valid) store8(dact.ptr + p * dact.pitch + g * 8, o);
+    }
+    __syncthreads();
+    for (int q = half * 64; q < half * 64 + 64; ++q) {
+      const float a = __bfloat162float(s_act[q][c]);
+#pragma unroll
+      for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+        if (k < ncls) {
+          const float d = s_dl[q][k];
+          accw[k] = fmaf(d, a, accw[k]);
+          if (c == 0) accb[k] += d;
+        }
+    }
+    __syncthreads();
+  }
+  // partial layout per block: [2 halves][ncls*64 + ncls]
+  float* dst = partials + (static_cast<long>(blockIdx.x) * 2 + half) * (ncls * 64 + ncls);
+#pragma unroll
+  for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+    if (k < ncls) {
+      dst[k * 64 + c] = accw[k];
+      if (c == 0) dst[ncls * 64 + k] = accb[k];
+    }
+}
+__global__ void head_bwd_finalize_kernel(const float* partials, int nparts, int ncls, float* dw, float* db,
+                                         int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = ncls * 64 + ncls;
+  if (i >= per) return;
+  double a = 0.0;
+  for (int b = 0; b < nparts; ++b) a += partials[static_cast<long>(b) * per + i];
+  float* d = i < ncls * 64 ? dw + i : db + (i - ncls * 64);
+  *d = accumulate ? *d + static_cast<float>(a) : static_cast<float>(a);
+}
+
+// ============================================================================ BN + ReLU backward
+// Thread = fixed 8-channel group, grid-stride over pixels; per-block partial sums [blocks][NQ][C].
+// phase 1 (reduce): g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * xhat
+template <int NQ, typename F>
+__device__ __forceinline__ void channel_reduce(int C, long npix, float* partials, F&& per_pixel) {
+  extern __shared__ float s_cr[];  // [ppb][NQ][C]
+  const int groups = C >> 3;
+  const int ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float acc[NQ][8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+  if (pl < ppb)
+    for (long p = static_cast<long>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<long>(gridDim.x) * ppb)
+      per_pixel(p, g, acc);
+  if (pl < ppb) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_cr[(pl * NQ + q) * C + g * 8 + j] = acc[q][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < ppb; ++l) a += s_cr[l * NQ * C + i];
+    partials[static_cast<long>(blockIdx.x) * NQ * C + i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dact, View raw, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, float* partials) {
+  const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
+  channel_reduce<2>(raw.C, npix, partials, [&](long p, int g, float(&acc)[2][8]) {
+    float d[8], r[8], sc[8], sh[8], mu[8], is[8];
+    load8(dact.ptr + p * dact.pitch + g * 8, d);
+    load8(raw.ptr + p * raw.pitch + g * 8, r);
+    ldg8f(scale + g * 8, sc);
+    ldg8f(shift + g * 8, sh);
+    ldg8f(mean + g * 8, mu);
+    ldg8f(invstd + g * 8, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
+      acc[0][j] += gg;
+      acc[1][j] += gg * (r[j] - mu[j]) * is[j];
+    }
+  });
+}
+
+// partials [nparts][2][C] -> dgamma, dbeta (fp32 grads) and the two per-channel means used by the apply pass
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
+                                       float* dgamma, float* dbeta, int accumulate, float* c1, float* c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nparts; ++i) {
+    a += partials[static_cast<long>(i) * 2 * C + c];
+    b += partials[static_cast<long>(i) * 2 * C + C + c];
+  }
+  dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(a) : static_cast<float>(a);
+  dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(b) : static_cast<float>(b);
+  c1[c] = static_cast<float>(a / count);
+  c2[c] = static_cast<float>(b / count);
+}
+
+// phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) -> bf16; partial = sum dRaw (= the conv-bias gradient)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ c1, const float* __restrict__ c2,
+                                                           View draw, float* partials) {
+  const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
+  channel_reduce<1>(raw.C, npix, partials, [&](long p, int g, float(&acc)[1][8]) {
+    float d[8], r[8], sc[8], sh[8], mu[8], is[8], k1[8], k2[8], o[8];
+    load8(dact.ptr + p * dact.pitch + g * 8, d);
+    load8(raw.ptr + p * raw.pitch + g * 8, r);
+    ldg8f(scale + g * 8, sc);
+    ldg8f(shift + g * 8, sh);
+    ldg8f(mean + g * 8, mu);
+    ldg8f(invstd + g * 8, is);
+    ldg8f(c1 + g * 8, k1);
+    ldg8f(c2 + g * 8, k2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
+      const float xh = (r[j] - mu[j]) * is[j];
+      o[j] = sc[j] * (gg - k1[j] - xh * k2[j]);
+    }
+    store8(draw.ptr + p * draw.pitch + g * 8, o);
+    float ob[8];
+    load8(draw.ptr + p * draw.pitch + g * 8, ob);  // the rounded values, as the wgrad/dgrad kernels will see them
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += ob[j];
+  });
+}
+
+// plain per-channel sum of a view (ConvTranspose bias gradient)
+__global__ void __launch_bounds__(256) view_colsum_kernel(View v, float* partials) {
+  const long npix = static_cast<long>(v.N) * v.H * v.W;
+  channel_reduce<1>(v.C, npix, partials, [&](long p, int g, float(&acc)[1][8]) {
+    float d[8];
+    load8(v.ptr + p * v.pitch + g * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += d[j];
+  });
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nparts, int C, float* out,
+                                       int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0;
+  for (int i = 0; i < nparts; ++i) a += partials[static_cast<long>(i) * C + c];
+  out[c] = accumulate ? out[c] + static_cast<float>(a) : static_cast<float>(a);
+}
+
+// ============================================================================ max-pool backward + skip gradient
+// dA[2x2 window] = dSkip[window] + (first maximal element of the window ? dP : 0)     (autograd of unet.py:86,92,132)
+__global__ void __launch_bounds__(256) pool_bwd_add_kernel(View act, View dpool, View dskip, View dact) {
+  const int groups = act.C >> 3;
+  const int Ho = act.H >> 1, Wo = act.W >> 1;
+  const long total = static_cast<long>(act.N) * Ho * Wo * groups;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long pix = i / groups;
+    const int xo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int yo = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    float a[4][8], dp[8];
+    long pidx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pidx[q] = (static_cast<long>(n) * act.H + 2 * yo + (q >> 1)) * act.W + 2 * xo + (q & 1);
+      load8(act.ptr + pidx[q] * act.pitch + g * 8, a[q]);
+    }
+    load8(dpool.ptr + ((static_cast<long>(n) * Ho + yo) * Wo + xo) * dpool.pitch + g * 8, dp);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = a[0][j];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (a[q][j] > bv) {
+          bv = a[q][j];
+          best = q;
+        }
+      arg[j] = best;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float o[8];
+      if (dskip.ptr != nullptr)
+        load8(dskip.ptr + pidx[q] * dskip.pitch + g * 8, o);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += (arg[j] == q) ? dp[j] : 0.f;
+      store8(dact.ptr + pidx[q] * dact.pitch + g * 8, o);
+    }
+  }
+}
+
+// ============================================================================ first conv weight gradient
+// dW[co][ci][tap] = sum_p dRaw[p][co] * x[p + tap][ci]   (fp32 NCHW input, Cin = #frequencies)
+template <int CIN>
+__global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const float* __restrict__ x, View draw, int NB, int H,
+                                                               int W, float* partials) {
+  constexpr int K = CIN * 9;
+  constexpr int KPT = (K + 3) / 4;  // k's per thread (4 thread groups of 64 output channels)
+  __shared__ float s_x[CIN][TILE_H + 2][TILE_W + 2];
+  __shared__ __align__(16) bf16 s_d[TILE_M][72];
+  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  int off[KPT];
+  bool kvalid[KPT];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const int k = kg * KPT + j;
+    kvalid[j] = k < K;
+    const int kk = kvalid[j] ? k : 0;
+    const int ci = kk / 9, tap = kk % 9;
+    off[j] = (ci * (TILE_H + 2) + tap / 3) * (TILE_W + 2) + tap % 3;
+  }
+  float acc[KPT];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) acc[j] = 0.f;
+  const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
+  const int total = NB * tiles_x * tiles_y;
+  const float* sx = &s_x[0][0][0];
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int img = t / tiles_y;
+    const int y0 = ty * TILE_H, x0 = tx * TILE_W;
+    for (int i = threadIdx.x; i < CIN * (TILE_H + 2) * (TILE_W + 2); i += 256) {
+      const int xx = i % (TILE_W + 2), yy = (i / (TILE_W + 2)) % (TILE_H + 2), ci = i / ((TILE_W + 2) * (TILE_H + 2));
+      const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+      (&s_x[0][0][0])[i] =
+          (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(&x[((static_cast<long>(img) * CIN + ci) * H + gy) * W + gx]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < TILE_M * 8; i += 256) {
+      const int pix = i >> 3, g = i & 7;
+      const int gy = y0 + (pix >> 4), gx = x0 + (pix & 15);
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (gy < H && gx < W)
+        u = *reinterpret_cast<const uint4*>(draw.ptr + ((static_cast<long>(img) * H + gy) * W + gx) * draw.pitch + g * 8);
+      *reinterpret_cast<uint4*>(&s_d[pix][g * 8]) = u;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int pix = 0; pix < TILE_M; ++pix) {
+      const float d = __bfloat162float(s_d[pix][co]);
+      const int pb = (pix >> 4) * (TILE_W + 2) + (pix & 15);
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) acc[j] = fmaf(d, sx[pb + off[j]], acc[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < KPT; ++j)
+    if (kvalid[j]) partials[static_cast<long>(blockIdx.x) * 64 * K + co * K + kg * KPT + j] = acc[j];
+}
+
+// ============================================================================ weight packing (fp32 params -> bf16 GEMM operands)
+// conv (Cout,Cin,3,3) -> fwd [Cout][tap][Cin] and bwd-data [Cin][8-tap][Cout]
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* fwd, bf16* bwd) {
+  const long total = static_cast<long>(Cout) * Cin * 9;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    // i indexes the fwd layout (ci fastest) so the bf16 writes of the forward operand are coalesced
+    const int ci = static_cast<int>(i % Cin);
+    const int tap = static_cast<int>((i / Cin) % 9);
+    const int co = static_cast<int>(i / (static_cast<long>(Cin) * 9));
+    const bf16 v = __float2bfloat16(w[(static_cast<long>(co) * Cin + ci) * 9 + tap]);
+    if (fwd) fwd[i] = v;
+    if (bwd) bwd[(static_cast<long>(ci) * 9 + (8 - tap)) * Cout + co] = v;
+  }
+}
+// convT (Cin,Cout,2,2) -> fwd [(kk*Cout+co)][Cin] and bwd-data [Cin][(kk*Cout+co)]
+__global__ void pack_convt_kernel(const float* __restrict__ w, int Cin, int Cout, bf16* fwd, bf16* bwd) {
+  const long total = static_cast<long>(Cin) * Cout * 4;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int co = static_cast<int>((i / Cin) % Cout);
+    const int kk = static_cast<int>(i / (static_cast<long>(Cin) * Cout));
+    const bf16 v = __float2bfloat16(w[(static_cast<long>(ci) * Cout + co) * 4 + kk]);
+    if (fwd) fwd[i] = v;
+    if (bwd) bwd[static_cast<long>(ci) * 4 * Cout + kk * Cout + co] = v;
+  }
+}
+
+inline int grid_for(long work_items, int threads) {
+  long b = (work_items + threads - 1) / threads;
+  if (b > kMaxBlocks) b = kMaxBlocks;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------- launchers (used by net_api.cu / ops_api2.cu)
+cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
+                              int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st) {
+  const int tiles = NB * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
+  const int grid = tiles < 148 * 16 ? tiles : 148 * 16;
+#define FC(C)                                                                                                   \
+  if (cin == C) {                                                                                               \
+    first_conv_kernel<C><<<grid, 128, 0, st>>>(x, w, scale, shift, relu, NB, H, W, out, out_pitch, stats);      \
+    return cudaGetLastError();                                                                                  \
+  }
+  FC(1) FC(2) FC(3) FC(4) FC(5) FC(6) FC(7) FC(8)
+#undef FC
+  return cudaErrorInvalidValue;
+}
+
+int first_conv_wgrad_blocks() { return 148 * 2; }
+cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
+                                    cudaStream_t st) {
+  const int tiles = draw.N * ((draw.H + TILE_H - 1) / TILE_H) * ((draw.W + TILE_W - 1) / TILE_W);
+  const int grid = tiles < first_conv_wgrad_blocks() ? tiles : first_conv_wgrad_blocks();
+#define FW(C)                                                                                       \
+  if (cin == C) {                                                                                   \
+    first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
+    colsum_finalize_kernel<<<(64 * C * 9 + 255) / 256, 256, 0, st>>>(partials, grid, 64 * C * 9, dw, accumulate); \
+    return cudaGetLastError();                                                                      \
+  }
+  FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
+#undef FW
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double count, const float* gamma,
+                               const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                               float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(partials, m_tiles, C, count, gamma, beta, rm, rv, nbt, momentum,
+                                                    eps, scale, shift, save_mean, save_invstd);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                const float* conv_bias, float eps, int C, float* scale, float* shift,
+                                cudaStream_t st) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, conv_bias, eps, C, scale, shift);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, cudaStream_t st) {
+  if (pool.ptr != nullptr) {
+    const long items = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2) * (raw.C / 8);
+    bn_apply_kernel<true><<<grid_for(items, 256), 256, 0, st>>>(raw, scale, shift, act, pool);
+  } else {
+    const long items = static_cast<long>(raw.N) * raw.H * raw.W * (raw.C / 8);
+    bn_apply_kernel<false><<<grid_for(items, 256), 256, 0, st>>>(raw, scale, shift, act, pool);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_head_fwd(View act, const float* hw, const float* hb, int ncls, float* logits, cudaStream_t st) {
+  const long px = static_cast<long>(act.N) * act.H * act.W;
+  head_fwd_kernel<<<grid_for(px, 128), 128, 0, st>>>(act, hw, hb, ncls, logits);
+  return cudaGetLastError();
+}
+int ce_blocks() { return 148 * 4; }
+cudaError_t launch_ce(const float* logits, const long long* labels, const float* cw, int ncls, int NB, long HW,
+                      long long ignore_index, float* dlogits, double* partials, float* out3, cudaStream_t st) {
+  const long total = NB * HW;
+  int blocks = grid_for(total, 256);
+  if (blocks > ce_blocks()) blocks = ce_blocks();
+  ce_fwd_bwd_kernel<<<blocks, 256, 0, st>>>(logits, labels, cw, ncls, HW, total, ignore_index, dlogits, partials);
+  ce_finalize_kernel<<<1, 1, 0, st>>>(partials, blocks, out3);
+  return cudaGetLastError();
+}
+int head_bwd_blocks() { return 148 * 4; }
+cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act, const float* hw, int ncls, View dact,
+                            float* partials, float* dw, float* db, int accumulate, cudaStream_t st) {
+  const long px = static_cast<long>(act.N) * act.H * act.W;
+  int blocks = grid_for(px, 128);
+  if (blocks > head_bwd_blocks()) blocks = head_bwd_blocks();
+  head_bwd_kernel<<<blocks, 128, 0, st>>>(dlogits, gscale, act, hw, ncls, dact, partials);
+  const int per = ncls * 64 + ncls;
+  head_bwd_finalize_kernel<<<(per + 127) / 128, 128, 0, st>>>(partials, blocks * 2, ncls, dw, db, accumulate);
+  return cudaGetLastError();
+}
+
+int reduce_blocks() { return 148 * 4; }
+static int reduce_grid(const View& v) {
+  const int ppb = 256 / (v.C / 8);
+  const long px = static_cast<long>(v.N) * v.H * v.W;
+  long b = (px + ppb - 1) / ppb;
+  if (b > reduce_blocks()) b = reduce_blocks();
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+// BN+ReLU backward: dact (grad wrt post-ReLU activation) -> draw (grad wrt conv output), dgamma/dbeta/dbias.
+// scratch: partials, at least reduce_blocks()*2*C floats; c1c2: 2*C floats.
+cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
+                          float* partials, float* c1c2, cudaStream_t st) {
+  const int C = raw.C;
+  if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
+  const int grid = reduce_grid(raw);
+  const int ppb = 256 / (C / 8);
+  const double count = static_cast<double>(raw.N) * raw.H * raw.W;
+  bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, partials);
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, grid, C, count, dgamma, dbeta, accumulate, c1c2,
+                                                          c1c2 + C);
+  bn_bwd_apply_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C,
+                                                                  draw, partials);
+  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, grid, C, dbias, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
+  const int C = v.C;
+  if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
+  const int grid = reduce_grid(v);
+  const int ppb = 256 / (C / 8);
+  view_colsum_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(v, partials);
+  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, grid, C, out, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st) {
+  const long items = static_cast<long>(act.N) * (act.H / 2) * (act.W / 2) * (act.C / 8);
+  pool_bwd_add_kernel<<<grid_for(items, 256), 256, 0, st>>>(act, dpool, dskip, dact);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_conv3x3(const float* w, int Cout, int Cin, bf16* fwd, bf16* bwd, cudaStream_t st) {
+  pack_conv3x3_kernel<<<grid_for(static_cast<long>(Cout) * Cin * 9, 256), 256, 0, st>>>(w, Cout, Cin, fwd, bwd);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_convt(const float* w, int Cin, int Cout, bf16* fwd, bf16* bwd, cudaStream_t st) {
+  pack_convt_kernel<<<grid_for(static_cast<long>(Cin) * Cout * 4, 256), 256, 0, st>>>(w, Cin, Cout, fwd, bwd);
+  return cudaGetLastError();
+}

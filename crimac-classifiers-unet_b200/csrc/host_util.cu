@@ -1,0 +1,83 @@
+#include "host_util.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+static thread_local std::string g_last_error;
+void crimac_set_error(const std::string& msg) { g_last_error = msg; }
+extern "C" const char* crimac_last_error() { return g_last_error.c_str(); }
+
+// cuTensorMapEncodeTiled is a driver-API entry point; resolve it through the runtime so the library has no
+// link-time dependency on libcuda.so (and loads, without computing, on a GPU-less host).
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+  });
+  return fn;
+}
+
+int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, int kx) {
+  auto enc = get_encode();
+  CRIMAC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  CRIMAC_REQUIRE(v.C % 8 == 0 && v.pitch % 8 == 0, "channel count / pitch must be multiples of 8");
+  CRIMAC_REQUIRE((reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, "activation pointer must be 16-byte aligned");
+  const cuuint64_t es = 2;
+  bf16* base = v.ptr;
+  cuuint64_t W = v.W, H = v.H;
+  cuuint64_t sx = static_cast<cuuint64_t>(v.pitch) * es;
+  cuuint64_t sy = static_cast<cuuint64_t>(v.W) * v.pitch * es;
+  const cuuint64_t sn = static_cast<cuuint64_t>(v.H) * v.W * v.pitch * es;
+  if (sub) {
+    base = v.ptr + (static_cast<size_t>(ky) * v.W + kx) * v.pitch;
+    W = v.W / 2;
+    H = v.H / 2;
+    sx *= 2;
+    sy *= 2;
+  }
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(v.C), W, H, static_cast<cuuint64_t>(v.N)};
+  cuuint64_t strides[3] = {sx, sy, sn};
+  cuuint32_t box[4] = {64, 16, static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    crimac_set_error("cuTensorMapEncodeTiled(activation) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 2;
+  }
+  return 0;
+}
+
+int make_weight_map(CUtensorMap* out, const bf16* w, int rows, int cols, int box_rows) {
+  auto enc = get_encode();
+  CRIMAC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  CRIMAC_REQUIRE(cols % 64 == 0, "packed weight K must be a multiple of 64");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    crimac_set_error("cuTensorMapEncodeTiled(weights) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 2;
+  }
+  return 0;
+}
+
+int device_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}

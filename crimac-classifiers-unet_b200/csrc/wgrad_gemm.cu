@@ -1,0 +1,227 @@
+// Weight-gradient GEMM for the echogram U-Net on sm_100a (autograd of reference models/unet.py:35-49,
+// i.e. what loss.backward() at pipeline_train_predict/pipeline.py:177 computes for every conv weight):
+//
+//     dW[m][n][tap] = sum over pixels p of  F[p][m] * T_tap[p][n]
+//
+//   3x3 conv      : F = dY (m = Cout),  T_tap = X shifted by (ky-1,kx-1) with zero fill (n = Cin), 9 taps
+//   ConvTranspose : F = X  (m = Cin),   T_tap = dY sub-sampled at (2y+ky, 2x+kx)        (n = Cout), 4 taps
+//
+// The reduction dimension (pixels) is the slow dimension of both NHWC operands, so both are fed to
+// tcgen05.mma as MN-major SWIZZLE_128B tiles: a k-step is a 4x16-pixel TMA box {64 ch, 16, 4, 1}
+// per 64-channel block, 64 k-rows of 128 bytes.  One CTA owns one (m-tile, n-tile, tap) output tile over one
+// split of the pixel range; partial tiles are accumulated with vectorised red.global.add.f32 into a
+// [tap][m][n] fp32 scratch which a small kernel then permutes into PyTorch's (m, n, kh, kw) layout.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int WG_KPIX = 64;                  // pixels per k-step
+constexpr int WG_BOX_BYTES = WG_KPIX * 128;  // one {64ch x 64px} box
+
+template <int BLOCK_N>
+struct WgCfg {
+  static constexpr int A_BYTES = 2 * WG_BOX_BYTES;  // 128 m-channels
+  static constexpr int B_BYTES = (BLOCK_N / 64) * WG_BOX_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* acc_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile decode: blockIdx.x -> (tap, m_tile, n_tile); blockIdx.y -> split of the pixel range
+  int t = blockIdx.x;
+  const int n_tile = t % p.n_tiles;
+  t /= p.n_tiles;
+  const int m_tile = t % p.m_tiles;
+  const int tap = t / p.m_tiles;
+  const int split = blockIdx.y;
+  const int kt_per = (p.k_tiles_total + p.splits - 1) / p.splits;
+  const int kt_begin = split * kt_per;
+  const int kt_end = min(p.k_tiles_total, kt_begin + kt_per);
+  const int ksteps = kt_end - kt_begin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.a_map);
+    ptx::prefetch_tmap(&p.b_map[p.tap_mode ? tap : 0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(acc_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (ksteps > 0) {
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      int dy = 0, dx = 0, mi = 0;
+      if (p.tap_mode == 0) {
+        if (p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+      } else {
+        mi = tap;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        int u = kt;
+        const int tx = u % p.tiles_x;
+        u /= p.tiles_x;
+        const int ty = u % p.tiles_y;
+        const int img = u / p.tiles_y;
+        const int x0 = tx * 16, y0 = ty * 4;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+          ptx::tma_load_4d(sa + b * WG_BOX_BYTES, &p.a_map, &full_bar[stage], m_tile * 128 + b * 64, x0, y0, img);
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b)
+          ptx::tma_load_4d(sb + b * WG_BOX_BYTES, &p.b_map[mi], &full_bar[stage], n_tile * BLOCK_N + b * 64, x0 + dx,
+                           y0 + dy, img);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        // MN-major SW128: LBO = byte distance between 64-channel boxes, SBO = 1024 (8 k-rows of 128 B)
+        const uint64_t adesc = ptx::make_smem_desc(sa, WG_BOX_BYTES, 1024);
+        const uint64_t bdesc = ptx::make_smem_desc(sa + Cfg::A_BYTES, WG_BOX_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < WG_KPIX / 16; ++k) {
+          // 16 pixels further along K = 16 rows * 128 B = 2048 B: start-address field += 128
+          ptx::umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (ks | k) != 0);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      ptx::umma_commit(acc_bar);
+    } else if (warp >= 4) {
+      // ===================== epilogue: TMEM -> red.add into [tap][m][n] scratch =====================
+      const int q = warp & 3;
+      const int m = m_tile * 128 + q * 32 + lane;
+      ptx::mbar_wait(acc_bar, 0);
+      ptx::tc_fence_after();
+      float* row = p.dw + (static_cast<long>(tap) * p.M_total + m) * p.N_total + n_tile * BLOCK_N;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, v);
+        ptx::tmem_ld_wait();
+        if (m < p.M_total) {
+          if (p.splits == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(row + chunk * 32 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                              __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(row + chunk * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                         __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// scratch [taps][M][N] fp32 -> PyTorch layout [M][N][taps] (conv: (Cout,Cin,3,3); convT: (Cin,Cout,2,2))
+__global__ void wgrad_unpack_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int M, int N, int taps,
+                                    int accumulate) {
+  const long total = static_cast<long>(M) * N;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    for (int tp = 0; tp < taps; ++tp) {
+      const float g = scratch[tp * total + i];
+      float* d = dw + i * taps + tp;
+      *d = accumulate ? (*d + g) : g;
+    }
+  }
+}
+
+template <int BLOCK_N>
+cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgCfg<BLOCK_N>;
+  auto kern = wgrad_gemm_kernel<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(p.taps * p.m_tiles * p.n_tiles, p.splits);
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream) {
+  if (block_n == 64) return launch_wg<64>(p, stream);
+  if (block_n == 128) return launch_wg<128>(p, stream);
+  if (block_n == 256) return launch_wg<256>(p, stream);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,
+                                cudaStream_t stream) {
+  const long total = static_cast<long>(M) * N;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  wgrad_unpack_kernel<<<blocks, 256, 0, stream>>>(scratch, dw, M, N, taps, accumulate);
+  return cudaGetLastError();
+}
