@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Headline benchmark: U-Net 256^2 patches/s, training fwd + class-weighted CE + bwd (+ NCCL gradient all-reduce and
+SGD step), batch 32 of 4x256x256 synthetic echogram patches per B200 (BASELINE.json configs[1] / configs[2]).
+
+  python bench.py --gpus 1 --steps K --warmup W                # this repo's sm_100a path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                         # the reference's PyTorch CPU path (oracle port), host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_TRAIN = 288.979156992   # per 4x256x256 patch, fwd+bwd (SURVEY.md §8d / BASELINE.md)
+GFLOP_INFER = 96.42704896
+METRIC = "U-Net 256x256 patches/s, train fwd+bwd (class-weighted CE), batch 32 per B200"
+WORKLOAD = "configs[1]: UNet(4 freq -> 3 classes) training fwd+bwd, class-weighted CE, batch 32 of 4x256x256 synthetic patches per GPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event breakdown of one step here")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_burst": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_train_patches_per_s(batch, reps, warm=1):
+    """Times the oracle port of the reference train step (fwd + weighted CE + bwd, fp32, torch CPU, all host cores)."""
+    import torch
+    from oracle import unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sys.path.insert(0, os.path.join(ROOT, "crimac-classifiers-unet_b200"))
+    import models.unet as M
+    state = {k: v.clone() for k, v in M.UNet_Baseline(3, 4).state_dict().items()}
+    x = O.synthetic_echogram(batch, 4, 256, 256, seed=0)
+    y = O.synthetic_labels(batch, 256, 256, seed=1)
+    for _ in range(warm):
+        O.train_step(state, x, y)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.train_step(state, x, y)
+    dt = (time.perf_counter() - t0) / reps
+    return batch / dt, cores, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: 2 patches per step (the full batch of 32 takes ~40 s per step on 8 cores)
+    sample_batch = 2
+    pps, cores, dt = cpu_train_patches_per_s(sample_batch, args.steps, warm=max(1, min(args.warmup, 2)))
+    sample = f"{sample_batch} of the {args.batch} patches of a batch per step (fp32 torch CPU, {cores} threads), oracle port of the reference train step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": pps, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    from oracle import unet_oracle as O   # synthetic workload generators only (and the cpu_baseline leg below)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the U-Net hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    load_package()
+    import crimac_unet_b200.engine as E
+    import crimac_unet_b200.models.unet as M
+    from crimac_unet_b200.trainer import Trainer
+
+    B = args.batch
+    torch.manual_seed(0)
+    model = M.UNet_Baseline(3, 4).to(dev)
+    x = O.synthetic_echogram(B, 4, 256, 256, seed=100 + rank, device=dev)
+    y = O.synthetic_labels(B, 256, 256, seed=200 + rank, device=dev)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.mode == "train":
+        model.train()
+        trainer = Trainer(model, lr=0.005, momentum=0.95)
+        trainer.broadcast_parameters(0)
+        step = lambda xx, yy: trainer.step(xx, yy)
+        gflop = GFLOP_TRAIN
+    else:
+        model.eval()
+        step = lambda xx, yy: model.predict_proba(xx)
+        gflop = GFLOP_INFER
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(x, y)
+        # ---- device-resident timing (value)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = E.launch_count()
+        ms_total = timed(lambda: step(x, y), args.steps)
+        launches = E.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step * 1e-3)
+
+        # ---- end to end through the module API with host buffers
+        xh = x.cpu().pin_memory()
+        yh = y.cpu().pin_memory()
+        xd, yd = torch.empty_like(x), torch.empty_like(y)
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            yd.copy_(yh, non_blocking=True)
+            out = step(xd, yd)
+            if args.mode == "train":
+                return out.item()                    # D2H read of the loss, as pipeline.py:181
+            return out[:, 1:, :, :].half().cpu()     # D2H of the two class probabilities the stitcher keeps
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps) / args.steps
+        h2d = xh.numel() * 4 + (yh.numel() * 8 if args.mode == "train" else 0)
+        d2h = 4 if args.mode == "train" else B * 2 * 256 * 256 * 2
+        e2e_value = world * B / (ms_e2e * 1e-3)
+
+        # ---- per-kernel breakdown of one more step (CUDA events around every launch, on the launching stream)
+        torch.cuda.synchronize()
+        E.profile_enable(True)
+        step(x, y)
+        recs = E.profile_read()
+        E.profile_enable(False)
+
+    fam = {}
+    for name, ms, fl, by, ln in recs:
+        key = "conv_igemm_kernel (tcgen05 implicit GEMM: 3x3 fwd/dgrad, convT fwd/dgrad)" if name.startswith(("conv3x3", "convT_fwd", "convT_dgrad")) else name
+        a = fam.setdefault(key, [0.0, 0.0, 0.0, 0])
+        a[0] += ms
+        a[1] += fl
+        a[2] += by
+        a[3] += ln
+    step_kernel_ms = sum(a[0] for a in fam.values())
+    peaks = measured_peaks()
+    dom_name, dom = max(((k, a) for k, a in fam.items() if a[1] > 0), key=lambda kv: kv[1][0])
+    achieved = dom[1] / (dom[0] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["tflops_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "launches_per_step": dom[3], "ms_per_step_in_kernel": dom[0], "share_of_step": dom[0] / step_kernel_ms,
+                "whole_step_tflops": value / world * gflop / 1e3, "whole_step_frac_of_burst_peak": value / world * gflop / 1e3 / peaks["tflops_burst"]}
+    if args.profile_out and rank == 0:
+        with open(args.profile_out, "w") as f:
+            f.write(f"# per-kernel CUDA-event breakdown of one {args.mode} step, batch {B}, 1 GPU; kernel ms sum {step_kernel_ms:.3f}\n")
+            f.write("family,ms,share,TFLOP/s,GB/s,launches\n")
+            for k, a in sorted(fam.items(), key=lambda kv: -kv[1][0]):
+                f.write(f"\"{k}\",{a[0]:.4f},{a[0] / step_kernel_ms:.4f},{a[1] / max(a[0], 1e-9) / 1e9:.1f},{a[2] / max(a[0], 1e-9) / 1e6:.1f},{a[3]}\n")
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pps, cores, dt = cpu_train_patches_per_s(4, reps=2, warm=1)
+        cpu_baseline = {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port",
+                        "sample": f"oracle port of the reference train step, fp32 torch CPU, batch 4 (of 32), 1 warm-up + 2 timed steps, {dt:.2f} s/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC if args.mode == "train" else "U-Net 256x256 patches/s, inference (softmax probabilities)",
+            "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (fp32 accumulate; first conv, BN statistics, head, loss in fp32)", "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.mode == "train" else "UNet inference, batch %d of 4x256x256" % B,
+                       "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single GPU",
+                       "step": "weight re-pack + forward + weighted CE + backward" + (" + NCCL all-reduce of the 124 MB gradient arena" if world > 1 else "") + " + fused SGD-momentum update" if args.mode == "train" else "forward + softmax",
+                       "l2": "per-step working set (activations + gradients) is ~6 GB >> 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e, "api": "UNet_Baseline.train_step_fused via Trainer.step; pinned host -> device copy of x (fp32) and labels (int64) and loss.item() each step" if args.mode == "train" else "UNet_Baseline.predict_proba; pinned host -> device copy of x, fp16 class-1/2 probabilities back to host"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

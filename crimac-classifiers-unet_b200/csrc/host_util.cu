@@ -81,3 +81,67 @@ int device_num_sms() {
   }
   return n;
 }
+
+// ------------------------------------------------------------------------------------------------ profiler
+#include <vector>
+namespace {
+struct ProfRec {
+  const char* name;
+  double flops, bytes;
+  int launches;
+  cudaEvent_t e0, e1;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+unsigned long long g_launches = 0;
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(const char* name, double flops, double bytes, cudaStream_t st, int launches) : st_(st), slot_(-1) {
+  g_launches += launches;
+  if (!g_prof_on) return;
+  ProfRec r{name, flops, bytes, launches, take_event(), take_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  slot_ = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot_ >= 0) cudaEventRecord(g_prof[slot_].e1, st_);
+}
+
+extern "C" unsigned long long crimac_launch_count() { return g_launches; }
+extern "C" int crimac_profile_enable(int on) {
+  for (ProfRec& r : g_prof) {
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return 0;
+}
+// Synchronises the device, then copies up to `cap` records out: names (pointers to static strings), milliseconds,
+// algorithmic flops and bytes per record.  Returns the number of records available.
+extern "C" int crimac_profile_read(const char** names, float* ms, double* flops, double* bytes, int* launches, int cap) {
+  cudaDeviceSynchronize();
+  const int n = static_cast<int>(g_prof.size());
+  for (int i = 0; i < n && i < cap; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_prof[i].e0, g_prof[i].e1);
+    if (names) names[i] = g_prof[i].name;
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = g_prof[i].flops;
+    if (bytes) bytes[i] = g_prof[i].bytes;
+    if (launches) launches[i] = g_prof[i].launches;
+  }
+  return n;
+}

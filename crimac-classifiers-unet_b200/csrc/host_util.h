@@ -36,3 +36,41 @@ cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, i
                                 cudaStream_t stream);
 
 int device_num_sms();
+
+// ---- launch accounting + optional per-launch CUDA-event timing (crimac_profile_* in the C-ABI).
+// Every kernel launch of the network-level entry points goes through a Scope: it always counts the launch and, when
+// profiling is enabled, brackets it with cudaEvents on the launching stream (read back by crimac_profile_read).
+struct ProfScope {
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t st, int launches = 1);
+  ~ProfScope();
+  cudaStream_t st_;
+  int slot_;
+};
+
+// ---- CUDA-core kernels (elementwise.cu)
+cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
+                              int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st);
+int first_conv_wgrad_blocks();
+cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
+                                    cudaStream_t st);
+cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double count, const float* gamma,
+                               const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
+                               float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                const float* conv_bias, float eps, int C, float* scale, float* shift, cudaStream_t st);
+cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, cudaStream_t st);
+cudaError_t launch_head_fwd(View act, const float* hw, const float* hb, int ncls, float* logits, cudaStream_t st);
+int ce_blocks();
+cudaError_t launch_ce(const float* logits, const long long* labels, const float* cw, int ncls, int NB, long HW,
+                      long long ignore_index, float* dlogits, double* partials, float* out3, cudaStream_t st);
+int head_bwd_blocks();
+cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act, const float* hw, int ncls, View dact,
+                            float* partials, float* dw, float* db, int accumulate, cudaStream_t st);
+int reduce_blocks();
+cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
+                          const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
+                          float* partials, float* c1c2, cudaStream_t st);
+cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st);
+cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st);
+cudaError_t launch_pack_conv3x3(const float* w, int Cout, int Cin, bf16* fwd, bf16* bwd, cudaStream_t st);
+cudaError_t launch_pack_convt(const float* w, int Cin, int Cout, bf16* fwd, bf16* bwd, cudaStream_t st);

@@ -1,0 +1,753 @@
+// Network-level C-ABI: the whole UNet_Baseline forward (eval / train) and backward as a fixed sequence of kernel
+// launches on the caller's stream.  Mirrors reference models/unet.py:200-343 (topology), pipeline.py:135-138,176-177
+// (loss, backward).  The context owns only sub-allocations of the caller's workspace plus host-side launch
+// descriptors (TMA tensor maps are encoded once here, not per call).
+//
+// Data layout in HBM (all activations NHWC bf16, [patch][range row][ping][channel]):
+//   level l has C_l = 64*2^l channels at (H>>l) x (W>>l).
+//   Cat_j  (decoder block j, level l = depth-2-j): ONE buffer of 2*C_l channels; ConvTranspose2d scatters into
+//          channels [0,C_l), the encoder's second conv of level l writes its activation into [C_l,2*C_l) — torch.cat
+//          (unet.py:132) never happens as a copy.
+//   train mode additionally keeps every conv's raw (pre-BN) output for the BN/ReLU backward.
+#include "host_util.h"
+#include "../../include/crimac_b200.h"
+#include <vector>
+#include <new>
+
+namespace {
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~static_cast<size_t>(1023);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  template <typename T>
+  T* arr(size_t n) {
+    return static_cast<T*>(take(n * sizeof(T)));
+  }
+};
+
+struct Conv3 {
+  int cin = 0, cout = 0, level = 0;
+  bool first = false;
+  int s_w = 0, s_b = 0, s_g = 0, s_beta = 0, s_rm = 0, s_rv = 0, s_nbt = 0;
+  int g_w = 0, g_b = 0, g_g = 0, g_beta = 0;
+  View in{}, raw{}, act{}, pool{}, gin{};
+  bf16 *w_fwd = nullptr, *w_bwd = nullptr;
+  float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
+  int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
+  ConvParams fwd{}, dgrad{};
+  WgradParams wg{};
+};
+struct ConvT {
+  int cin = 0, cout = 0, level_in = 0;
+  int s_w = 0, s_b = 0, g_w = 0, g_b = 0;
+  View in{}, out{}, gout{}, gin{};
+  bf16 *w_fwd = nullptr, *w_bwd = nullptr;
+  int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
+  ConvParams fwd{}, dgrad{};
+  WgradParams wg{};
+};
+
+int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+
+}  // namespace
+
+struct crimac_ctx {
+  crimac_config cfg{};
+  int device = 0;
+  int D = 0;
+  std::vector<Conv3> conv;  // enc c1,c2 per level, then dec c1,c2 per block (forward order is built separately)
+  std::vector<ConvT> up;
+  std::vector<int> enc1, enc2, dec1, dec2;  // indices into conv
+  int s_head_w = 0, s_head_b = 0, g_head_w = 0, g_head_b = 0;
+  // shared scratch
+  bf16 *GA = nullptr, *GR = nullptr, *GP = nullptr;
+  std::vector<bf16*> dcat;
+  float* stats = nullptr;
+  float* red_partials = nullptr;
+  float* c1c2 = nullptr;
+  float* wg_scratch = nullptr;
+  float* head_partials = nullptr;
+  float* fc_partials = nullptr;
+  double* ce_partials = nullptr;
+  float* logits = nullptr;   // internal logits / dlogits for the fused train step
+  float* dlogits = nullptr;
+  float* loss3 = nullptr;
+  ConvParams head_fused{};   // last conv with the 1x1 head in its epilogue (eval)
+  int prepared_mode = -1;
+};
+
+namespace {
+
+int level_h(const crimac_ctx* c, int l) { return c->cfg.height >> l; }
+int level_w(const crimac_ctx* c, int l) { return c->cfg.width >> l; }
+
+int validate(const crimac_config* cfg) {
+  CRIMAC_REQUIRE(cfg != nullptr, "cfg is NULL");
+  CRIMAC_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 8, "in_channels must be 1..8");
+  CRIMAC_REQUIRE(cfg->n_classes >= 1 && cfg->n_classes <= CRIMAC_MAX_CLASSES, "n_classes must be 1..8");
+  CRIMAC_REQUIRE(cfg->depth >= 2 && cfg->depth <= 5, "depth must be 2..5");
+  CRIMAC_REQUIRE(cfg->start_filts == 64, "start_filts must be 64 (tensor-core tiles are 64 channels wide)");
+  CRIMAC_REQUIRE(cfg->max_batch >= 1, "max_batch");
+  const int m = 1 << (cfg->depth - 1);
+  CRIMAC_REQUIRE(cfg->height > 0 && cfg->width > 0 && cfg->height % m == 0 && cfg->width % m == 0,
+                 "height/width must be multiples of 2^(depth-1) (the reference has the same constraint, unet.py:132)");
+  return 0;
+}
+
+// Builds the layer graph.  With ws == nullptr only sizes are computed (crimac_workspace_bytes).
+int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
+  const crimac_config& cfg = c->cfg;
+  const int D = c->D = cfg.depth;
+  const int B = cfg.max_batch;
+  const bool train = cfg.train != 0;
+  Bump bump(ws);
+  auto chan = [&](int l) { return cfg.start_filts << l; };
+  auto dense = [&](int l, int C) {
+    View v{bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * C), B, level_h(c, l), level_w(c, l), C,
+           C};
+    return v;
+  };
+  auto slice = [&](const View& v, int c0, int C) {
+    View s = v;
+    s.ptr = v.ptr ? v.ptr + c0 : nullptr;
+    s.C = C;
+    return s;
+  };
+
+  // ---- activations
+  std::vector<View> cat(D - 1), pooled(D - 1);
+  for (int j = 0; j < D - 1; ++j) cat[j] = dense(D - 2 - j, 2 * chan(D - 2 - j));
+  for (int l = 0; l < D - 1; ++l) pooled[l] = dense(l + 1, chan(l));
+
+  c->conv.clear();
+  c->up.clear();
+  c->enc1.clear();
+  c->enc2.clear();
+  c->dec1.clear();
+  c->dec2.clear();
+  int s_idx = 0, g_idx = 0;
+  auto new_conv = [&](int cin, int cout, int level) {
+    Conv3 L;
+    L.cin = cin;
+    L.cout = cout;
+    L.level = level;
+    c->conv.push_back(L);
+    return static_cast<int>(c->conv.size()) - 1;
+  };
+  // state/grad indices follow state_dict()/parameters() order
+  for (int l = 0; l < D; ++l) {
+    const int cin = l == 0 ? cfg.in_channels : chan(l - 1), co = chan(l);
+    const int i1 = new_conv(cin, co, l);
+    const int i2 = new_conv(co, co, l);
+    c->enc1.push_back(i1);
+    c->enc2.push_back(i2);
+    for (int which = 0; which < 2; ++which) {
+      Conv3& L = c->conv[which == 0 ? i1 : i2];
+      L.s_w = s_idx++;
+      L.s_b = s_idx++;
+      L.s_g = s_idx++;
+      L.s_beta = s_idx++;
+      L.s_rm = s_idx++;
+      L.s_rv = s_idx++;
+      L.s_nbt = s_idx++;
+      L.g_w = g_idx++;
+      L.g_b = g_idx++;
+      L.g_g = g_idx++;
+      L.g_beta = g_idx++;
+    }
+    c->conv[i1].first = (l == 0);
+  }
+  for (int j = 0; j < D - 1; ++j) {
+    const int l = D - 2 - j, co = chan(l);
+    ConvT U;
+    U.cin = 2 * co;
+    U.cout = co;
+    U.level_in = l + 1;
+    U.s_w = s_idx++;
+    U.s_b = s_idx++;
+    U.g_w = g_idx++;
+    U.g_b = g_idx++;
+    c->up.push_back(U);
+    const int i1 = new_conv(2 * co, co, l);
+    const int i2 = new_conv(co, co, l);
+    c->dec1.push_back(i1);
+    c->dec2.push_back(i2);
+    Conv3& L1 = c->conv[i1];
+    Conv3& L2 = c->conv[i2];
+    L1.s_w = s_idx++;
+    L1.s_b = s_idx++;
+    L2.s_w = s_idx++;
+    L2.s_b = s_idx++;
+    for (Conv3* L : {&L1, &L2}) {
+      L->s_g = s_idx++;
+      L->s_beta = s_idx++;
+      L->s_rm = s_idx++;
+      L->s_rv = s_idx++;
+      L->s_nbt = s_idx++;
+    }
+    L1.g_w = g_idx++;
+    L1.g_b = g_idx++;
+    L2.g_w = g_idx++;
+    L2.g_b = g_idx++;
+    L1.g_g = g_idx++;
+    L1.g_beta = g_idx++;
+    L2.g_g = g_idx++;
+    L2.g_beta = g_idx++;
+  }
+  c->s_head_w = s_idx++;
+  c->s_head_b = s_idx++;
+  c->g_head_w = g_idx++;
+  c->g_head_b = g_idx++;
+
+  // ---- wire views
+  for (int l = 0; l < D; ++l) {
+    Conv3& L1 = c->conv[c->enc1[l]];
+    Conv3& L2 = c->conv[c->enc2[l]];
+    if (l > 0) L1.in = pooled[l - 1];
+    L1.act = dense(l, chan(l));
+    L2.in = L1.act;
+    if (l < D - 1) {
+      L2.act = slice(cat[D - 2 - l], chan(l), chan(l));
+      L2.pool = pooled[l];
+    } else {
+      L2.act = dense(l, chan(l));
+    }
+  }
+  for (int j = 0; j < D - 1; ++j) {
+    const int l = D - 2 - j;
+    ConvT& U = c->up[j];
+    U.in = (j == 0) ? c->conv[c->enc2[D - 1]].act : c->conv[c->dec2[j - 1]].act;
+    U.out = slice(cat[j], 0, chan(l));
+    Conv3& L1 = c->conv[c->dec1[j]];
+    Conv3& L2 = c->conv[c->dec2[j]];
+    L1.in = cat[j];
+    L1.act = dense(l, chan(l));
+    L2.in = L1.act;
+    L2.act = dense(l, chan(l));
+  }
+  // ---- per-layer parameters-derived buffers
+  size_t max_stats = 0;
+  for (Conv3& L : c->conv) {
+    if (!L.first) {
+      L.w_fwd = bump.arr<bf16>(static_cast<size_t>(L.cout) * 9 * L.cin);
+      if (train) L.w_bwd = bump.arr<bf16>(static_cast<size_t>(L.cout) * 9 * L.cin);
+    }
+    L.scale = bump.arr<float>(L.cout);
+    L.shift = bump.arr<float>(L.cout);
+    L.mean = bump.arr<float>(L.cout);
+    L.invstd = bump.arr<float>(L.cout);
+    if (train) L.raw = dense(L.level, L.cout);
+    const size_t mt = static_cast<size_t>(B) * ((level_h(c, L.level) + TILE_H - 1) / TILE_H) *
+                      ((level_w(c, L.level) + TILE_W - 1) / TILE_W);
+    if (mt * 2 * L.cout > max_stats) max_stats = mt * 2 * L.cout;
+    L.bn_fwd = pick_bn(L.cout);
+    L.bn_bwd = pick_bn(L.cin);
+    L.bn_wg = pick_bn(L.cin);
+  }
+  for (ConvT& U : c->up) {
+    U.w_fwd = bump.arr<bf16>(static_cast<size_t>(U.cin) * U.cout * 4);
+    if (train) U.w_bwd = bump.arr<bf16>(static_cast<size_t>(U.cin) * U.cout * 4);
+    U.bn_fwd = pick_bn(4 * U.cout);
+    U.bn_bwd = pick_bn(U.cin);
+    U.bn_wg = pick_bn(U.cout);
+  }
+  // ---- training scratch
+  c->dcat.assign(D - 1, nullptr);
+  if (train) {
+    const size_t lvl0 = static_cast<size_t>(B) * cfg.height * cfg.width * cfg.start_filts;
+    c->GA = bump.arr<bf16>(lvl0);
+    c->GR = bump.arr<bf16>(lvl0);
+    c->GP = bump.arr<bf16>(lvl0 / 4);
+    for (int j = 0; j < D - 1; ++j) {
+      const int l = D - 2 - j;
+      c->dcat[j] = bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * 2 * chan(l));
+    }
+    const int cmax = chan(D - 1);
+    c->stats = bump.arr<float>(max_stats);
+    c->red_partials = bump.arr<float>(static_cast<size_t>(reduce_blocks()) * 2 * cmax);
+    c->c1c2 = bump.arr<float>(2 * cmax);
+    c->wg_scratch = bump.arr<float>(static_cast<size_t>(9) * cmax * cmax);
+    c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 2 * (cfg.n_classes * 64 + cfg.n_classes));
+    c->fc_partials = bump.arr<float>(static_cast<size_t>(first_conv_wgrad_blocks()) * 64 * cfg.in_channels * 9);
+    c->ce_partials = bump.arr<double>(static_cast<size_t>(ce_blocks()) * 2);
+    const size_t lg = static_cast<size_t>(B) * cfg.n_classes * cfg.height * cfg.width;
+    c->logits = bump.arr<float>(lg);
+    c->dlogits = bump.arr<float>(lg);
+    c->loss3 = bump.arr<float>(4);
+    // gradient destinations of every dgrad
+    for (int l = 0; l < D; ++l) {
+      Conv3& L1 = c->conv[c->enc1[l]];
+      Conv3& L2 = c->conv[c->enc2[l]];
+      if (l > 0) L1.gin = View{c->GP, B, level_h(c, l), level_w(c, l), L1.cin, L1.cin};
+      L2.gin = View{c->GA, B, level_h(c, l), level_w(c, l), L2.cin, L2.cin};
+    }
+    for (int j = 0; j < D - 1; ++j) {
+      const int l = D - 2 - j;
+      Conv3& L1 = c->conv[c->dec1[j]];
+      Conv3& L2 = c->conv[c->dec2[j]];
+      L1.gin = View{c->dcat[j], B, level_h(c, l), level_w(c, l), L1.cin, L1.cin};
+      L2.gin = View{c->GA, B, level_h(c, l), level_w(c, l), L2.cin, L2.cin};
+      ConvT& U = c->up[j];
+      U.gout = View{c->dcat[j], B, level_h(c, l), level_w(c, l), U.cout, 2 * U.cout};
+      U.gin = View{c->GA, B, level_h(c, l + 1), level_w(c, l + 1), U.cin, U.cin};
+    }
+  } else {
+    c->stats = nullptr;
+  }
+  if (bytes_out) *bytes_out = bump.off + 1024;
+  if (!encode_maps) return 0;
+
+  // ---- launch descriptors (tensor maps encoded once)
+  auto geom = [&](ConvParams& p, int H, int W, int n_total, int bn) {
+    p.H = H;
+    p.W = W;
+    p.tiles_x = (W + TILE_W - 1) / TILE_W;
+    p.tiles_y = (H + TILE_H - 1) / TILE_H;
+    p.n_tiles = n_total / bn;
+  };
+  auto wgeom = [&](WgradParams& p, int H, int W, int m_total, int n_total, int bn, int taps, int tap_mode) {
+    p.taps = taps;
+    p.tap_mode = tap_mode;
+    p.M_total = m_total;
+    p.N_total = n_total;
+    p.H = H;
+    p.W = W;
+    p.tiles_x = (W + 15) / 16;
+    p.tiles_y = (H + 3) / 4;
+    p.m_tiles = (m_total + 127) / 128;
+    p.n_tiles = n_total / bn;
+    p.dw = c->wg_scratch;
+  };
+  int rc;
+  for (Conv3& L : c->conv) {
+    const int H = level_h(c, L.level), W = level_w(c, L.level);
+    if (!L.first) {
+      ConvParams& p = L.fwd;
+      p.taps = 9;
+      p.tap_mode = 0;
+      p.cin = L.cin;
+      geom(p, H, W, L.cout, L.bn_fwd);
+      if ((rc = make_act_map(&p.a_map[0], L.in, TILE_H))) return rc;
+      if ((rc = make_weight_map(&p.b_map, L.w_fwd, L.cout, 9 * L.cin, L.bn_fwd))) return rc;
+    }
+    if (train) {
+      View gr{c->GR, B, H, W, L.cout, L.cout};
+      if (!L.first) {
+        ConvParams& p = L.dgrad;
+        p.taps = 9;
+        p.tap_mode = 0;
+        p.cin = L.cout;
+        geom(p, H, W, L.cin, L.bn_bwd);
+        if ((rc = make_act_map(&p.a_map[0], gr, TILE_H))) return rc;
+        if ((rc = make_weight_map(&p.b_map, L.w_bwd, L.cin, 9 * L.cout, L.bn_bwd))) return rc;
+        p.out = L.gin.ptr;
+        p.out_pitch = L.gin.pitch;
+        WgradParams& w = L.wg;
+        wgeom(w, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
+        if ((rc = make_act_map(&w.a_map, gr, 4))) return rc;
+        if ((rc = make_act_map(&w.b_map[0], L.in, 4))) return rc;
+      }
+    }
+  }
+  for (size_t j = 0; j < c->up.size(); ++j) {
+    ConvT& U = c->up[j];
+    const int H = level_h(c, U.level_in), W = level_w(c, U.level_in);
+    ConvParams& p = U.fwd;
+    p.taps = 1;
+    p.tap_mode = 0;
+    p.cin = U.cin;
+    geom(p, H, W, 4 * U.cout, U.bn_fwd);
+    if ((rc = make_act_map(&p.a_map[0], U.in, TILE_H))) return rc;
+    if ((rc = make_weight_map(&p.b_map, U.w_fwd, 4 * U.cout, U.cin, U.bn_fwd))) return rc;
+    p.out = U.out.ptr;
+    p.out_pitch = U.out.pitch;
+    p.convt_cout = U.cout;
+    if (train) {
+      ConvParams& d = U.dgrad;
+      d.taps = 4;
+      d.tap_mode = 1;
+      d.cin = U.cout;
+      geom(d, H, W, U.cin, U.bn_bwd);
+      for (int kk = 0; kk < 4; ++kk)
+        if ((rc = make_act_map(&d.a_map[kk], U.gout, TILE_H, 1, kk >> 1, kk & 1))) return rc;
+      if ((rc = make_weight_map(&d.b_map, U.w_bwd, U.cin, 4 * U.cout, U.bn_bwd))) return rc;
+      d.out = U.gin.ptr;
+      d.out_pitch = U.gin.pitch;
+      WgradParams& w = U.wg;
+      wgeom(w, H, W, U.cin, U.cout, U.bn_wg, 4, 1);
+      if ((rc = make_act_map(&w.a_map, U.in, 4))) return rc;
+      for (int kk = 0; kk < 4; ++kk)
+        if ((rc = make_act_map(&w.b_map[kk], U.gout, 4, 1, kk >> 1, kk & 1))) return rc;
+    }
+  }
+  return 0;
+}
+
+void set_batch(ConvParams& p, int nb) {
+  p.NB = nb;
+  p.total_tiles = nb * p.tiles_x * p.tiles_y * p.n_tiles;
+}
+void set_batch(WgradParams& p, int nb) {
+  p.NB = nb;
+  p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
+  const int tiles = p.taps * p.m_tiles * p.n_tiles;
+  int splits = (2 * device_num_sms() + tiles - 1) / tiles;
+  if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+}
+
+template <typename T>
+const T* S(const void* const* state, int i) {
+  return static_cast<const T*>(state[i]);
+}
+template <typename T>
+T* SM(const void* const* state, int i) {
+  return static_cast<T*>(const_cast<void*>(state[i]));
+}
+
+int check_call(crimac_ctx* c, const void* const* state, int nb) {
+  CRIMAC_REQUIRE(c != nullptr, "ctx is NULL");
+  CRIMAC_REQUIRE(state != nullptr, "state table is NULL");
+  CRIMAC_REQUIRE(nb >= 1 && nb <= c->cfg.max_batch, "nb must be in 1..max_batch");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) {
+    crimac_set_error(std::string("cudaSetDevice failed: ") + cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+double igemm_flops_n(const ConvParams& p, int n_total) {
+  return 2.0 * p.NB * static_cast<double>(p.H) * p.W * n_total * p.taps * p.cin;
+}
+
+int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, float* dw, cudaStream_t st) {
+  set_batch(w, nb);
+  const double wbytes = sizeof(float) * w.taps * static_cast<double>(w.M_total) * w.N_total;
+  if (w.splits > 1) {
+    ProfScope ps("wgrad_zero", 0, wbytes, st);
+    CRIMAC_CHECK_CUDA(cudaMemsetAsync(w.dw, 0, static_cast<size_t>(wbytes), st));
+  }
+  {
+    ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.M_total * w.N_total * w.taps, 0, st);
+    CRIMAC_CHECK_CUDA(launch_wgrad_gemm(w, bn, st));
+  }
+  {
+    ProfScope ps("wgrad_unpack", 0, 2 * wbytes, st);
+    CRIMAC_CHECK_CUDA(launch_wgrad_unpack(w.dw, dw, w.M_total, w.N_total, w.taps, 0, st));
+  }
+  return 0;
+}
+
+View with_batch(View v, int nb) {
+  v.N = nb;
+  return v;
+}
+
+}  // namespace
+
+extern "C" int crimac_state_count(const crimac_config* cfg) {
+  if (!cfg) return 0;
+  return cfg->depth * 14 + (cfg->depth - 1) * 16 + 2;
+}
+extern "C" int crimac_grad_count(const crimac_config* cfg) {
+  if (!cfg) return 0;
+  return cfg->depth * 8 + (cfg->depth - 1) * 10 + 2;
+}
+
+extern "C" int crimac_workspace_bytes(const crimac_config* cfg, size_t* bytes) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(bytes != nullptr, "bytes is NULL");
+  crimac_ctx tmp;
+  tmp.cfg = *cfg;
+  return build(&tmp, nullptr, bytes, false);
+}
+
+extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* workspace_dev, size_t workspace_bytes,
+                             int device) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(out != nullptr && workspace_dev != nullptr, "NULL argument");
+  CRIMAC_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "workspace must be 1024-byte aligned");
+  CRIMAC_CHECK_CUDA(cudaSetDevice(device));
+  int major = 0, minor = 0;
+  CRIMAC_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CRIMAC_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  CRIMAC_REQUIRE(major == 10, "libcrimac_b200 runs on sm_100a (B200) only; there is no fallback path");
+  crimac_ctx* c = new (std::nothrow) crimac_ctx;
+  CRIMAC_REQUIRE(c != nullptr, "out of host memory");
+  c->cfg = *cfg;
+  c->device = device;
+  size_t need = 0;
+  rc = build(c, nullptr, &need, false);
+  if (rc == 0 && need > workspace_bytes) {
+    crimac_set_error("workspace too small: need " + std::to_string(need) + " bytes");
+    rc = 1;
+  }
+  if (rc == 0) rc = build(c, workspace_dev, nullptr, true);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" int crimac_destroy(crimac_ctx* c) {
+  delete c;
+  return 0;
+}
+
+extern "C" int crimac_prepare(crimac_ctx* c, const void* const* state, int train, void* stream) {
+  int rc = check_call(c, state, 1);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(!train || c->cfg.train, "context was created without train=1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope ps("pack_weights", 0, 0, st, static_cast<int>(c->conv.size() + c->up.size()));
+  for (Conv3& L : c->conv) {
+    if (!L.first)
+      CRIMAC_CHECK_CUDA(launch_pack_conv3x3(S<float>(state, L.s_w), L.cout, L.cin, L.w_fwd, train ? L.w_bwd : nullptr, st));
+    if (!train)
+      CRIMAC_CHECK_CUDA(launch_bn_fold_eval(S<float>(state, L.s_g), S<float>(state, L.s_beta), S<float>(state, L.s_rm),
+                                            S<float>(state, L.s_rv), S<float>(state, L.s_b), 1e-5f, L.cout, L.scale,
+                                            L.shift, st));
+  }
+  for (ConvT& U : c->up)
+    CRIMAC_CHECK_CUDA(launch_pack_convt(S<float>(state, U.s_w), U.cin, U.cout, U.w_fwd, train ? U.w_bwd : nullptr, st));
+  c->prepared_mode = train ? 1 : 0;
+  return 0;
+}
+
+static int forward_impl(crimac_ctx* c, const void* const* state, const float* x, int nb, float* out, int softmax,
+                        bool train, cudaStream_t st) {
+  const int sms = device_num_sms();
+  const int D = c->D;
+  const int last = c->dec2[D - 2];
+  auto run_conv = [&](int idx) -> int {
+    Conv3& L = c->conv[idx];
+    const int H = level_h(c, L.level), W = level_w(c, L.level);
+    const int m_tiles = nb * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
+    if (train) {
+      View raw = with_batch(L.raw, nb);
+      const double px = static_cast<double>(nb) * H * W;
+      if (L.first) {
+        ProfScope ps("first_conv", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st);
+        CRIMAC_CHECK_CUDA(launch_first_conv(x, S<float>(state, L.s_w), nullptr, S<float>(state, L.s_b), 0, nb, L.cin, H,
+                                            W, raw.ptr, raw.pitch, c->stats, st));
+      } else {
+        ConvParams p = L.fwd;
+        set_batch(p, nb);
+        p.out = raw.ptr;
+        p.out_pitch = raw.pitch;
+        p.scale = nullptr;
+        p.shift = S<float>(state, L.s_b);
+        p.relu = 0;
+        p.stats = c->stats;
+        ProfScope ps("conv3x3_fwd", igemm_flops_n(p, L.cout), px * 2.0 * (L.cin + L.cout), st);
+        CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_fwd, EPI_STATS, sms, st));
+      }
+      {
+      ProfScope ps("bn_finalize", 0, 0, st);
+      CRIMAC_CHECK_CUDA(launch_bn_finalize(c->stats, m_tiles, L.cout, static_cast<double>(nb) * H * W,
+                                           S<float>(state, L.s_g), S<float>(state, L.s_beta), SM<float>(state, L.s_rm),
+                                           SM<float>(state, L.s_rv), SM<long long>(state, L.s_nbt), 0.1f, 1e-5f, L.scale,
+                                           L.shift, L.mean, L.invstd, st));
+      }
+      View pool = L.pool;
+      if (pool.ptr) pool.N = nb;
+      ProfScope ps("bn_apply", 0, px * L.cout * (pool.ptr ? 4.5 : 4.0), st);
+      CRIMAC_CHECK_CUDA(launch_bn_apply(raw, L.scale, L.shift, with_batch(L.act, nb), pool, st));
+    } else {
+      const double px = static_cast<double>(nb) * H * W;
+      if (L.first) {
+        ProfScope ps("first_conv", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st);
+        CRIMAC_CHECK_CUDA(launch_first_conv(x, S<float>(state, L.s_w), L.scale, L.shift, 1, nb, L.cin, H, W, L.act.ptr,
+                                            L.act.pitch, nullptr, st));
+      } else {
+        ConvParams p = L.fwd;
+        set_batch(p, nb);
+        p.scale = L.scale;
+        p.shift = L.shift;
+        p.relu = 1;
+        int epi = EPI_STORE;
+        if (idx == last) {
+          // fused 1x1 head (+softmax): the 64-channel activation of the last conv never goes to HBM
+          p.out = nullptr;
+          p.head_w = S<float>(state, c->s_head_w);
+          p.head_b = S<float>(state, c->s_head_b);
+          p.head_out = out;
+          p.n_classes = c->cfg.n_classes;
+          p.head_softmax = softmax;
+          epi = EPI_HEAD;
+        } else {
+          p.out = L.act.ptr;
+          p.out_pitch = L.act.pitch;
+          p.pool_out = L.pool.ptr;
+          p.pool_pitch = L.pool.pitch;
+        }
+        ProfScope ps(epi == EPI_HEAD ? "conv3x3_fwd_head" : "conv3x3_fwd", igemm_flops_n(p, L.cout),
+                     px * 2.0 * (L.cin + L.cout), st);
+        CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_fwd, epi, sms, st));
+      }
+    }
+    return 0;
+  };
+  int rc;
+  for (int l = 0; l < D; ++l) {
+    if ((rc = run_conv(c->enc1[l]))) return rc;
+    if ((rc = run_conv(c->enc2[l]))) return rc;
+  }
+  for (int j = 0; j < D - 1; ++j) {
+    ConvT& U = c->up[j];
+    ConvParams p = U.fwd;
+    set_batch(p, nb);
+    p.scale = nullptr;
+    p.shift = S<float>(state, U.s_b);
+    p.relu = 0;
+    {
+      ProfScope ps("convT_fwd", igemm_flops_n(p, 4 * U.cout), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_fwd, EPI_STORE, sms, st));
+    }
+    if ((rc = run_conv(c->dec1[j]))) return rc;
+    if ((rc = run_conv(c->dec2[j]))) return rc;
+  }
+  if (train) {
+    ProfScope ps("head_fwd", 0, static_cast<double>(nb) * c->cfg.height * c->cfg.width * (128.0 + 4.0 * c->cfg.n_classes), st);
+    CRIMAC_CHECK_CUDA(launch_head_fwd(with_batch(c->conv[last].act, nb), S<float>(state, c->s_head_w),
+                                      S<float>(state, c->s_head_b), c->cfg.n_classes, out, st));
+  }
+  return 0;
+}
+
+extern "C" int crimac_forward_infer(crimac_ctx* c, const void* const* state, const float* x, int nb, float* out,
+                                    int softmax, void* stream) {
+  int rc = check_call(c, state, nb);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(x != nullptr && out != nullptr, "NULL tensor");
+  CRIMAC_REQUIRE(c->prepared_mode == 0, "call crimac_prepare(ctx, state, train=0) first");
+  return forward_impl(c, state, x, nb, out, softmax, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int crimac_forward_train(crimac_ctx* c, const void* const* state, const float* x, int nb, float* logits,
+                                    void* stream) {
+  int rc = check_call(c, state, nb);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(x != nullptr && logits != nullptr, "NULL tensor");
+  CRIMAC_REQUIRE(c->cfg.train, "context was created without train=1");
+  CRIMAC_REQUIRE(c->prepared_mode == 1, "call crimac_prepare(ctx, state, train=1) first");
+  return forward_impl(c, state, x, nb, logits, 0, true, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int crimac_loss(crimac_ctx* c, const float* logits, const int64_t* labels, const float* class_w,
+                           int64_t ignore_index, int nb, float* out3, float* dlogits, void* stream) {
+  CRIMAC_REQUIRE(c != nullptr && c->cfg.train, "train context required");
+  CRIMAC_REQUIRE(nb >= 1 && nb <= c->cfg.max_batch, "nb");
+  CRIMAC_REQUIRE(logits && labels && class_w && out3, "NULL tensor");
+  CRIMAC_CHECK_CUDA(cudaSetDevice(c->device));
+  ProfScope ps("ce_loss", 0, static_cast<double>(nb) * c->cfg.height * c->cfg.width * (8.0 * c->cfg.n_classes + 8.0),
+               static_cast<cudaStream_t>(stream), 2);
+  CRIMAC_CHECK_CUDA(launch_ce(logits, reinterpret_cast<const long long*>(labels), class_w, c->cfg.n_classes, nb,
+                              static_cast<long>(c->cfg.height) * c->cfg.width, ignore_index, dlogits, c->ce_partials,
+                              out3, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const float* x, const float* dlogits,
+                               const float* gscale, int nb, float* const* grads, void* stream) {
+  int rc = check_call(c, state, nb);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(c->cfg.train && c->prepared_mode == 1, "backward needs a train context after forward_train");
+  CRIMAC_REQUIRE(x && dlogits && grads, "NULL tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sms = device_num_sms();
+  const int D = c->D;
+
+  // BN/ReLU backward of layer idx (dA in GA) -> dRaw in GR; then wgrad (+ dgrad into L.gin)
+  auto conv_bwd = [&](int idx) -> int {
+    Conv3& L = c->conv[idx];
+    const int H = level_h(c, L.level), W = level_w(c, L.level);
+    View da{c->GA, nb, H, W, L.cout, L.cout};
+    View dr{c->GR, nb, H, W, L.cout, L.cout};
+    const double px = static_cast<double>(nb) * H * W;
+    {
+      ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 4);
+      CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
+                                      grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2, st));
+    }
+    if (L.first) {
+      ProfScope ps("first_conv_wgrad", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st, 2);
+      CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, dr, L.cin, c->fc_partials, grads[L.g_w], 0, st));
+      return 0;
+    }
+    int r = wgrad_run(c, L.wg, L.bn_wg, nb, grads[L.g_w], st);
+    if (r) return r;
+    if (L.gin.ptr != nullptr) {
+      ConvParams p = L.dgrad;
+      set_batch(p, nb);
+      ProfScope ps("conv3x3_dgrad", igemm_flops_n(p, L.cin), px * 2.0 * (L.cin + L.cout), st);
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_bwd, EPI_STORE, sms, st));
+    }
+    return 0;
+  };
+
+  // head
+  const int last = c->dec2[D - 2];
+  {
+    Conv3& L = c->conv[last];
+    View dact{c->GA, nb, c->cfg.height, c->cfg.width, 64, 64};
+    ProfScope ps("head_bwd", 0, static_cast<double>(nb) * c->cfg.height * c->cfg.width * (256.0 + 4.0 * c->cfg.n_classes), st, 2);
+    CRIMAC_CHECK_CUDA(launch_head_bwd(dlogits, gscale, with_batch(L.act, nb), S<float>(state, c->s_head_w),
+                                      c->cfg.n_classes, dact, c->head_partials, grads[c->g_head_w],
+                                      grads[c->g_head_b], 0, st));
+  }
+  // decoder, last block first
+  for (int j = D - 2; j >= 0; --j) {
+    if ((rc = conv_bwd(c->dec2[j]))) return rc;
+    if ((rc = conv_bwd(c->dec1[j]))) return rc;  // dgrad wrote dCat_j
+    ConvT& U = c->up[j];
+    {
+      ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, st, 2);
+      CRIMAC_CHECK_CUDA(launch_view_colsum(with_batch(U.gout, nb), c->red_partials, grads[U.g_b], 0, st));
+    }
+    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, grads[U.g_w], st))) return rc;
+    ConvParams p = U.dgrad;
+    set_batch(p, nb);
+    ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
+    CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));  // -> GA (grad of the convT input)
+  }
+  // encoder, deepest level first
+  for (int l = D - 1; l >= 0; --l) {
+    Conv3& L2 = c->conv[c->enc2[l]];
+    if (l < D - 1) {
+      const int j = D - 2 - l;
+      View dpool{c->GP, nb, level_h(c, l + 1), level_w(c, l + 1), L2.cout, L2.cout};
+      View dskip{c->dcat[j] + L2.cout, nb, level_h(c, l), level_w(c, l), L2.cout, 2 * L2.cout};
+      View dact{c->GA, nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
+      ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 3.25, st);
+      CRIMAC_CHECK_CUDA(launch_pool_bwd_add(with_batch(L2.act, nb), dpool, dskip, dact, st));
+    }
+    if ((rc = conv_bwd(c->enc2[l]))) return rc;
+    if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
+  }
+  return 0;
+}
+
+extern "C" int crimac_train_step(crimac_ctx* c, const void* const* state, const float* x, const int64_t* labels,
+                                 const float* class_w, int64_t ignore_index, int nb, float* const* grads, float* loss3,
+                                 void* stream) {
+  int rc = crimac_prepare(c, state, 1, stream);
+  if (rc) return rc;
+  if ((rc = crimac_forward_train(c, state, x, nb, c->logits, stream))) return rc;
+  float* l3 = loss3 ? loss3 : c->loss3;
+  if ((rc = crimac_loss(c, c->logits, labels, class_w, ignore_index, nb, l3, c->dlogits, stream))) return rc;
+  return crimac_backward(c, state, x, c->dlogits, l3 + 1, nb, grads, stream);
+}

@@ -1,0 +1,142 @@
+// HBM-bound kernels either side of the U-Net: patch gather + sv->dB transform (feeds the first conv), on-device
+// overlap stitching of whole-echogram predictions, and the SGD-momentum step.
+#include "host_util.h"
+#include "../../include/crimac_b200.h"
+#include <cuda_fp16.h>
+
+namespace {
+
+// batch/dataset.py:192-205 (get_preload_data_labels) + utils/np.py:40-46,362-375 (getGrid, new_get_crop_3d) +
+// remove_nan_inf.py:23-34 + db_with_limits.py:20-24,36-38.  One thread = 4 consecutive pings of one patch row.
+__global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict__ sv, int F, int R, int P,
+                                                         int data_ping0, const int* __restrict__ centres, int n,
+                                                         int ph, int pw, float* __restrict__ out,
+                                                         uint8_t* __restrict__ nan_mask) {
+  const int pw4 = pw >> 2;
+  const long total = static_cast<long>(n) * F * ph * pw4;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int x4 = static_cast<int>(i % pw4);
+    long t = i / pw4;
+    const int py = static_cast<int>(t % ph);
+    t /= ph;
+    const int f = static_cast<int>(t % F);
+    const int b = static_cast<int>(t / F);
+    const int cy = centres[2 * b], cx = centres[2 * b + 1];
+    const int y = cy - ph / 2 + 1 + py;
+    const int x0 = cx - pw / 2 + 1 + 4 * x4 - data_ping0;
+    float v[4];
+    uint8_t bad[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      float s = 0.f;  // out-of-data -> 0 BEFORE the dB transform (boundary_val_data, dataset.py:194)
+      bool nf = false;
+      if (y >= 0 && y < R && x >= 0 && x < P) {
+        s = __ldg(&sv[(static_cast<long>(f) * R + y) * P + x]);
+        nf = !isfinite(s);
+        if (nf) s = 0.f;
+      }
+      float d = 10.f * log10f(s + 1e-10f);
+      d = fminf(fmaxf(d, -75.f), 0.f);
+      v[j] = d;
+      bad[j] = nf ? 1 : 0;
+    }
+    const long o = ((static_cast<long>(b) * F + f) * ph + py) * pw + 4 * x4;
+    *reinterpret_cast<float4*>(out + o) = make_float4(v[0], v[1], v[2], v[3]);
+    if (f == 0 && nan_mask != nullptr)
+      *reinterpret_cast<uchar4*>(nan_mask + (static_cast<long>(b) * ph + py) * pw + 4 * x4) =
+          make_uchar4(bad[0], bad[1], bad[2], bad[3]);
+  }
+}
+
+// save_predict.py:41-65 (fill_out_array) with the label semantics of mask_label_overlap.py:31-48,
+// mask_label_seabed.py:32-68 (seabed_pad = 10, shifted inside the patch's clipped range window),
+// new_get_crop_2d's LABEL_BOUNDARY_VAL outside [ping_start, ping_start+Pc) x [0,R), and remove_nan_inf.py:32.
+__global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ probs, int n, int ncls, int ph, int pw,
+                                                     const int* __restrict__ centres,
+                                                     const uint8_t* __restrict__ nan_mask,
+                                                     const short* __restrict__ labels, const int* __restrict__ seabed,
+                                                     int seabed_pad, int overlap, int ping_start, int Pc, int R,
+                                                     int c0, int c1, int c2, int c3, int K, __half* __restrict__ out) {
+  const int cls[4] = {c0, c1, c2, c3};
+  const long total = static_cast<long>(n) * ph * pw;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(i % pw);
+    const int py = static_cast<int>((i / pw) % ph);
+    const int b = static_cast<int>(i / (static_cast<long>(pw) * ph));
+    if (py < overlap || py >= ph - overlap || px < overlap || px >= pw - overlap) continue;  // -70 frame
+    const int cy = centres[2 * b], cx = centres[2 * b + 1];
+    const int y_upper = cy - ph / 2 + 1;
+    const int y = y_upper + py;
+    const int xl = cx - pw / 2 + 1 + px - ping_start;  // ping index inside the chunk
+    if (y < 0 || y >= R || xl < 0 || xl >= Pc) continue;  // -100 outside the chunk's label slice
+    if (nan_mask != nullptr && nan_mask[i]) continue;     // -100 where frequency 0 was non-finite
+    const int l0 = labels ? labels[static_cast<long>(y) * Pc + xl] : 0;
+    if (l0 == -100 || l0 == -70 || l0 == -50) continue;
+    if (seabed != nullptr && l0 == 0) {
+      const int win0 = y_upper > 0 ? y_upper : 0;  // the mask is padded inside the patch's clipped range window
+      if (y - win0 >= seabed_pad && y - seabed_pad >= seabed[xl]) continue;  // -50 below seabed (+pad)
+    }
+    for (int k = 0; k < K; ++k)
+      out[(static_cast<long>(k) * R + y) * Pc + xl] =
+          __float2half(probs[((static_cast<long>(b) * ncls + cls[k]) * ph + py) * pw + px]);
+  }
+}
+
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, float* __restrict__ v,
+                                                  const float* __restrict__ g, size_t n, float lr, float momentum,
+                                                  float gscale) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float nv = momentum * v[i] + g[i] * gscale;
+    v[i] = nv;
+    p[i] -= lr * nv;
+  }
+}
+
+}  // namespace
+
+extern "C" int crimac_preprocess(const float* sv, int F, int R, int P, int data_ping0, const int32_t* centres, int n,
+                                 int ph, int pw, float* out, uint8_t* nan_mask, void* stream) {
+  CRIMAC_REQUIRE(sv && centres && out, "NULL tensor");
+  CRIMAC_REQUIRE(F >= 1 && R >= 1 && P >= 1 && n >= 1, "empty input");
+  CRIMAC_REQUIRE(ph % 2 == 0 && pw % 4 == 0, "patch height must be even and width a multiple of 4");
+  const long total = static_cast<long>(n) * F * ph * (pw / 4);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  preprocess_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sv, F, R, P, data_ping0, centres, n, ph, pw, out, nan_mask);
+  CRIMAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int crimac_stitch(const float* probs, int n, int n_classes, int ph, int pw, const int32_t* centres,
+                             const uint8_t* nan_mask, const int16_t* labels, const int32_t* seabed, int seabed_pad,
+                             int overlap, int ping_start, int Pc, int R, const int32_t* cls, int K, void* out,
+                             void* stream) {
+  CRIMAC_REQUIRE(probs && centres && out && cls, "NULL tensor");
+  CRIMAC_REQUIRE(K >= 1 && K <= 4, "K must be 1..4");
+  for (int k = 0; k < K; ++k) CRIMAC_REQUIRE(cls[k] >= 0 && cls[k] < n_classes, "class index out of range");
+  const long total = static_cast<long>(n) * ph * pw;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stitch_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      probs, n, n_classes, ph, pw, centres, nan_mask, labels, seabed, seabed_pad, overlap, ping_start, Pc, R, cls[0],
+      K > 1 ? cls[1] : 0, K > 2 ? cls[2] : 0, K > 3 ? cls[3] : 0, K, static_cast<__half*>(out));
+  CRIMAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int crimac_sgd_step(float* params, float* mom, const float* grads, size_t n, float lr, float momentum,
+                               float gscale, void* stream) {
+  CRIMAC_REQUIRE(params && mom && grads, "NULL tensor");
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks == 0) return 0;
+  sgd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, mom, grads, n, lr,
+                                                                                      momentum, gscale);
+  CRIMAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

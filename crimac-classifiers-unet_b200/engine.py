@@ -1,0 +1,184 @@
+"""Host-side driver of libcrimac_b200.so for one UNet module: owns the native context + workspace (a torch uint8
+tensor), builds the parameter tables the C-ABI expects, and exposes the three calls the module uses
+(infer / train-forward / backward) plus the fused train step.  PyTorch is plumbing here: device memory, streams.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [
+        ("in_channels", ctypes.c_int),
+        ("n_classes", ctypes.c_int),
+        ("depth", ctypes.c_int),
+        ("start_filts", ctypes.c_int),
+        ("max_batch", ctypes.c_int),
+        ("height", ctypes.c_int),
+        ("width", ctypes.c_int),
+        ("train", ctypes.c_int),
+    ]
+
+
+def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, height, width, train):
+    """Size of the device workspace a context of this shape needs (pure host computation)."""
+    L = _lib.load()
+    cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train))
+    n = ctypes.c_size_t(0)
+    _lib.check(L.crimac_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)), "crimac_workspace_bytes")
+    return n.value
+
+
+class Context:
+    """One native context: fixed (max_batch, H, W), inference-only or train-capable."""
+
+    def __init__(self, in_channels, n_classes, depth, start_filts, max_batch, height, width, train, device):
+        self.L = _lib.load()
+        self.cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train))
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CrimacError("the CRIMAC U-Net hot path runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        n = ctypes.c_size_t(0)
+        _lib.check(self.L.crimac_workspace_bytes(ctypes.byref(self.cfg), ctypes.byref(n)), "crimac_workspace_bytes")
+        self.workspace = torch.empty(n.value + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.workspace.data_ptr() + 1023) & ~1023
+        self.handle = ctypes.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(
+            self.L.crimac_create(ctypes.byref(self.handle), ctypes.byref(self.cfg), ctypes.c_void_p(base),
+                                 ctypes.c_size_t(n.value), dev_index),
+            "crimac_create",
+        )
+        self.n_state = self.L.crimac_state_count(ctypes.byref(self.cfg))
+        self.n_grad = self.L.crimac_grad_count(ctypes.byref(self.cfg))
+        self.prepared_key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.L.crimac_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- tables
+    def state_table(self, tensors):
+        if len(tensors) != self.n_state:
+            raise _lib.CrimacError(f"state table needs {self.n_state} tensors, got {len(tensors)}")
+        arr = (ctypes.c_void_p * self.n_state)(*[t.data_ptr() for t in tensors])
+        return arr
+
+    def grad_table(self, tensors):
+        if len(tensors) != self.n_grad:
+            raise _lib.CrimacError(f"grad table needs {self.n_grad} tensors, got {len(tensors)}")
+        return (ctypes.c_void_p * self.n_grad)(*[t.data_ptr() for t in tensors])
+
+    # ---- calls
+    def prepare(self, state, train):
+        _lib.check(self.L.crimac_prepare(self.handle, state, int(train), _lib.stream_ptr()), "crimac_prepare")
+
+    def forward_infer(self, state, x, out, softmax):
+        _lib.check(
+            self.L.crimac_forward_infer(self.handle, state, _lib.ptr(x), x.shape[0], _lib.ptr(out), int(softmax),
+                                        _lib.stream_ptr()),
+            "crimac_forward_infer",
+        )
+
+    def forward_train(self, state, x, logits):
+        _lib.check(
+            self.L.crimac_forward_train(self.handle, state, _lib.ptr(x), x.shape[0], _lib.ptr(logits), _lib.stream_ptr()),
+            "crimac_forward_train",
+        )
+
+    def loss(self, logits, labels, class_w, ignore_index, out3, dlogits):
+        _lib.check(
+            self.L.crimac_loss(self.handle, _lib.ptr(logits), _lib.ptr(labels), _lib.ptr(class_w),
+                               ctypes.c_int64(ignore_index), logits.shape[0], _lib.ptr(out3), _lib.ptr(dlogits),
+                               _lib.stream_ptr()),
+            "crimac_loss",
+        )
+
+    def backward(self, state, x, dlogits, gscale, grads):
+        _lib.check(
+            self.L.crimac_backward(self.handle, state, _lib.ptr(x), _lib.ptr(dlogits), _lib.ptr(gscale), x.shape[0],
+                                   grads, _lib.stream_ptr()),
+            "crimac_backward",
+        )
+
+    def train_step(self, state, x, labels, class_w, ignore_index, grads, loss3):
+        _lib.check(
+            self.L.crimac_train_step(self.handle, state, _lib.ptr(x), _lib.ptr(labels), _lib.ptr(class_w),
+                                     ctypes.c_int64(ignore_index), x.shape[0], grads, _lib.ptr(loss3),
+                                     _lib.stream_ptr()),
+            "crimac_train_step",
+        )
+
+
+def sgd_step(params_flat, momentum_flat, grads_flat, lr, momentum, gscale=1.0):
+    """Fused SGD(momentum) on flat fp32 arenas (reference pipeline.py:156,178)."""
+    L = _lib.load()
+    _lib.check(
+        L.crimac_sgd_step(_lib.ptr(params_flat), _lib.ptr(momentum_flat), _lib.ptr(grads_flat),
+                          ctypes.c_size_t(params_flat.numel()), ctypes.c_float(lr), ctypes.c_float(momentum),
+                          ctypes.c_float(gscale), _lib.stream_ptr()),
+        "crimac_sgd_step",
+    )
+
+
+def preprocess(sv, data_ping0, centres, patch_hw, out=None, nan_mask=None):
+    """sv: fp32 (F,R,P) device tensor; centres: int32 (n,2) device tensor (y,x) survey coords."""
+    L = _lib.load()
+    F, R, P = sv.shape
+    n = centres.shape[0]
+    ph, pw = patch_hw
+    if out is None:
+        out = torch.empty((n, F, ph, pw), dtype=torch.float32, device=sv.device)
+    if nan_mask is None:
+        nan_mask = torch.empty((n, ph, pw), dtype=torch.uint8, device=sv.device)
+    _lib.check(
+        L.crimac_preprocess(_lib.ptr(sv), F, R, P, int(data_ping0), _lib.ptr(centres), n, ph, pw, _lib.ptr(out),
+                            _lib.ptr(nan_mask), _lib.stream_ptr()),
+        "crimac_preprocess",
+    )
+    return out, nan_mask
+
+
+def stitch(probs, centres, nan_mask, out, ping_start, overlap, labels=None, seabed=None, seabed_pad=10, classes=(1, 2)):
+    """probs: fp32 (n,ncls,ph,pw); out: fp16 (K,R,Pc) device tensor written in place."""
+    L = _lib.load()
+    n, ncls, ph, pw = probs.shape
+    K, R, Pc = out.shape
+    cls = (ctypes.c_int32 * len(classes))(*classes)
+    _lib.check(
+        L.crimac_stitch(_lib.ptr(probs), n, ncls, ph, pw, _lib.ptr(centres), _lib.ptr(nan_mask), _lib.ptr(labels),
+                        _lib.ptr(seabed), int(seabed_pad), int(overlap), int(ping_start), Pc, R, cls, K, _lib.ptr(out),
+                        _lib.stream_ptr()),
+        "crimac_stitch",
+    )
+    return out
+
+
+def launch_count():
+    L = _lib.load()
+    L.crimac_launch_count.restype = ctypes.c_ulonglong
+    return int(L.crimac_launch_count())
+
+
+def profile_enable(on=True):
+    _lib.check(_lib.load().crimac_profile_enable(int(on)), "crimac_profile_enable")
+
+
+def profile_read():
+    """Returns a list of (kernel family, ms, algorithmic flops, algorithmic bytes, launches) since profile_enable(1)."""
+    L = _lib.load()
+    cap = 4096
+    names = (ctypes.c_char_p * cap)()
+    ms = (ctypes.c_float * cap)()
+    fl = (ctypes.c_double * cap)()
+    by = (ctypes.c_double * cap)()
+    ln = (ctypes.c_int * cap)()
+    n = L.crimac_profile_read(names, ms, fl, by, ln, cap)
+    n = min(n, cap)
+    return [(names[i].decode(), float(ms[i]), float(fl[i]), float(by[i]), int(ln[i])) for i in range(n)]

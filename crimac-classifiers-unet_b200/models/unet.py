@@ -1,0 +1,357 @@
+"""Drop-in replacement for the reference ``crimac_unet/models/unet.py`` (same class / function names, constructor
+arguments, attributes, ``forward`` signatures and the 136 ``state_dict`` keys of SURVEY.md App. B), whose hot path —
+``UNet_Baseline.forward`` (reference models/unet.py:327-343) and its autograd backward — runs in hand-written sm_100a
+kernels behind the C-ABI of ``include/crimac_b200.h``.
+
+The sub-modules (``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.ConvTranspose2d``) are kept purely as PARAMETER HOLDERS in
+the same tree positions so checkpoints load unchanged; their own ``forward`` is never used on the hot path.  There is
+no CPU / PyTorch fallback for ``UNet_Baseline``: a configuration the native path does not cover raises.
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import weakref
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _runtime():
+    """The host-side driver package (``engine.py``), importable whichever way this file itself was imported."""
+    name = "crimac_unet_b200"
+    if name not in sys.modules:
+        pkg_dir = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location(
+            name, os.path.join(pkg_dir, "__init__.py"), submodule_search_locations=[pkg_dir]
+        )
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    return importlib.import_module(name + ".engine")
+
+
+# native contexts live outside the module object so that copy.deepcopy / pickling of a model never touches them
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+# --------------------------------------------------------------------------------------------- layer factories
+def conv3x3(in_channels, out_channels, stride=1, padding=1, bias=True, groups=1):
+    """3x3 convolution holder (reference unet.py:35-44)."""
+    return nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=padding, bias=bias, groups=groups)
+
+
+def conv1x1(in_channels, out_channels, groups=1):
+    """1x1 convolution holder (reference unet.py:59-60)."""
+    return nn.Conv2d(in_channels, out_channels, kernel_size=1, groups=groups, stride=1)
+
+
+def upconv2x2(in_channels, out_channels, mode="transpose"):
+    """2x up-sampling holder (reference unet.py:47-56): transposed conv, or bilinear upsample + 1x1 conv."""
+    if mode == "transpose":
+        return nn.ConvTranspose2d(in_channels, out_channels, kernel_size=2, stride=2)
+    return nn.Sequential(nn.Upsample(mode="bilinear", scale_factor=2), conv1x1(in_channels, out_channels))
+
+
+class DownConv(nn.Module):
+    """Encoder block: (conv3x3, BN, ReLU) x 2 and an optional 2x2 max-pool (reference unet.py:63-93).
+
+    ``main`` keeps the reference's Sequential indexing (0 conv, 1 bn, 2 relu, 3 conv, 4 bn, 5 relu) because the
+    state_dict keys ``main.0/1/3/4.*`` depend on it.  ``forward`` is the plain-torch composition; the native engine
+    bypasses it and only reads the parameters.
+    """
+
+    def __init__(self, in_channels, out_channels, pooling=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.pooling = in_channels, out_channels, pooling
+        layers = []
+        for cin in (in_channels, out_channels):
+            layers += [conv3x3(cin, out_channels), nn.BatchNorm2d(out_channels), nn.ReLU()]
+        self.main = nn.Sequential(*layers)
+        if pooling:
+            self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
+
+    def forward(self, x):
+        before_pool = self.main(x)
+        return (self.pool(before_pool) if self.pooling else before_pool), before_pool
+
+
+class UpConv(nn.Module):
+    """Decoder block: up-conv, merge with the skip tensor, (conv3x3, BN, ReLU) x 2 (reference unet.py:96-137).
+    Registration order upconv, conv1, conv2, bn1, bn2 fixes ``parameters()`` order."""
+
+    def __init__(self, in_channels, out_channels, merge_mode="concat", up_mode="transpose"):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.merge_mode, self.up_mode = merge_mode, up_mode
+        self.upconv = upconv2x2(in_channels, out_channels, mode=up_mode)
+        self.conv1 = conv3x3(2 * out_channels if merge_mode == "concat" else out_channels, out_channels)
+        self.conv2 = conv3x3(out_channels, out_channels)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.bn2 = nn.BatchNorm2d(out_channels)
+
+    def forward(self, from_down, from_up):
+        up = self.upconv(from_up)
+        merged = torch.cat((up, from_down), 1) if self.merge_mode == "concat" else up + from_down
+        y = F.relu(self.bn1(self.conv1(merged)))
+        return F.relu(self.bn2(self.conv2(y)))
+
+
+class MetaPostProcessing(nn.Module):
+    """Per-pixel MLP on the metadata channels (reference unet.py:140-166); not on the benchmark path."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels = in_channels
+        self.hidden_channels_1 = 32
+        self.hidden_channels_2 = 32
+        self.out_channels = out_channels
+        self.main = nn.Sequential(
+            nn.Linear(in_channels, self.hidden_channels_1),
+            nn.ReLU(),
+            nn.Linear(self.hidden_channels_1, self.hidden_channels_2),
+            nn.ReLU(),
+            nn.Linear(self.hidden_channels_2, out_channels),
+        )
+
+    def forward(self, x):
+        return self.main(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------------------------- autograd bridge
+class _NativeUNetFunction(torch.autograd.Function):
+    """Train-mode forward / backward of the whole network through the C-ABI (one Function for all layers)."""
+
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        eng = model._engine_for(x, train=True)
+        state = eng.state_table(model._state_tensors())
+        eng.prepare(state, True)
+        logits = torch.empty((x.shape[0], model.n_classes, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
+        eng.forward_train(state, x, logits)
+        ctx.model, ctx.eng = model, eng
+        ctx.save_for_backward(x)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        (x,) = ctx.saved_tensors
+        model, eng = ctx.model, ctx.eng
+        params = model._param_tensors()
+        arena = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=x.device)
+        grads, off = [], 0
+        for p in params:
+            grads.append(arena[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        state = eng.state_table(model._state_tensors())
+        eng.backward(state, x, dlogits.contiguous().float(), None, eng.grad_table(grads))
+        return (None, None) + tuple(grads)
+
+
+class UNet(nn.Module):
+    """Base class: builds the encoder / decoder holders exactly where the reference does (unet.py:169-301)."""
+
+    valid = False
+    pad = 0
+    fow = [192, 192]
+    dim = 2
+    type = "seg"
+    stride = 1
+    increase_fow = 16
+
+    def __init__(self, n_classes=2, in_channels=1, meta_in_channels=0, late_meta_inject=False, depth=5, start_filts=64,
+                 up_mode="transpose", merge_mode="concat"):
+        super().__init__()
+        if up_mode not in ("transpose", "upsample"):
+            raise ValueError(
+                '"{}" is not a valid mode for upsampling. Only "transpose" and "upsample" are allowed.'.format(up_mode)
+            )
+        if merge_mode not in ("concat", "add"):
+            # the reference formats this message with up_mode (unet.py:236-241); kept for identical error text
+            raise ValueError(
+                '"{}" is not a valid mode formerging up and down paths. Only "concat" and "add" are allowed.'.format(up_mode)
+            )
+        if up_mode == "upsample" and merge_mode == "add":
+            raise ValueError(
+                'up_mode "upsample" is incompatible with merge_mode "add" at the moment because it doesn\'t make sense '
+                "to use nearest neighbour to reduce depth channels (by half)."
+            )
+        self.up_mode, self.merge_mode = up_mode, merge_mode
+        self.in_channels = in_channels
+        self.start_filts = start_filts
+        self.depth = depth
+        self.n_classes = n_classes
+        self.meta_in_channels = meta_in_channels
+
+        widths = [start_filts * (2 ** i) for i in range(depth)]
+        downs = [DownConv(in_channels if i == 0 else widths[i - 1], widths[i], pooling=i < depth - 1) for i in range(depth)]
+        ups = [UpConv(widths[i], widths[i - 1], up_mode=up_mode, merge_mode=merge_mode) for i in range(depth - 1, 0, -1)]
+        self.down_convs = nn.Sequential(*downs)
+        self.up_convs = nn.Sequential(*ups)
+        head_in = widths[0] if depth > 1 else widths[-1]
+        if not late_meta_inject:
+            self.conv_final = conv1x1(head_in, n_classes)
+        else:
+            self.conv_final = conv1x1(head_in + meta_in_channels, n_classes)
+            self.post_processing_weights = MetaPostProcessing(in_channels=meta_in_channels, out_channels=1)
+
+    @staticmethod
+    def weight_init(m):
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight)
+            nn.init.constant_(m.bias, 0)
+
+    def reset_params(self):
+        for i, m in enumerate(self.modules()):
+            print(i, m)
+            self.weight_init(m)
+
+    # plain-torch composition, used only by the variants that are NOT on the hot path (UNet_LateMetInject)
+    def _features_torch(self, x):
+        skips = []
+        for block in self.down_convs:
+            x, before_pool = block(x)
+            skips.append(before_pool)
+        for i, block in enumerate(self.up_convs):
+            x = block(skips[-(i + 2)], x)
+        return x
+
+
+class UNet_Baseline(UNet):
+    """The hot-path model (reference unet.py:304-343; the only model SegPipeUNet builds, pipeline.py:390-398)."""
+
+    def __init__(self, n_classes, in_channels, meta_in_channels=0, late_meta_inject=False, depth=5, start_filts=64,
+                 up_mode="transpose", merge_mode="concat"):
+        super().__init__(n_classes, in_channels, meta_in_channels, late_meta_inject, depth, start_filts, up_mode, merge_mode)
+
+    # ---- native plumbing
+    def _check_supported(self, x):
+        problems = []
+        if self.up_mode != "transpose" or self.merge_mode != "concat":
+            problems.append("only up_mode='transpose' with merge_mode='concat' is implemented natively")
+        if self.start_filts != 64 or not (2 <= self.depth <= 5):
+            problems.append("start_filts must be 64 and depth in 2..5")
+        if not (1 <= self.in_channels <= 8) or not (1 <= self.n_classes <= 8):
+            problems.append("in_channels and n_classes must be in 1..8")
+        if self.conv_final.in_channels != 64:
+            problems.append("late_meta_inject heads are not on the native path")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            problems.append(f"expected input (N,{self.in_channels},H,W), got {tuple(x.shape)}")
+        elif x.shape[2] % (1 << (self.depth - 1)) or x.shape[3] % (1 << (self.depth - 1)):
+            problems.append("H and W must be multiples of 2^(depth-1)")
+        if not x.is_cuda:
+            problems.append("input must be a CUDA tensor: the U-Net hot path has no CPU fallback")
+        if problems:
+            raise RuntimeError("crimac_unet_b200.UNet_Baseline cannot run this call natively: " + "; ".join(problems))
+
+    def _state_tensors(self):
+        """The 136 tensors of state_dict() in its order, gathered without building the dict."""
+        def bn(m):
+            return [m.weight, m.bias, m.running_mean, m.running_var, m.num_batches_tracked]
+
+        out = []
+        for d in self.down_convs:
+            c1, b1, _, c2, b2, _ = d.main
+            out += [c1.weight, c1.bias] + bn(b1) + [c2.weight, c2.bias] + bn(b2)
+        for u in self.up_convs:
+            out += [u.upconv.weight, u.upconv.bias, u.conv1.weight, u.conv1.bias, u.conv2.weight, u.conv2.bias]
+            out += bn(u.bn1) + bn(u.bn2)
+        return out + [self.conv_final.weight, self.conv_final.bias]
+
+    def _param_tensors(self):
+        return list(self.parameters())
+
+    def _engine_for(self, x, train):
+        rt = _runtime()
+        nb, _, h, w = x.shape
+        key = (h, w, bool(train), x.device)
+        engines = _ENGINES.setdefault(self, {})
+        eng = engines.get(key)
+        if eng is None or eng.cfg.max_batch < nb:
+            eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, x.device)
+            engines[key] = eng
+        return eng
+
+    def _versions(self):
+        return tuple((t.data_ptr(), t._version) for t in self._state_tensors())
+
+    def _prep_input(self, x):
+        self._check_supported(x)
+        for t in self._state_tensors():
+            if t.device != x.device:
+                raise RuntimeError("model parameters and input are on different devices")
+            break
+        return x.contiguous().float()
+
+    def _infer(self, x, softmax):
+        x = self._prep_input(x)
+        eng = self._engine_for(x, train=False)
+        state = eng.state_table(self._state_tensors())
+        key = self._versions()
+        if eng.prepared_key != key:
+            eng.prepare(state, False)
+            eng.prepared_key = key
+        out = torch.empty((x.shape[0], self.n_classes, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
+        eng.forward_infer(state, x, out, softmax)
+        return out
+
+    # ---- public surface
+    def forward(self, x):
+        """(N,C,H,W) fp32 -> raw logits (N,n_classes,H,W) fp32, as the reference (no softmax, unet.py:339-343)."""
+        if self.training:
+            x = self._prep_input(x)
+            if x.requires_grad:
+                raise RuntimeError("gradients w.r.t. the input echogram are not produced by the native path")
+            return _NativeUNetFunction.apply(x, self, *self._param_tensors())
+        return self._infer(x, softmax=False)
+
+    @torch.no_grad()
+    def predict_proba(self, x):
+        """Eval forward with the softmax of pipeline.py:218 fused into the last kernel."""
+        if self.training:
+            raise RuntimeError("predict_proba() is an eval-mode call; use model.eval() first")
+        return self._infer(x, softmax=True)
+
+    def train_step_fused(self, x, labels, class_weight, ignore_index=-100):
+        """Forward + class-weighted CE + backward in one native call (pipeline.py:171-177).
+
+        Fills ``p.grad`` of every parameter (views of one flat arena kept in ``self._grad_arena``) and returns the
+        loss as a 0-dim device tensor (no host sync)."""
+        if not self.training:
+            raise RuntimeError("train_step_fused() needs model.train()")
+        x = self._prep_input(x)
+        eng = self._engine_for(x, train=True)
+        params = self._param_tensors()
+        arena = getattr(self, "_grad_arena", None)
+        total = sum(p.numel() for p in params)
+        if arena is None or arena.numel() != total or arena.device != x.device:
+            arena = torch.zeros(total, dtype=torch.float32, device=x.device)
+            self._grad_arena = arena
+            off = 0
+            for p in params:
+                p.grad = arena[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        grads = [p.grad for p in params]
+        loss3 = torch.empty(4, dtype=torch.float32, device=x.device)
+        state = eng.state_table(self._state_tensors())
+        eng.train_step(state, x, labels.contiguous().long(), class_weight.contiguous().float(), ignore_index,
+                       eng.grad_table(grads), loss3)
+        return loss3[0]
+
+
+class UNet_LateMetInject(UNet):
+    """Late metadata injection variant (reference unet.py:346-391). Not on the benchmark path: plain torch modules."""
+
+    def __init__(self, n_classes, in_channels, meta_in_channels, late_meta_inject=True, depth=5, start_filts=64,
+                 up_mode="transpose", merge_mode="concat"):
+        super().__init__(n_classes, in_channels, meta_in_channels, late_meta_inject, depth, start_filts, up_mode, merge_mode)
+        self.conv_final = conv1x1(65, 3)  # hard-coded in the reference as well (unet.py:370)
+
+    def forward(self, x, meta_tensor):
+        feats = self._features_torch(x)
+        return self.conv_final(torch.cat((feats, self.post_processing_weights(meta_tensor)), 1))
+
+
+if __name__ == "__main__":
+    pass

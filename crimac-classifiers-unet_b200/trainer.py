@@ -1,0 +1,60 @@
+"""Data-parallel training loop body for the native U-Net (reference pipeline_train_predict/pipeline.py:144-203:
+SGD(lr, momentum) + ExponentialLR, one optimizer step per batch).
+
+One process per GPU.  Parameters and gradients live in two flat fp32 arenas so that the gradient exchange is ONE
+NCCL all-reduce over NVLink (the path has no other collective: BatchNorm statistics stay per replica, as in the
+reference which has no SyncBN) and the optimizer is one fused kernel.  Semantics = DistributedDataParallel: the
+update uses the mean over replicas of the per-replica (weighted-mean) loss gradients.
+"""
+import torch
+import torch.distributed as dist
+
+from . import engine as _engine
+
+
+def reduce_gradients(flat_grads, world):
+    """Sum the flat gradient arena over all replicas (NCCL on GPUs, gloo in the CPU tests) and return the factor that
+    turns the sum into the DDP mean; the factor is folded into the SGD kernel instead of a separate scaling pass."""
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+    return 1.0 / world
+
+
+class Trainer:
+    def __init__(self, model, lr=0.005, momentum=0.95, lr_reduction=0.5, lr_step=1000, class_weight=(10.0, 300.0, 250.0)):
+        # defaults: reference configs/config_baseline.yaml:28-31,38 and pipeline.py:135
+        self.model = model
+        self.lr, self.momentum = float(lr), float(momentum)
+        self.lr_reduction, self.lr_step = float(lr_reduction), int(lr_step)
+        self.iteration = 0
+        params = list(model.parameters())
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat_params = torch.empty(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:  # re-seat every parameter as a view of the arena (values preserved)
+            n = p.numel()
+            self.flat_params[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_params[off:off + n].view_as(p)
+            off += n
+        self.flat_momentum = torch.zeros_like(self.flat_params)
+        self.class_weight = torch.tensor(class_weight, dtype=torch.float32, device=dev)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def broadcast_parameters(self, src=0):
+        """Make every replica start from rank `src`'s weights and BN buffers."""
+        if self.world > 1:
+            dist.broadcast(self.flat_params, src)
+            for b in self.model.buffers():
+                dist.broadcast(b, src)
+
+    def step(self, x, labels):
+        """One optimisation step on device tensors; returns the replica's loss as a 0-dim device tensor."""
+        loss = self.model.train_step_fused(x, labels, self.class_weight)
+        grads = self.model._grad_arena
+        gscale = reduce_gradients(grads, self.world)  # NCCL over NVLink / NVSwitch
+        _engine.sgd_step(self.flat_params, self.flat_momentum, grads, self.lr, self.momentum, gscale)
+        self.iteration += 1
+        if self.lr_step > 0 and self.iteration % self.lr_step == 0:
+            self.lr *= self.lr_reduction  # ExponentialLR stepped every lr_step iterations (pipeline.py:157,188-189)
+        return loss

@@ -1,0 +1,125 @@
+/*
+ * crimac_b200.h — C ABI of libcrimac_b200.so: the B200 (sm_100a) implementation of the CRIMAC echogram U-Net hot path.
+ *
+ * The reference (CRIMAC-classifiers-unet) is pure Python/PyTorch and has NO native boundary of its own; the seam this
+ * library sits behind is the nn.Module stored in SegPipe.model.  Each entry point below names the reference call it
+ * replaces (paths relative to the reference's crimac_unet/ directory):
+ *
+ *   crimac_forward_infer   models/unet.py:327-343 (UNet_Baseline.forward, eval) + pipeline_train_predict/pipeline.py:218 (F.softmax)
+ *   crimac_forward_train   models/unet.py:327-343 under model.train()  (pipeline.py:167-171)
+ *   crimac_loss            pipeline.py:135-138,176 (nn.CrossEntropyLoss(weight=[10,300,250]))
+ *   crimac_backward        pipeline.py:177 (loss.backward(): autograd of every layer of models/unet.py)
+ *   crimac_train_step      pipeline.py:171-177 in one call
+ *   crimac_sgd_step        pipeline.py:156,178 (optim.SGD(momentum) step)
+ *   crimac_preprocess      batch/dataset.py:192-205 + utils/np.py:362-375 + batch/data_transforms/{remove_nan_inf,db_with_limits}.py
+ *   crimac_stitch          pipeline_train_predict/save_predict.py:41-65 (fill_out_array) + label masks of
+ *                          batch/label_transforms/mask_label_{overlap,seabed}.py
+ *   crimac_op_* / crimac_dbg_*   single-kernel entry points used by the parity tests only.
+ *
+ * Conventions: every function returns 0 on success, 1 for an invalid argument, 2 for a CUDA failure;
+ * crimac_last_error() returns a thread-local description.  All pointers named *_dev are device pointers owned by the
+ * caller (PyTorch); `stream` is a cudaStream_t.  The library never allocates device memory, never synchronises and
+ * never falls back to the CPU.  One context per (process, device); calls on one context are not re-entrant.
+ *
+ * Parameter tables.  `state` is an array of 136 device pointers in the order of UNet_Baseline.state_dict()
+ * (SURVEY.md App. B): for each encoder block i: main.0.{weight,bias}, main.1.{weight,bias,running_mean,running_var,
+ * num_batches_tracked}, main.3.{weight,bias}, main.4.{...5}; for each decoder block j: upconv.{weight,bias},
+ * conv1.{weight,bias}, conv2.{weight,bias}, bn1.{weight,bias,running_mean,running_var,num_batches_tracked}, bn2.{...5};
+ * then conv_final.{weight,bias}.  fp32 except num_batches_tracked (int64).  `grads` is an array of 82 fp32 device
+ * pointers in the order of UNet_Baseline.parameters() (the same list without the BN buffers).
+ */
+#ifndef CRIMAC_B200_H
+#define CRIMAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crimac_ctx crimac_ctx;
+
+typedef struct crimac_config {
+  int in_channels;   /* frequencies, 1..8                                   (unet.py:200 in_channels) */
+  int n_classes;     /* 1..8                                                (unet.py:200 n_classes)   */
+  int depth;         /* encoder blocks, 2..5 (reference default 5)          (unet.py:206)             */
+  int start_filts;   /* must be 64                                          (unet.py:207)             */
+  int max_batch;     /* largest batch a call may pass                                                 */
+  int height, width; /* patch size, multiples of 2^(depth-1) * 8 ... see crimac_create                */
+  int train;         /* 1: allocate saved activations + gradient scratch for forward_train/backward   */
+} crimac_config;
+
+const char* crimac_last_error(void);
+int crimac_state_count(const crimac_config* cfg); /* 136 for depth 5 */
+int crimac_grad_count(const crimac_config* cfg);  /* 82 for depth 5  */
+
+int crimac_workspace_bytes(const crimac_config* cfg, size_t* bytes);
+int crimac_create(crimac_ctx** ctx, const crimac_config* cfg, void* workspace_dev, size_t workspace_bytes, int device);
+int crimac_destroy(crimac_ctx* ctx);
+
+/* Re-pack fp32 parameters into the bf16 GEMM operands (and, for train==0, fold BatchNorm running statistics into the
+ * conv epilogue).  Must be called after every change of the parameters and before the forward call that uses them. */
+int crimac_prepare(crimac_ctx* ctx, const void* const* state, int train, void* stream);
+
+/* x_dev: fp32 NCHW (nb, in_channels, H, W).  out_dev: fp32 NCHW (nb, n_classes, H, W): class probabilities
+ * (softmax != 0) or raw logits. */
+int crimac_forward_infer(crimac_ctx* ctx, const void* const* state, const float* x_dev, int nb, float* out_dev,
+                         int softmax, void* stream);
+/* Train-mode forward (batch statistics, running-stat update, activations kept for backward). logits_dev as above. */
+int crimac_forward_train(crimac_ctx* ctx, const void* const* state, const float* x_dev, int nb, float* logits_dev,
+                         void* stream);
+/* Class-weighted cross-entropy with ignore_index.  labels_dev: int64 (nb,H,W).  out3_dev: {loss, 1/sum_w, sum_w}.
+ * dlogits_dev (optional): UNNORMALISED gradient w[y]*(softmax-onehot); multiply by out3[1] (crimac_backward does). */
+int crimac_loss(crimac_ctx* ctx, const float* logits_dev, const int64_t* labels_dev, const float* class_w_dev,
+                int64_t ignore_index, int nb, float* out3_dev, float* dlogits_dev, void* stream);
+/* Backward of the last crimac_forward_train.  dlogits_dev: fp32 NCHW gradient of the loss w.r.t. the logits;
+ * gscale_dev (optional) points at one device float multiplied into it.  Writes (not accumulates) all 82 gradients. */
+int crimac_backward(crimac_ctx* ctx, const void* const* state, const float* x_dev, const float* dlogits_dev,
+                    const float* gscale_dev, int nb, float* const* grads, void* stream);
+/* prepare(train) + forward_train + loss + backward.  loss3_dev as crimac_loss. */
+int crimac_train_step(crimac_ctx* ctx, const void* const* state, const float* x_dev, const int64_t* labels_dev,
+                      const float* class_w_dev, int64_t ignore_index, int nb, float* const* grads, float* loss3_dev,
+                      void* stream);
+
+/* SGD with momentum on flat fp32 arrays: v = momentum*v + g*gscale ; p -= lr*v   (torch.optim.SGD, dampening 0). */
+int crimac_sgd_step(float* params_dev, float* momentum_dev, const float* grads_dev, size_t n, float lr, float momentum,
+                    float gscale, void* stream);
+
+/* Patch gather + sv->dB transform.  sv_dev: fp32 (F, R, P) preloaded pings [frequency][range][ping] whose column 0 is
+ * survey ping data_ping0; centres_dev: int32 (n,2) patch centres (y, x) in survey coordinates (batch/samplers/
+ * gridded.py:22-54); out_dev: fp32 NCHW (n, F, ph, pw) = clip(10*log10(sv+1e-10), -75, 0) with out-of-data and
+ * non-finite samples -> 0 before the transform; nan_dev (optional) uint8 (n, ph, pw) = 1 where frequency 0 was
+ * non-finite (the pixels remove_nan_inf marks LABEL_IGNORE_VAL). */
+int crimac_preprocess(const float* sv_dev, int F, int R, int P, int data_ping0, const int32_t* centres_dev, int n,
+                      int ph, int pw, float* out_dev, uint8_t* nan_dev, void* stream);
+/* Overlap-stitch (fill_out_array): for every patch pixel whose label would not be one of {-70 overlap frame,
+ * -50 below seabed+pad on background, -100 outside [ping_start, ping_start+Pc) x [0,R) or non-finite}, write
+ * probs[:, cls[k]] as fp16 into out_dev (K, R, Pc).  labels_dev: optional int16 (R, Pc) chunk labels after the
+ * label-only transforms (NULL = all background); seabed_dev: optional int32 (Pc) first below-seabed range index per
+ * ping (NULL = no seabed mask); cls: HOST array of K (<=4) class indices. Pixels never written keep their value. */
+int crimac_stitch(const float* probs_dev, int n, int n_classes, int ph, int pw, const int32_t* centres_dev,
+                  const uint8_t* nan_dev, const int16_t* labels_dev, const int32_t* seabed_dev, int seabed_pad,
+                  int overlap, int ping_start, int Pc, int R, const int32_t* cls, int K, void* out_dev, void* stream);
+
+/* ---- measurement aids (bench.py): launch counter and per-launch CUDA-event timing of the network-level calls */
+unsigned long long crimac_launch_count(void);      /* kernels launched by this process through the library so far */
+int crimac_profile_enable(int on);                 /* clears earlier records; on!=0 brackets every launch with events */
+int crimac_profile_read(const char** names, float* ms, double* flops, double* bytes, int* launches, int cap);
+
+/* ---- single-kernel entry points (parity tests) */
+int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, int cin, int x_pitch, const void* w, int n_total,
+                    const float* scale, const float* shift, int relu, void* out, int out_pitch, int convt_cout,
+                    void* pool_out, int pool_pitch, float* stats, const float* head_w, const float* head_b,
+                    float* head_out, int n_classes, int head_softmax, int block_n, void* stream);
+int crimac_op_wgrad(int mode, const void* f, int f_pitch, int m_total, const void* t, int t_pitch, int n_total, int NB,
+                    int H, int W, float* scratch, float* dw, int splits, int block_n, void* stream);
+int crimac_dbg_umma(const void* image_dev, int image_bytes, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                    int n_mma, int a_step_bytes, int b_step_bytes, float* out_dev, int N, void* stream);
+int crimac_dbg_tma_box(const void* x_dev, int NB, int H, int W, int C, int pitch, int box_h, int sub, int ky, int kx,
+                       int c0, int x0, int y0, int n0, void* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRIMAC_B200_H */

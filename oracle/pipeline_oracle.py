@@ -1,0 +1,142 @@
+"""ORACLE (test infrastructure, not product code): numpy restatement of the reference's CPU steps either side of
+the U-Net — patch grid, preload gather + sv->dB transform, label masks and the overlap stitcher.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file.
+Pinned against the reference's own functions (driven by a fake in-memory reader) by oracle/make_golden.py ->
+tests/golden/pipeline_*.npz.  Paths cited are relative to /root/reference/crimac_unet/.
+"""
+import numpy as np
+
+LABEL_IGNORE_VAL = -100        # constants.py:25
+LABEL_BOUNDARY_VAL = -100      # constants.py:26
+LABEL_OVERLAP_VAL = -70        # constants.py:27
+LABEL_SEABED_MASK_VAL = -50    # constants.py:28
+BACKGROUND, SANDEEL, OTHER = 0, 1, 2   # constants.py:20-22
+
+
+def get_data_split(valid_ping_ranges, max_n_pings=1000):
+    """utils/preload_data_split.py:22-30: equal chunks via np.linspace(...).astype(int)."""
+    splits = []
+    for start, end in valid_ping_ranges:
+        n_splits = int(np.ceil((end - start) / max_n_pings))
+        edges = np.linspace(start, end, n_splits + 1).astype(int)
+        splits.extend([[edges[i], edges[i + 1]] for i in range(n_splits)])
+    return np.array(splits)
+
+
+def get_data_grid(start_ping, end_ping, start_range, end_range, patch_size=(256, 256), patch_overlap=20):
+    """batch/samplers/gridded.py:22-54 (mode 'all'): centres (y, x), all x for the first y, then the next y.
+    NB the reference unpacks (patch_width, patch_height) = patch_size (gridded.py:37); square patches only here."""
+    pw, ph = patch_size
+    ys = np.arange(start_range - (patch_overlap + 1), end_range - (patch_overlap + 1), ph - 2 * patch_overlap) + ph // 2
+    xs = np.arange(start_ping - (patch_overlap + 1), end_ping - (patch_overlap + 1), pw - 2 * patch_overlap) + pw // 2
+    return np.array(np.meshgrid(ys, xs)).T.reshape(-1, 2)
+
+
+def end_range_from_seabed(R, seabed_idx):
+    """gridded.py:151-159: range limited to the deepest seabed in the chunk + 50."""
+    return int(min(R, int(np.max(seabed_idx)) + 50))
+
+
+def preload_extents(grid, n_pings_total, patch_w):
+    """batch/dataset.py:176-177: pings [first_cx - w/2, last_cx + w/2) clipped to the survey."""
+    return max(0, int(grid[0, 1]) - patch_w // 2), min(n_pings_total, int(grid[-1, 1]) + patch_w // 2)
+
+
+def patch_offsets(n):
+    """utils/np.py:40-46 getGrid for one axis: -((n+1)//2)+1 .. n//2."""
+    return np.arange(-((n + 1) // 2) + 1, n // 2 + 1)
+
+
+def gather_data(sv, centre, data_ping0, patch_hw):
+    """dataset.py:192-205 + utils/np.py:362-375 (new_get_crop_3d, boundary 0): sv is (F, R, P) [freq][range][ping]."""
+    ph, pw = patch_hw
+    ys = centre[0] + patch_offsets(ph)
+    xs = centre[1] - data_ping0 + patch_offsets(pw)
+    yy, xx = np.meshgrid(ys, xs, indexing="ij")
+    oob = (yy < 0) | (xx < 0) | (yy >= sv.shape[1]) | (xx >= sv.shape[2])
+    yc, xc = np.where(oob, 0, yy), np.where(oob, 0, xx)
+    out = sv[:, yc, xc].copy()
+    out[:, oob] = 0
+    return out
+
+
+def gather_labels(labels, centre, label_ping0, patch_hw):
+    """dataset.py:196-198 + utils/np.py:347-360 (new_get_crop_2d, boundary LABEL_BOUNDARY_VAL): labels (R, Pc)."""
+    ph, pw = patch_hw
+    ys = centre[0] + patch_offsets(ph)
+    xs = centre[1] - label_ping0 + patch_offsets(pw)
+    yy, xx = np.meshgrid(ys, xs, indexing="ij")
+    oob = (yy < 0) | (xx < 0) | (yy >= labels.shape[0]) | (xx >= labels.shape[1])
+    out = labels[np.where(oob, 0, yy), np.where(oob, 0, xx)].copy()
+    out[oob] = LABEL_BOUNDARY_VAL
+    return out
+
+
+def data_transform(data, labels):
+    """remove_nan_inf.py:23-34 then db_with_limits.py:20-24,36-38."""
+    labels = labels.copy()
+    labels[~np.isfinite(data[0])] = LABEL_IGNORE_VAL
+    data = data.copy()
+    data[~np.isfinite(data)] = 0.0
+    db = 10 * np.log10(data + 1e-10)
+    db[db > 0] = 0
+    db[db < -75] = -75
+    return db, labels
+
+
+def mask_seabed(labels, centre, seabed_idx_survey, R, n_pings_total, pad=10):
+    """mask_label_seabed.py:32-68 with a per-ping seabed index (mask[y] = y >= seabed[x]); the +pad shift happens
+    inside the patch's clipped range window (data_reader.py:839-843)."""
+    ph, pw = labels.shape
+    y_upper, x_left = centre[0] - ph // 2 + 1, centre[1] - pw // 2 + 1
+    y_lower, x_right = centre[0] + ph // 2 + 1, centre[1] + pw // 2 + 1
+    sxl, syu = max(x_left, 0), max(y_upper, 0)
+    sxr, syl = min(x_right, n_pings_total), min(y_lower, R)
+    rng = np.arange(syu, syl)[:, None]
+    m = (rng >= np.asarray(seabed_idx_survey[sxl:sxr])[None, :]).astype(np.int8)      # (range, ping) window
+    mp = np.zeros_like(m)
+    if pad:
+        mp[pad:, :] = m[:-pad, :]
+    else:
+        mp = m
+    full = np.zeros_like(labels)
+    full[syu - y_upper:syu - y_upper + mp.shape[0], sxl - x_left:sxl - x_left + mp.shape[1]] = mp
+    out = labels.copy()
+    out[full.astype(bool) & (labels == BACKGROUND)] = LABEL_SEABED_MASK_VAL
+    return out
+
+
+def mask_overlap(labels, overlap):
+    """mask_label_overlap.py:31-48."""
+    if overlap == 0:
+        return labels
+    out = np.ones_like(labels) * LABEL_OVERLAP_VAL
+    out[overlap:-overlap, overlap:-overlap] = labels[overlap:-overlap, overlap:-overlap]
+    out[labels == LABEL_BOUNDARY_VAL] = LABEL_BOUNDARY_VAL
+    return out
+
+
+def fill_out_array(out_array, probs, labels, centre, ping_start, classes=(SANDEEL, OTHER)):
+    """save_predict.py:41-65."""
+    sel = np.argwhere((labels != LABEL_OVERLAP_VAL) & (labels != LABEL_SEABED_MASK_VAL) & (labels != LABEL_BOUNDARY_VAL))
+    if len(sel) == 0:
+        return out_array
+    yl, xl = sel.T
+    ya = yl + centre[0] - labels.shape[0] // 2 + 1
+    xa = xl + centre[1] - labels.shape[1] // 2 + 1 - ping_start
+    out_array[:, ya, xa] = probs[list(classes)][:, yl, xl]
+    return out_array
+
+
+def patch_item(sv_preload, data_ping0, labels_chunk, ping_start, centre, seabed_idx_survey, R, n_pings_total,
+               patch_hw=(256, 256), overlap=20):
+    """DatasetGriddedReader.__getitem__ (dataset.py:207-242) with save_predict's transforms (save_predict.py:149-150,
+    batch/transforms.py:48-54,78-92; the label-only transforms convert_label_indexing_unused_species /
+    refine_label_boundary are assumed applied to labels_chunk already). Returns (data fp32, labels int16)."""
+    data = gather_data(sv_preload, centre, data_ping0, patch_hw)
+    labels = gather_labels(labels_chunk, centre, ping_start, patch_hw)
+    labels = mask_seabed(labels, centre, seabed_idx_survey, R, n_pings_total)
+    labels = mask_overlap(labels, overlap)
+    data, labels = data_transform(data, labels)
+    return data.astype(np.float32), labels.astype(np.int16)

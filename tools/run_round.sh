@@ -1,0 +1,14 @@
+#!/bin/bash
+# GPU-box round script: parity tests, headline bench (train) + inference bench, per-kernel breakdowns.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 1200 python -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 3 --profile-out gpurun_out/breakdown_train.csv > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
+echo "bench train exit $?"; cat gpurun_out/bench_train.json; tail -5 gpurun_out/bench_train.err
+cat gpurun_out/breakdown_train.csv
+timeout 300 python bench.py --mode infer --steps 20 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/breakdown_infer.csv > gpurun_out/bench_infer.json 2> gpurun_out/bench_infer.err
+echo "bench infer exit $?"; cat gpurun_out/bench_infer.json; tail -5 gpurun_out/bench_infer.err
+cat gpurun_out/breakdown_infer.csv
