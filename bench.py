@@ -248,6 +248,9 @@ def run_b200(args):
             f.write("family,ms,share,TFLOP/s,GB/s,launches\n")
             for k, a in sorted(fam.items(), key=lambda kv: -kv[1][0]):
                 f.write(f"\"{k}\",{a[0]:.4f},{a[0] / step_kernel_ms:.4f},{a[1] / max(a[0], 1e-9) / 1e9:.1f},{a[2] / max(a[0], 1e-9) / 1e6:.1f},{a[3]}\n")
+            f.write("# per launch, in issue order: name,ms,GFLOP,TFLOP/s,GB/s\n")
+            for name, ms, fl, by, ln in recs:
+                f.write(f"{name},{ms:.4f},{fl / 1e9:.3f},{fl / max(ms, 1e-9) / 1e9:.1f},{by / max(ms, 1e-9) / 1e6:.1f}\n")
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

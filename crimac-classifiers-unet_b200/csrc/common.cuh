@@ -46,7 +46,7 @@ struct ConvParams {
   const float* shift;    // [N_total]
   bf16* pool_out;        // optional (EPI_STORE): 2x2 max-pooled copy, H/2 x W/2
   int pool_pitch;
-  float* stats;          // EPI_STATS: [m_tiles][2][N_total] partial sums
+  float* stats;          // EPI_STATS: [gridDim.x][2][N_total] per-CTA partial sums (sum, sum of squares)
   // EPI_HEAD
   const float* head_w;   // [n_classes][64]
   const float* head_b;   // [n_classes]

@@ -29,8 +29,9 @@ struct ConvCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int MAX_STAT_CH = 1024;  // per-CTA running channel sums (EPI_STATS), all n-tiles
   static constexpr int AUX_BYTES = 256 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
-                                   (CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4;
+                                   (CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 + 2 * MAX_STAT_CH * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
 };
 
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   float* s_affine = reinterpret_cast<float*>(aux + 256);  // [2 acc stages][scale BLOCK_N | shift BLOCK_N]
   float* s_red = s_affine + 4 * BLOCK_N;                  // [4 warps][2][BLOCK_N]
   float* s_head = s_red + 8 * BLOCK_N;                    // [ncls][64] + [ncls]
+  float* s_acc = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2][n_total] CTA-lifetime channel sums
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,6 +74,9 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   if (warp == 2) {
     ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (EPI == EPI_STATS && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < 2 * p.n_tiles * BLOCK_N; i += 128) s_acc[i] = 0.f;
   }
   if (EPI == EPI_HEAD && warp >= 4) {
     const int e = threadIdx.x - 128;
@@ -291,9 +296,9 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
             a += s_red[(w * 2 + 0) * BLOCK_N + c];
             b += s_red[(w * 2 + 1) * BLOCK_N + c];
           }
-          float* dst = p.stats + static_cast<long>(m_tile_id) * 2 * n_total;
-          dst[n0 + c] = a;
-          dst[n_total + n0 + c] = b;
+          // channel c of this n-tile always belongs to this thread: no race on the CTA-lifetime accumulators
+          s_acc[n0 + c] += a;
+          s_acc[n_total + n0 + c] += b;
         }
       }
 
@@ -322,6 +327,12 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     }
   }
 
+  if (EPI == EPI_STATS && warp >= 4) {
+    // one partial row per CTA: stats[blockIdx.x][2][n_total]; bn_finalize sums gridDim.x rows
+    const int n2 = 2 * p.n_tiles * BLOCK_N;
+    epi_bar();
+    for (int i = threadIdx.x - 128; i < n2; i += 128) p.stats[static_cast<long>(blockIdx.x) * n2 + i] = s_acc[i];
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {

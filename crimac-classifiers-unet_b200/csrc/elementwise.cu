@@ -12,29 +12,32 @@ namespace {
 constexpr int kMaxBlocks = 148 * 8;
 
 // ============================================================================ first conv (fp32 NCHW in -> 64 ch)
-// One thread = one pixel of an 8x16 tile (same tile numbering as conv_igemm so the statistics buffers line up).
+// One thread = TWO horizontally adjacent pixels of an 8x16 tile (64 threads per tile): every broadcast LDS.128 of four
+// weights feeds 8 FFMAs, which keeps the kernel FFMA-bound instead of shared-memory-bound.  Train mode accumulates the
+// channel statistics of the stored (bf16-rounded) values per block: stats[blockIdx.x][2][64].
 template <int CIN>
-__global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ scale,
-                                                         const float* __restrict__ shift, int relu, int NB, int H, int W,
-                                                         bf16* __restrict__ out, int out_pitch, float* stats) {
+__global__ void __launch_bounds__(64) first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int relu, int NB, int H, int W,
+                                                        bf16* __restrict__ out, int out_pitch, float* stats) {
   constexpr int K = CIN * 9;
   __shared__ __align__(16) float ws[K * 64];  // [k][co]
   __shared__ float s_sc[64], s_sh[64];
-  __shared__ float s_red[4][2][64];
-  for (int i = threadIdx.x; i < K * 64; i += 128) {
+  __shared__ float s_red[2][2][64];
+  __shared__ float s_acc[2][64];
+  for (int i = threadIdx.x; i < K * 64; i += 64) {
     const int co = i & 63, k = i >> 6;
     ws[i] = w[co * K + k];
   }
-  if (threadIdx.x < 64) {
-    s_sc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f;
-    s_sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
-  }
+  s_sc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f;
+  s_sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
+  s_acc[0][threadIdx.x] = 0.f;
+  s_acc[1][threadIdx.x] = 0.f;
   __syncthreads();
   const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
   const int total = NB * tiles_x * tiles_y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int py = threadIdx.x >> 4, px = threadIdx.x & 15;
+  const int py = threadIdx.x >> 3, px = (threadIdx.x & 7) * 2;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     int t = tile;
     const int tx = t % tiles_x;
@@ -42,61 +45,83 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict
     const int ty = t % tiles_y;
     const int img = t / tiles_y;
     const int y = ty * TILE_H + py, xx = tx * TILE_W + px;
-    const bool valid = y < H && xx < W;
-    float in[K];
+    const bool valid0 = y < H && xx < W, valid1 = y < H && xx + 1 < W;
+    // 3 rows x 4 columns of inputs per frequency cover both pixels' 3x3 windows
+    float in[CIN][3][4];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yy = y + tap / 3 - 1, xq = xx + tap % 3 - 1;
-        const bool ok = valid && yy >= 0 && yy < H && xq >= 0 && xq < W;
-        in[ci * 9 + tap] = ok ? __ldg(&x[((static_cast<long>(img) * CIN + ci) * H + yy) * W + xq]) : 0.f;
-      }
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int yy = y + r - 1, xq = xx + c - 1;
+          const bool ok = yy >= 0 && yy < H && xq >= 0 && xq < W;
+          in[ci][r][c] = ok ? __ldg(&x[((static_cast<long>(img) * CIN + ci) * H + yy) * W + xq]) : 0.f;
+        }
     bf16* dst = out + ((static_cast<long>(img) * H + y) * W + xx) * out_pitch;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      float acc[32];
+      float a0[32], a1[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 32; ++j) a0[j] = a1[j] = 0.f;
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float4* wr = reinterpret_cast<const float4*>(&ws[k * 64 + half * 32]);
+      for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 wv = wr[j4];
-          acc[4 * j4 + 0] = fmaf(in[k], wv.x, acc[4 * j4 + 0]);
-          acc[4 * j4 + 1] = fmaf(in[k], wv.y, acc[4 * j4 + 1]);
-          acc[4 * j4 + 2] = fmaf(in[k], wv.z, acc[4 * j4 + 2]);
-          acc[4 * j4 + 3] = fmaf(in[k], wv.w, acc[4 * j4 + 3]);
+        for (int tap = 0; tap < 9; ++tap) {
+          const float v0 = in[ci][tap / 3][tap % 3], v1 = in[ci][tap / 3][tap % 3 + 1];
+          const float4* wr = reinterpret_cast<const float4*>(&ws[(ci * 9 + tap) * 64 + half * 32]);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = wr[j4];
+            a0[4 * j4 + 0] = fmaf(v0, wv.x, a0[4 * j4 + 0]);
+            a0[4 * j4 + 1] = fmaf(v0, wv.y, a0[4 * j4 + 1]);
+            a0[4 * j4 + 2] = fmaf(v0, wv.z, a0[4 * j4 + 2]);
+            a0[4 * j4 + 3] = fmaf(v0, wv.w, a0[4 * j4 + 3]);
+            a1[4 * j4 + 0] = fmaf(v1, wv.x, a1[4 * j4 + 0]);
+            a1[4 * j4 + 1] = fmaf(v1, wv.y, a1[4 * j4 + 1]);
+            a1[4 * j4 + 2] = fmaf(v1, wv.z, a1[4 * j4 + 2]);
+            a1[4 * j4 + 3] = fmaf(v1, wv.w, a1[4 * j4 + 3]);
+          }
         }
-      }
-      uint32_t pk[16];
+      uint32_t pk0[16], pk1[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float a = acc[2 * j] * s_sc[half * 32 + 2 * j] + s_sh[half * 32 + 2 * j];
-        float b = acc[2 * j + 1] * s_sc[half * 32 + 2 * j + 1] + s_sh[half * 32 + 2 * j + 1];
+        const float sa = s_sc[half * 32 + 2 * j], sb = s_sc[half * 32 + 2 * j + 1];
+        const float ha = s_sh[half * 32 + 2 * j], hb = s_sh[half * 32 + 2 * j + 1];
+        float p0 = a0[2 * j] * sa + ha, p1 = a0[2 * j + 1] * sb + hb;
+        float q0 = a1[2 * j] * sa + ha, q1 = a1[2 * j + 1] * sb + hb;
         if (relu) {
-          a = fmaxf(a, 0.f);
-          b = fmaxf(b, 0.f);
+          p0 = fmaxf(p0, 0.f);
+          p1 = fmaxf(p1, 0.f);
+          q0 = fmaxf(q0, 0.f);
+          q1 = fmaxf(q1, 0.f);
         }
-        pk[j] = pack_bf16x2(a, b);
+        pk0[j] = pack_bf16x2(p0, p1);
+        pk1[j] = pack_bf16x2(q0, q1);
       }
-      if (valid) {
-        store16(dst + half * 32, pk);
-        store16(dst + half * 32 + 8, pk + 4);
-        store16(dst + half * 32 + 16, pk + 8);
-        store16(dst + half * 32 + 24, pk + 12);
+      if (valid0) {
+        store16(dst + half * 32, pk0);
+        store16(dst + half * 32 + 8, pk0 + 4);
+        store16(dst + half * 32 + 16, pk0 + 8);
+        store16(dst + half * 32 + 24, pk0 + 12);
+      }
+      if (valid1) {
+        store16(dst + out_pitch + half * 32, pk1);
+        store16(dst + out_pitch + half * 32 + 8, pk1 + 4);
+        store16(dst + out_pitch + half * 32 + 16, pk1 + 8);
+        store16(dst + out_pitch + half * 32 + 24, pk1 + 12);
       }
       if (stats != nullptr) {
         float s1[32], s2[32];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float2 v = unpack_bf16x2(pk[j]);
-          const float a = valid ? v.x : 0.f, b = valid ? v.y : 0.f;
-          s1[2 * j] = a;
-          s1[2 * j + 1] = b;
-          s2[2 * j] = a * a;
-          s2[2 * j + 1] = b * b;
+          const float2 u = unpack_bf16x2(pk0[j]), v = unpack_bf16x2(pk1[j]);
+          const float ua = valid0 ? u.x : 0.f, ub = valid0 ? u.y : 0.f;
+          const float va = valid1 ? v.x : 0.f, vb = valid1 ? v.y : 0.f;
+          s1[2 * j] = ua + va;
+          s1[2 * j + 1] = ub + vb;
+          s2[2 * j] = ua * ua + va * va;
+          s2[2 * j + 1] = ub * ub + vb * vb;
         }
         xpose_reduce(s1, lane);
         xpose_reduce(s2, lane);
@@ -106,19 +131,15 @@ __global__ void __launch_bounds__(128) first_conv_kernel(const float* __restrict
     }
     if (stats != nullptr) {
       __syncthreads();
-      if (threadIdx.x < 64) {
-        const int c = threadIdx.x;
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < 4; ++wv) {
-          a += s_red[wv][0][c];
-          b += s_red[wv][1][c];
-        }
-        stats[static_cast<long>(tile) * 128 + c] = a;
-        stats[static_cast<long>(tile) * 128 + 64 + c] = b;
-      }
+      const int c = threadIdx.x;
+      s_acc[0][c] += s_red[0][0][c] + s_red[1][0][c];
+      s_acc[1][c] += s_red[0][1][c] + s_red[1][1][c];
       __syncthreads();
     }
+  }
+  if (stats != nullptr) {
+    stats[static_cast<long>(blockIdx.x) * 128 + threadIdx.x] = s_acc[0][threadIdx.x];
+    stats[static_cast<long>(blockIdx.x) * 128 + 64 + threadIdx.x] = s_acc[1][threadIdx.x];
   }
 }
 
@@ -400,28 +421,16 @@ __global__ void head_bwd_finalize_kernel(const float* partials, int nparts, int 
 }
 
 // ============================================================================ BN + ReLU backward
-// Thread = fixed 8-channel group, grid-stride over pixels; per-block partial sums [blocks][NQ][C].
-// phase 1 (reduce): g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * xhat
-template <int NQ, typename F>
-__device__ __forceinline__ void channel_reduce(int C, long npix, float* partials, F&& per_pixel) {
+// Thread = fixed 8-channel group (its per-channel constants stay in registers), grid-stride over pixels; the block's
+// partial sums go to partials[blockIdx.x][NQ][C] and are combined by a small parallel finalize kernel (deterministic).
+template <int NQ>
+__device__ __forceinline__ void block_channel_sums(const float (&acc)[NQ][8], int C, int g, int pl, int ppb,
+                                                   float* partials) {
   extern __shared__ float s_cr[];  // [ppb][NQ][C]
-  const int groups = C >> 3;
-  const int ppb = blockDim.x / groups;
-  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
-  float acc[NQ][8];
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
-  if (pl < ppb)
-    for (long p = static_cast<long>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<long>(gridDim.x) * ppb)
-      per_pixel(p, g, acc);
-  if (pl < ppb) {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s_cr[(pl * NQ + q) * C + g * 8 + j] = acc[q][j];
-  }
+    for (int j = 0; j < 8; ++j) s_cr[(pl * NQ + q) * C + g * 8 + j] = acc[q][j];
   __syncthreads();
   for (int i = threadIdx.x; i < NQ * C; i += blockDim.x) {
     float a = 0.f;
@@ -430,42 +439,83 @@ __device__ __forceinline__ void channel_reduce(int C, long npix, float* partials
   }
 }
 
+// phase 1: g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * xhat
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dact, View raw, const float* __restrict__ scale,
                                                             const float* __restrict__ shift,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, float* partials) {
+  const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
-  channel_reduce<2>(raw.C, npix, partials, [&](long p, int g, float(&acc)[2][8]) {
-    float d[8], r[8], sc[8], sh[8], mu[8], is[8];
-    load8(dact.ptr + p * dact.pitch + g * 8, d);
-    load8(raw.ptr + p * raw.pitch + g * 8, r);
-    ldg8f(scale + g * 8, sc);
-    ldg8f(shift + g * 8, sh);
-    ldg8f(mean + g * 8, mu);
-    ldg8f(invstd + g * 8, is);
+  float sc[8], sh[8], mu[8], is[8];
+  ldg8f(scale + g * 8, sc);
+  ldg8f(shift + g * 8, sh);
+  ldg8f(mean + g * 8, mu);
+  ldg8f(invstd + g * 8, is);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const long stride = static_cast<long>(gridDim.x) * ppb;
+  long p = static_cast<long>(blockIdx.x) * ppb + pl;
+  // two pixels per iteration: four independent 16-byte loads in flight per thread
+  for (; p + stride < npix; p += 2 * stride) {
+    float d0[8], r0[8], d1[8], r1[8];
+    load8(dact.ptr + p * dact.pitch + g * 8, d0);
+    load8(raw.ptr + p * raw.pitch + g * 8, r0);
+    load8(dact.ptr + (p + stride) * dact.pitch + g * 8, d1);
+    load8(raw.ptr + (p + stride) * raw.pitch + g * 8, r1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
-      acc[0][j] += gg;
-      acc[1][j] += gg * (r[j] - mu[j]) * is[j];
+      const float g0 = fmaf(r0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
+      const float g1 = fmaf(r1[j], sc[j], sh[j]) > 0.f ? d1[j] : 0.f;
+      acc[0][j] += g0 + g1;
+      acc[1][j] += g0 * (r0[j] - mu[j]) * is[j] + g1 * (r1[j] - mu[j]) * is[j];
     }
-  });
+  }
+  if (p < npix) {
+    float d0[8], r0[8];
+    load8(dact.ptr + p * dact.pitch + g * 8, d0);
+    load8(raw.ptr + p * raw.pitch + g * 8, r0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g0 = fmaf(r0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
+      acc[0][j] += g0;
+      acc[1][j] += g0 * (r0[j] - mu[j]) * is[j];
+    }
+  }
+  block_channel_sums<2>(acc, C, g, pl, ppb, partials);
 }
 
-// partials [nparts][2][C] -> dgamma, dbeta (fp32 grads) and the two per-channel means used by the apply pass
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count,
-                                       float* dgamma, float* dbeta, int accumulate, float* c1, float* c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0.0, b = 0.0;
-  for (int i = 0; i < nparts; ++i) {
-    a += partials[static_cast<long>(i) * 2 * C + c];
-    b += partials[static_cast<long>(i) * 2 * C + C + c];
+// partials [nparts][NQ][C] -> out_q[c] = sum over parts (block = 32 channels x 8 part-lanes)
+// NQ == 2: BN backward: dbeta = q0, dgamma = q1, c1 = q0/count, c2 = q1/count.  NQ == 1: plain column sum.
+template <int NQ>
+__global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* __restrict__ partials, int nparts, int C,
+                                                                   double count, float* out0, float* out1,
+                                                                   int accumulate, float* c1, float* c2) {
+  __shared__ double sh[NQ][8][32];
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) a[q] = 0.0;
+  if (c < C)
+    for (int i = tl; i < nparts; i += 8)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) a[q] += partials[(static_cast<long>(i) * NQ + q) * C + c];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) sh[q][tl][cl] = a[q];
+  __syncthreads();
+  if (tl == 0 && c < C) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      for (int t = 1; t < 8; ++t) a[q] += sh[q][t][cl];
+    out0[c] = accumulate ? out0[c] + static_cast<float>(a[0]) : static_cast<float>(a[0]);
+    if (NQ == 2) {
+      out1[c] = accumulate ? out1[c] + static_cast<float>(a[NQ - 1]) : static_cast<float>(a[NQ - 1]);
+      c1[c] = static_cast<float>(a[0] / count);
+      c2[c] = static_cast<float>(a[NQ - 1] / count);
+    }
   }
-  dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(a) : static_cast<float>(a);
-  dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(b) : static_cast<float>(b);
-  c1[c] = static_cast<float>(a / count);
-  c2[c] = static_cast<float>(b / count);
 }
 
 // phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) -> bf16; partial = sum dRaw (= the conv-bias gradient)
@@ -475,48 +525,62 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, 
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ c1, const float* __restrict__ c2,
                                                            View draw, float* partials) {
+  const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
-  channel_reduce<1>(raw.C, npix, partials, [&](long p, int g, float(&acc)[1][8]) {
-    float d[8], r[8], sc[8], sh[8], mu[8], is[8], k1[8], k2[8], o[8];
-    load8(dact.ptr + p * dact.pitch + g * 8, d);
-    load8(raw.ptr + p * raw.pitch + g * 8, r);
-    ldg8f(scale + g * 8, sc);
-    ldg8f(shift + g * 8, sh);
-    ldg8f(mean + g * 8, mu);
-    ldg8f(invstd + g * 8, is);
-    ldg8f(c1 + g * 8, k1);
-    ldg8f(c2 + g * 8, k2);
+  float sc[8], sh[8], mu[8], is[8], k1[8], k2[8];
+  ldg8f(scale + g * 8, sc);
+  ldg8f(shift + g * 8, sh);
+  ldg8f(mean + g * 8, mu);
+  ldg8f(invstd + g * 8, is);
+  ldg8f(c1 + g * 8, k1);
+  ldg8f(c2 + g * 8, k2);
+  float acc[1][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
-      const float xh = (r[j] - mu[j]) * is[j];
-      o[j] = sc[j] * (gg - k1[j] - xh * k2[j]);
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  const long stride = static_cast<long>(gridDim.x) * ppb;
+  for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += 2 * stride) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long p = p0 + u * stride;
+      if (p < npix) {
+        float d[8], r[8], o[8];
+        load8(dact.ptr + p * dact.pitch + g * 8, d);
+        load8(raw.ptr + p * raw.pitch + g * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
+          const float xh = (r[j] - mu[j]) * is[j];
+          o[j] = sc[j] * (gg - k1[j] - xh * k2[j]);
+        }
+        const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                    pack_bf16x2(o[6], o[7]));
+        *reinterpret_cast<uint4*>(draw.ptr + p * draw.pitch + g * 8) = pk;
+        // bias gradient from the rounded values, as the wgrad / dgrad kernels will see them
+        const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y), cc = unpack_bf16x2(pk.z), dd = unpack_bf16x2(pk.w);
+        acc[0][0] += a.x; acc[0][1] += a.y; acc[0][2] += b.x; acc[0][3] += b.y;
+        acc[0][4] += cc.x; acc[0][5] += cc.y; acc[0][6] += dd.x; acc[0][7] += dd.y;
+      }
     }
-    store8(draw.ptr + p * draw.pitch + g * 8, o);
-    float ob[8];
-    load8(draw.ptr + p * draw.pitch + g * 8, ob);  // the rounded values, as the wgrad/dgrad kernels will see them
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][j] += ob[j];
-  });
+  }
+  block_channel_sums<1>(acc, C, g, pl, ppb, partials);
 }
 
 // plain per-channel sum of a view (ConvTranspose bias gradient)
 __global__ void __launch_bounds__(256) view_colsum_kernel(View v, float* partials) {
+  const int C = v.C, groups = C >> 3, ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(v.N) * v.H * v.W;
-  channel_reduce<1>(v.C, npix, partials, [&](long p, int g, float(&acc)[1][8]) {
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (long p = static_cast<long>(blockIdx.x) * ppb + pl; p < npix; p += static_cast<long>(gridDim.x) * ppb) {
     float d[8];
     load8(v.ptr + p * v.pitch + g * 8, d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] += d[j];
-  });
-}
-__global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nparts, int C, float* out,
-                                       int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0.0;
-  for (int i = 0; i < nparts; ++i) a += partials[static_cast<long>(i) * C + c];
-  out[c] = accumulate ? out[c] + static_cast<float>(a) : static_cast<float>(a);
+  }
+  block_channel_sums<1>(acc, C, g, pl, ppb, partials);
 }
 
 // ============================================================================ max-pool backward + skip gradient
@@ -671,13 +735,16 @@ inline int grid_for(long work_items, int threads) {
 }  // namespace
 
 // ---------------------------------------------------------------------------- launchers (used by net_api.cu / ops_api2.cu)
+int first_conv_grid(int NB, int H, int W) {
+  const int tiles = NB * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
+  return tiles < 148 * 8 ? tiles : 148 * 8;
+}
 cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
                               int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st) {
-  const int tiles = NB * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
-  const int grid = tiles < 148 * 16 ? tiles : 148 * 16;
+  const int grid = first_conv_grid(NB, H, W);
 #define FC(C)                                                                                                   \
   if (cin == C) {                                                                                               \
-    first_conv_kernel<C><<<grid, 128, 0, st>>>(x, w, scale, shift, relu, NB, H, W, out, out_pitch, stats);      \
+    first_conv_kernel<C><<<grid, 64, 0, st>>>(x, w, scale, shift, relu, NB, H, W, out, out_pitch, stats);       \
     return cudaGetLastError();                                                                                  \
   }
   FC(1) FC(2) FC(3) FC(4) FC(5) FC(6) FC(7) FC(8)
@@ -693,7 +760,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 #define FW(C)                                                                                       \
   if (cin == C) {                                                                                   \
     first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
-    colsum_finalize_kernel<<<(64 * C * 9 + 255) / 256, 256, 0, st>>>(partials, grid, 64 * C * 9, dw, accumulate); \
+    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 31) / 32, 256, 0, st>>>(partials, grid, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
   FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
@@ -751,7 +818,7 @@ cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act,
   return cudaGetLastError();
 }
 
-int reduce_blocks() { return 148 * 4; }
+int reduce_blocks() { return 148 * 4; }  // 4 blocks of 256 threads per SM
 static int reduce_grid(const View& v) {
   const int ppb = 256 / (v.C / 8);
   const long px = static_cast<long>(v.N) * v.H * v.W;
@@ -770,11 +837,12 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
   bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, partials);
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, grid, C, count, dgamma, dbeta, accumulate, c1c2,
-                                                          c1c2 + C);
+  partial_sum_finalize_kernel<2><<<(C + 31) / 32, 256, 0, st>>>(partials, grid, C, count, dbeta, dgamma, accumulate, c1c2,
+                                                                c1c2 + C);
   bn_bwd_apply_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C,
                                                                   draw, partials);
-  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, grid, C, dbias, accumulate);
+  partial_sum_finalize_kernel<1><<<(C + 31) / 32, 256, 0, st>>>(partials, grid, C, 1.0, dbias, nullptr, accumulate, nullptr,
+                                                                nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
@@ -783,7 +851,8 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
   const int grid = reduce_grid(v);
   const int ppb = 256 / (C / 8);
   view_colsum_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(v, partials);
-  colsum_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partials, grid, C, out, accumulate);
+  partial_sum_finalize_kernel<1><<<(C + 31) / 32, 256, 0, st>>>(partials, grid, C, 1.0, out, nullptr, accumulate, nullptr,
+                                                                nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st) {

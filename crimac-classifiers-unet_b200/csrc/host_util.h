@@ -31,6 +31,7 @@ int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub = 0, int ky
 int make_weight_map(CUtensorMap* out, const bf16* w, int rows, int cols, int box_rows);
 
 cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num_sms, cudaStream_t stream);
+inline int conv_grid(int total_tiles, int num_sms) { return total_tiles < num_sms ? total_tiles : num_sms; }
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream);
 cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,
                                 cudaStream_t stream);
@@ -50,6 +51,7 @@ struct ProfScope {
 // ---- CUDA-core kernels (elementwise.cu)
 cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
                               int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st);
+int first_conv_grid(int NB, int H, int W);  // = rows of the statistics partials the kernel writes
 int first_conv_wgrad_blocks();
 cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
                                     cudaStream_t st);

@@ -244,9 +244,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     L.mean = bump.arr<float>(L.cout);
     L.invstd = bump.arr<float>(L.cout);
     if (train) L.raw = dense(L.level, L.cout);
-    const size_t mt = static_cast<size_t>(B) * ((level_h(c, L.level) + TILE_H - 1) / TILE_H) *
-                      ((level_w(c, L.level) + TILE_W - 1) / TILE_W);
-    if (mt * 2 * L.cout > max_stats) max_stats = mt * 2 * L.cout;
+    const size_t rows = L.first ? 148 * 8 : 256;  // >= first_conv_grid() / >= number of SMs (one partial row per CTA)
+    if (rows * 2 * L.cout > max_stats) max_stats = rows * 2 * L.cout;
     L.bn_fwd = pick_bn(L.cout);
     L.bn_bwd = pick_bn(L.cin);
     L.bn_wg = pick_bn(L.cin);
@@ -535,12 +534,13 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
   auto run_conv = [&](int idx) -> int {
     Conv3& L = c->conv[idx];
     const int H = level_h(c, L.level), W = level_w(c, L.level);
-    const int m_tiles = nb * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
+    int stat_rows = 0;  // partial rows written by the conv kernel (one per CTA)
     if (train) {
       View raw = with_batch(L.raw, nb);
       const double px = static_cast<double>(nb) * H * W;
       if (L.first) {
         ProfScope ps("first_conv", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st);
+        stat_rows = first_conv_grid(nb, H, W);
         CRIMAC_CHECK_CUDA(launch_first_conv(x, S<float>(state, L.s_w), nullptr, S<float>(state, L.s_b), 0, nb, L.cin, H,
                                             W, raw.ptr, raw.pitch, c->stats, st));
       } else {
@@ -552,12 +552,13 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
         p.shift = S<float>(state, L.s_b);
         p.relu = 0;
         p.stats = c->stats;
+        stat_rows = conv_grid(p.total_tiles, sms);
         ProfScope ps("conv3x3_fwd", igemm_flops_n(p, L.cout), px * 2.0 * (L.cin + L.cout), st);
         CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_fwd, EPI_STATS, sms, st));
       }
       {
       ProfScope ps("bn_finalize", 0, 0, st);
-      CRIMAC_CHECK_CUDA(launch_bn_finalize(c->stats, m_tiles, L.cout, static_cast<double>(nb) * H * W,
+      CRIMAC_CHECK_CUDA(launch_bn_finalize(c->stats, stat_rows, L.cout, static_cast<double>(nb) * H * W,
                                            S<float>(state, L.s_g), S<float>(state, L.s_beta), SM<float>(state, L.s_rm),
                                            SM<float>(state, L.s_rv), SM<long long>(state, L.s_nbt), 0.1f, 1e-5f, L.scale,
                                            L.shift, L.mean, L.invstd, st));

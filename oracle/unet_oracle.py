@@ -166,7 +166,7 @@ def synthetic_labels(batch, height, width, seed=1, device="cpu"):
     return lab.to(device)
 
 
-def trained_like_state(state, seed=0):
+def trained_like_state(state, seed=0, head_gain=8.0):
     """Makes a randomly initialised state_dict behave like a trained checkpoint for parity runs:
     BN running statistics away from (0,1), non-trivial affine BN parameters and a confident head."""
     g = torch.Generator().manual_seed(seed)
@@ -182,6 +182,6 @@ def trained_like_state(state, seed=0):
         elif (".main.1." in k or ".main.4." in k or ".bn1." in k or ".bn2." in k) and k.endswith("bias"):
             v = 0.1 * torch.randn(v.shape, generator=g)
         elif k == "conv_final.weight":
-            v = v * 8.0
+            v = v * head_gain
         out[k] = v
     return out

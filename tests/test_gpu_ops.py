@@ -62,8 +62,7 @@ def test_conv3x3_bn_relu_pool_and_train_epilogue(env, NB, H, W, Cin, Cout, bn):
     _close(_nchw(out), ref)
     assert torch.equal(_nchw(pool), F.max_pool2d(_nchw(out), 2))       # pool of the stored values: bit exact
     # train-mode epilogue: raw + bias, per-tile channel sums of the stored values
-    m_tiles = NB * ((H + 7) // 8) * ((W + 15) // 16)
-    stats = torch.zeros(m_tiles, 2, Cout, device=dev)
+    stats = torch.zeros(256, 2, Cout, device=dev)       # one partial row per CTA (<= number of SMs rows are written)
     raw = torch.zeros_like(out)
     _igemm(env, 0, x, wp, Cout, None, shift, 0, raw, Cout, stats=stats, block_n=bn)
     _close(_nchw(raw), conv + shift[None, :, None, None])

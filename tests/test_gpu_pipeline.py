@@ -82,7 +82,7 @@ def test_sliding_window_driver_matches_oracle_pipeline(E, pkg):
     sv[0, 30:34, 100:120] = np.nan
     seabed = (100 + 10 * np.sin(np.arange(NP) / 40.0)).astype(np.int32)
     m = Mm.UNet_Baseline(3, Fq, depth=3)
-    m.load_state_dict(O.trained_like_state(m.state_dict(), 0))
+    m.load_state_dict(O.trained_like_state(m.state_dict(), 0, head_gain=2.0))
     m = m.to(dev).eval()
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     pred = Pr.SurveyPredictor(m, patch, ov, preload, batch_size=8)
