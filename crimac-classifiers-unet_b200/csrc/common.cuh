@@ -34,6 +34,7 @@ struct ConvParams {
   CUtensorMap b_map;     // packed weights [N_total][taps*cin] bf16, K contiguous
   int taps;              // 9, 1 or 4
   int tap_mode;          // 0: tap -> (dy,dx) offsets on map 0 (3x3: tap=ky*3+kx; 1 tap: centre); 1: tap -> map index
+  int halo;              // 1: 3x3 conv with the 16x8 tile / halo-box main loop (a_map[0] = box {64,10,18,1})
   int cin;               // channels per tap, multiple of 64
   int NB, H, W;          // GEMM-M geometry: output pixels = NB*H*W
   int tiles_x, tiles_y, n_tiles, total_tiles;
@@ -66,6 +67,20 @@ struct WgradParams {
   int splits;            // split-K factor (gridDim.z)
   int m_tiles, n_tiles;
   float* dw;             // fp32 gradient in PyTorch layout: index (m*N_total + n)*taps + tap ; accumulated with red.add
+};
+
+// Weight gradient of a 3x3 conv with ALL nine taps per CTA: the shifted operand (dY) is loaded once per k-step as a
+// halo tile and read through nine row-shifted UMMA descriptors; taps are paired along the MMA M dimension.
+struct WgradHaloParams {
+  CUtensorMap s_map;     // shifted operand dY (NB,H,W,Cs): box {64, 18, 6, 1}
+  CUtensorMap f_map;     // fixed operand X (NB,H,W,Cf):   box {64, 16, 4, 1}
+  int Cs, Cf;            // Cout, Cin
+  int NB, H, W;
+  int tiles_x, tiles_y;  // 4x16-pixel k-tiles per image
+  int k_tiles_total;
+  int splits;
+  int s_tiles, f_tiles;  // Cs/64, Cf/64
+  float* dw;             // scratch [9][Cs][Cf] fp32
 };
 
 #define CRIMAC_MAX_CLASSES 8

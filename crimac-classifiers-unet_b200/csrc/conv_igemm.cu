@@ -22,33 +22,52 @@
 
 namespace {
 
-template <int BLOCK_N>
+// HALO variant (3x3 convs): the M tile is 16 rows x 8 pings and the A operand of one 64-channel block is ONE
+// 18 x 10 pixel TMA box; the nine taps are nine UMMA descriptors into that tile (start = the tap's first halo row,
+// stride between 8-pixel row groups SBO = 10*128 B).  Valid because SWIZZLE_128B is a pure function of the shared
+// memory address (probed on B200, profiles/r01_probe_first_run.log).  A-operand L2->SMEM traffic drops 6.25x; the
+// weights keep their own, deeper ring.
+constexpr int HALO_W = 10, HALO_H = 18;
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;  // 23040
+constexpr int HALO_SLOT = 23552;                   // padded to a multiple of 1024
+
+template <int BLOCK_N, bool HALO = false>
 struct ConvCfg {
   static constexpr int A_BYTES = TILE_M * KBLK * 2;
   static constexpr int B_BYTES = BLOCK_N * KBLK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  // halo rings
+  static constexpr int NA = (BLOCK_N == 256) ? 2 : 3;
+  static constexpr int NB = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 7 : 12);
+  static constexpr int OPERAND_BYTES = HALO ? (NA * HALO_SLOT + NB * B_BYTES) : (STAGES * STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int MAX_STAT_CH = 1024;  // per-CTA running channel sums (EPI_STATS), all n-tiles
-  static constexpr int AUX_BYTES = 256 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
+  static constexpr int AUX_BYTES = 512 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
                                    (CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 + 2 * MAX_STAT_CH * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
+  static constexpr int SMEM_BYTES = OPERAND_BYTES + AUX_BYTES + 1024;
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool HALO>
 __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  using Cfg = ConvCfg<BLOCK_N, HALO>;
+  constexpr int TW = HALO ? 8 : TILE_W;    // tile width (pings)
+  constexpr int TH = HALO ? 16 : TILE_H;   // tile height (range rows)
+  constexpr int NBAR_A = HALO ? Cfg::NA : Cfg::STAGES;   // non-halo: full/empty per stage live in the "A" arrays
+  constexpr int NBAR_B = HALO ? Cfg::NB : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint8_t* aux = smem + Cfg::OPERAND_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);   // [NBAR_A]  (halo: A tiles)
+  uint64_t* empty_bar = full_bar + NBAR_A;
+  uint64_t* bfull_bar = empty_bar + NBAR_A;                // [NBAR_B]  (halo: weight tiles)
+  uint64_t* bempty_bar = bfull_bar + NBAR_B;
+  uint64_t* tmem_full = bempty_bar + NBAR_B;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_affine = reinterpret_cast<float*>(aux + 256);  // [2 acc stages][scale BLOCK_N | shift BLOCK_N]
+  float* s_affine = reinterpret_cast<float*>(aux + 512);  // [2 acc stages][scale BLOCK_N | shift BLOCK_N]
   float* s_red = s_affine + 4 * BLOCK_N;                  // [4 warps][2][BLOCK_N]
   float* s_head = s_red + 8 * BLOCK_N;                    // [ncls][64] + [ncls]
   float* s_acc = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2][n_total] CTA-lifetime channel sums
@@ -61,9 +80,13 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     ptx::prefetch_tmap(&p.b_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < NBAR_A; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < NBAR_B; ++s) {
+      ptx::mbar_init(&bfull_bar[s], 1);
+      ptx::mbar_init(&bempty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
@@ -94,8 +117,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, bstage = 0;
+      uint32_t phase = 0, bphase = 0;
+      (void)bstage;
+      (void)bphase;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int m_tile = tile / p.n_tiles;
@@ -103,7 +128,29 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
         m_tile /= p.tiles_x;
         const int ty = m_tile % p.tiles_y;
         const int img = m_tile / p.tiles_y;
-        const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BLOCK_N;
+        const int x0 = tx * TW, y0 = ty * TH, n0 = n_tile * BLOCK_N;
+        if constexpr (HALO) {
+          for (int cb = 0; cb < cblocks; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], HALO_BYTES);
+            ptx::tma_load_4d(smem + stage * HALO_SLOT, &p.a_map[0], &full_bar[stage], cb * KBLK, x0 - 1, y0 - 1, img);
+            if (++stage == Cfg::NA) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            for (int tap = 0; tap < 9; ++tap) {
+              ptx::mbar_wait(&bempty_bar[bstage], bphase ^ 1u);
+              ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], Cfg::B_BYTES);
+              ptx::tma_load_2d(smem + Cfg::NA * HALO_SLOT + bstage * Cfg::B_BYTES, &p.b_map, &bfull_bar[bstage],
+                               tap * p.cin + cb * KBLK, n0);
+              if (++bstage == Cfg::NB) {
+                bstage = 0;
+                bphase ^= 1u;
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy = 0, dx = 0, mi = 0;
           if (p.tap_mode == 0) {
@@ -133,8 +180,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, bstage = 0;
+      uint32_t phase = 0, bphase = 0;
+      (void)bstage;
+      (void)bphase;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1;
@@ -142,6 +191,36 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        if constexpr (HALO) {
+          for (int cb = 0; cb < cblocks; ++cb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            const uint32_t sa = ptx::smem_u32(smem + stage * HALO_SLOT);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              ptx::mbar_wait(&bfull_bar[bstage], bphase);
+              ptx::tc_fence_after();
+              const uint32_t sb = ptx::smem_u32(smem + Cfg::NA * HALO_SLOT + bstage * Cfg::B_BYTES);
+              // output pixel (ty,tx) reads halo pixel (ty+ky, tx+kx): first row (ky*10+kx), row groups 10 pixels apart
+              const uint64_t adesc = ptx::make_smem_desc(sa + ((tap / 3) * HALO_W + tap % 3) * 128, 16, HALO_W * 128);
+              const uint64_t bdesc = ptx::make_smem_desc(sb, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k)
+                ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) != 0);
+              ptx::umma_commit(&bempty_bar[bstage]);
+              if (++bstage == Cfg::NB) {
+                bstage = 0;
+                bphase ^= 1u;
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == Cfg::NA) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          ptx::umma_commit(&tmem_full[as]);
+          continue;
+        }
         for (int ks = 0; ks < ksteps; ++ks) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -167,7 +246,8 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     const int e = threadIdx.x - 128;  // 0..127
     const int q = warp & 3;           // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;      // tile row <-> pixel
-    const int py = r >> 4, px = r & 15;
+    const int py = HALO ? (r >> 3) : (r >> 4), px = HALO ? (r & 7) : (r & 15);
+    constexpr int POOL_Y_XOR = HALO ? 8 : 16;  // lane distance of the vertical 2x2-pool partner
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -180,7 +260,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int ty = m_tile % p.tiles_y;
       const int img = m_tile / p.tiles_y;
       const int n0 = n_tile * BLOCK_N;
-      const int y = ty * TILE_H + py, x = tx * TILE_W + px;
+      const int y = ty * TH + py, x = tx * TW + px;
       const bool valid = (y < p.H) && (x < p.W);
 
       float* sc = s_affine + as * 2 * BLOCK_N;
@@ -251,7 +331,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             uint32_t m = bf16x2_max(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
-            pm[j] = bf16x2_max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            pm[j] = bf16x2_max(m, __shfl_xor_sync(0xffffffffu, m, POOL_Y_XOR));
           }
           if (valid && !(px & 1) && !(py & 1)) {
             const long ppix = (static_cast<long>(img) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
@@ -341,10 +421,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool HALO>
 cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
-  auto kern = conv_igemm_kernel<BLOCK_N, EPI>;
+  using Cfg = ConvCfg<BLOCK_N, HALO>;
+  auto kern = conv_igemm_kernel<BLOCK_N, EPI, HALO>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -360,8 +440,10 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
 
 // BLOCK_N in {64,128,256}; p.n_tiles*BLOCK_N == N_total must hold.
 cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num_sms, cudaStream_t stream) {
-#define CASE(BN, EP) \
-  if (block_n == BN && epi == EP) return launch_one<BN, EP>(p, num_sms, stream);
+  if (p.halo && p.taps != 9) return cudaErrorInvalidValue;
+#define CASE(BN, EP)                                                               \
+  if (block_n == BN && epi == EP)                                                  \
+    return p.halo ? launch_one<BN, EP, true>(p, num_sms, stream) : launch_one<BN, EP, false>(p, num_sms, stream);
   CASE(64, EPI_STORE) CASE(128, EPI_STORE) CASE(256, EPI_STORE)
   CASE(64, EPI_STATS) CASE(128, EPI_STATS) CASE(256, EPI_STATS)
   CASE(64, EPI_HEAD)

@@ -21,7 +21,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, int kx) {
+int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, int kx, int box_w) {
   auto enc = get_encode();
   CRIMAC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   CRIMAC_REQUIRE(v.C % 8 == 0 && v.pitch % 8 == 0, "channel count / pitch must be multiples of 8");
@@ -41,7 +41,7 @@ int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, in
   }
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(v.C), W, H, static_cast<cuuint64_t>(v.N)};
   cuuint64_t strides[3] = {sx, sy, sn};
-  cuuint32_t box[4] = {64, 16, static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -13,6 +13,7 @@
 #include "../../include/crimac_b200.h"
 #include <vector>
 #include <new>
+#include <cstdlib>
 
 namespace {
 
@@ -42,7 +43,9 @@ struct Conv3 {
   float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
   int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
   ConvParams fwd{}, dgrad{};
-  WgradParams wg{};
+  WgradHaloParams wg{};   // all-taps halo kernel (wide, shallow layers)
+  WgradParams wg_tap{};   // one-tap-per-CTA kernel (deep layers: few pixels, many channels)
+  bool wg_use_halo = true;
 };
 struct ConvT {
   int cin = 0, cout = 0, level_in = 0;
@@ -304,12 +307,17 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   if (!encode_maps) return 0;
 
   // ---- launch descriptors (tensor maps encoded once)
+  const bool use_halo = getenv("CRIMAC_NO_HALO") == nullptr;  // A/B switch for measurements
   auto geom = [&](ConvParams& p, int H, int W, int n_total, int bn) {
     p.H = H;
     p.W = W;
-    p.tiles_x = (W + TILE_W - 1) / TILE_W;
-    p.tiles_y = (H + TILE_H - 1) / TILE_H;
+    p.halo = (p.taps == 9 && use_halo) ? 1 : 0;
+    p.tiles_x = p.halo ? (W + 7) / 8 : (W + TILE_W - 1) / TILE_W;
+    p.tiles_y = p.halo ? (H + 15) / 16 : (H + TILE_H - 1) / TILE_H;
     p.n_tiles = n_total / bn;
+  };
+  auto conv_map = [&](ConvParams& p, const View& v) {
+    return p.halo ? make_act_map(&p.a_map[0], v, 18, 0, 0, 0, 10) : make_act_map(&p.a_map[0], v, TILE_H);
   };
   auto wgeom = [&](WgradParams& p, int H, int W, int m_total, int n_total, int bn, int taps, int tap_mode) {
     p.taps = taps;
@@ -333,7 +341,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       p.tap_mode = 0;
       p.cin = L.cin;
       geom(p, H, W, L.cout, L.bn_fwd);
-      if ((rc = make_act_map(&p.a_map[0], L.in, TILE_H))) return rc;
+      if ((rc = conv_map(p, L.in))) return rc;
       if ((rc = make_weight_map(&p.b_map, L.w_fwd, L.cout, 9 * L.cin, L.bn_fwd))) return rc;
     }
     if (train) {
@@ -344,14 +352,29 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         p.tap_mode = 0;
         p.cin = L.cout;
         geom(p, H, W, L.cin, L.bn_bwd);
-        if ((rc = make_act_map(&p.a_map[0], gr, TILE_H))) return rc;
+        if ((rc = conv_map(p, gr))) return rc;
         if ((rc = make_weight_map(&p.b_map, L.w_bwd, L.cin, 9 * L.cout, L.bn_bwd))) return rc;
         p.out = L.gin.ptr;
         p.out_pitch = L.gin.pitch;
-        WgradParams& w = L.wg;
-        wgeom(w, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
-        if ((rc = make_act_map(&w.a_map, gr, 4))) return rc;
-        if ((rc = make_act_map(&w.b_map[0], L.in, 4))) return rc;
+        WgradHaloParams& w = L.wg;
+        w.Cs = L.cout;
+        w.Cf = L.cin;
+        w.H = H;
+        w.W = W;
+        w.tiles_x = (W + 15) / 16;
+        w.tiles_y = (H + 3) / 4;
+        w.s_tiles = L.cout / 64;
+        w.f_tiles = L.cin / 64;
+        w.dw = c->wg_scratch;
+        if ((rc = make_act_map(&w.s_map, gr, 6, 0, 0, 0, 18))) return rc;
+        if ((rc = make_act_map(&w.f_map, L.in, 4))) return rc;
+        // measured on B200 (profiles/): the 64x64-channel halo tiles win up to Cout*Cin = 256*128, beyond that the
+        // 128 x 256 one-tap tiles re-read fewer operand bytes per FLOP
+        L.wg_use_halo = static_cast<long>(L.cout) * L.cin <= 256L * 128L;
+        WgradParams& wt = L.wg_tap;
+        wgeom(wt, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
+        if ((rc = make_act_map(&wt.a_map, gr, 4))) return rc;
+        if ((rc = make_act_map(&wt.b_map[0], L.in, 4))) return rc;
       }
     }
   }
@@ -403,6 +426,16 @@ void set_batch(WgradParams& p, int nb) {
   p.splits = splits;
 }
 
+void set_batch(WgradHaloParams& p, int nb) {
+  p.NB = nb;
+  p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
+  const int tiles = p.s_tiles * p.f_tiles;
+  int splits = (2 * device_num_sms() + tiles - 1) / tiles;
+  if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+}
+
 template <typename T>
 const T* S(const void* const* state, int i) {
   return static_cast<const T*>(state[i]);
@@ -442,6 +475,24 @@ int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, float* dw, cudaStre
   {
     ProfScope ps("wgrad_unpack", 0, 2 * wbytes, st);
     CRIMAC_CHECK_CUDA(launch_wgrad_unpack(w.dw, dw, w.M_total, w.N_total, w.taps, 0, st));
+  }
+  return 0;
+}
+
+int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, float* dw, cudaStream_t st) {
+  set_batch(w, nb);
+  const double wbytes = sizeof(float) * 9.0 * w.Cs * w.Cf;
+  if (w.splits > 1) {
+    ProfScope ps("wgrad_zero", 0, wbytes, st);
+    CRIMAC_CHECK_CUDA(cudaMemsetAsync(w.dw, 0, static_cast<size_t>(wbytes), st));
+  }
+  {
+    ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * 9, 0, st);
+    CRIMAC_CHECK_CUDA(launch_wgrad_halo(w, st));
+  }
+  {
+    ProfScope ps("wgrad_unpack", 0, 2 * wbytes, st);
+    CRIMAC_CHECK_CUDA(launch_wgrad_unpack(w.dw, dw, w.Cs, w.Cf, 9, 0, st));
   }
   return 0;
 }
@@ -689,7 +740,8 @@ extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const fl
       CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, dr, L.cin, c->fc_partials, grads[L.g_w], 0, st));
       return 0;
     }
-    int r = wgrad_run(c, L.wg, L.bn_wg, nb, grads[L.g_w], st);
+    int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, grads[L.g_w], st)
+                          : wgrad_run(c, L.wg_tap, L.bn_wg, nb, grads[L.g_w], st);
     if (r) return r;
     if (L.gin.ptr != nullptr) {
       ConvParams p = L.dgrad;

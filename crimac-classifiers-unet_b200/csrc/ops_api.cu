@@ -11,7 +11,7 @@ static int pick_block_n(int n_total, int requested) {
   return 0;
 }
 
-// Generic implicit GEMM.  mode: 0 = 3x3 conv (taps 9), 1 = 1x1 / ConvTranspose forward (taps 1; convt_cout > 0 turns on
+// Generic implicit GEMM.  mode: 0 = 3x3 conv (taps 9, halo main loop; 3 = same through the 9-box main loop), 1 = 1x1 / ConvTranspose forward (taps 1; convt_cout > 0 turns on
 // the 2x upsampling scatter), 2 = ConvTranspose backward-data (taps 4: x is the (2H x 2W) gradient, sub-sampled).
 // x: NHWC bf16 view (NB,H,W,cin) with pixel pitch x_pitch (for mode 2: dims of x are 2H x 2W).
 // w: packed bf16 [n_total][taps*cin].   out: NHWC bf16 with pitch out_pitch.
@@ -21,7 +21,9 @@ extern "C" int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, in
                                int out_pitch, int convt_cout, void* pool_out, int pool_pitch, float* stats,
                                const float* head_w, const float* head_b, float* head_out, int n_classes,
                                int head_softmax, int block_n, void* stream) {
-  CRIMAC_REQUIRE(mode >= 0 && mode <= 2, "mode");
+  CRIMAC_REQUIRE(mode >= 0 && mode <= 3, "mode");
+  const bool halo = (mode == 0);  // mode 3 = 3x3 conv through the plain 9-box main loop (kept for A/B measurements)
+  if (mode == 3) mode = 0;
   CRIMAC_REQUIRE(cin % 64 == 0, "cin must be a multiple of 64");
   const int bn = pick_block_n(n_total, head_w ? 64 : block_n);
   CRIMAC_REQUIRE(bn != 0, "n_total must be a multiple of 64 (and of block_n when given)");
@@ -32,8 +34,9 @@ extern "C" int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, in
   p.NB = NB;
   p.H = H;
   p.W = W;
-  p.tiles_x = (W + TILE_W - 1) / TILE_W;
-  p.tiles_y = (H + TILE_H - 1) / TILE_H;
+  p.halo = halo ? 1 : 0;
+  p.tiles_x = halo ? (W + 7) / 8 : (W + TILE_W - 1) / TILE_W;
+  p.tiles_y = halo ? (H + 15) / 16 : (H + TILE_H - 1) / TILE_H;
   p.n_tiles = n_total / bn;
   p.total_tiles = NB * p.tiles_x * p.tiles_y * p.n_tiles;
   if (mode == 2) {
@@ -44,7 +47,7 @@ extern "C" int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, in
     }
   } else {
     View v{static_cast<bf16*>(const_cast<void*>(x)), NB, H, W, cin, x_pitch};
-    int rc = make_act_map(&p.a_map[0], v, TILE_H);
+    int rc = halo ? make_act_map(&p.a_map[0], v, 18, 0, 0, 0, 10) : make_act_map(&p.a_map[0], v, TILE_H);
     if (rc) return rc;
   }
   int rc = make_weight_map(&p.b_map, static_cast<const bf16*>(w), n_total, p.taps * cin, bn);
@@ -123,5 +126,43 @@ extern "C" int crimac_op_wgrad(int mode, const void* f, int f_pitch, int m_total
     CRIMAC_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * p.taps * static_cast<size_t>(m_total) * n_total, st));
   CRIMAC_CHECK_CUDA(launch_wgrad_gemm(p, bn, st));
   CRIMAC_CHECK_CUDA(launch_wgrad_unpack(scratch, dw, m_total, n_total, p.taps, 0, st));
+  return 0;
+}
+
+// 3x3-conv weight gradient with all nine taps per CTA (halo tile of dY, taps paired along M).
+// dy: NHWC bf16 (NB,H,W,cout) pitch dy_pitch; x: NHWC bf16 (NB,H,W,cin) pitch x_pitch; scratch fp32 [9][cout][cin];
+// dw: fp32 (cout,cin,3,3).
+extern "C" int crimac_op_wgrad_halo(const void* dy, int dy_pitch, int cout, const void* x, int x_pitch, int cin, int NB,
+                                    int H, int W, float* scratch, float* dw, int splits, void* stream) {
+  CRIMAC_REQUIRE(cout % 64 == 0 && cin % 64 == 0, "channel counts must be multiples of 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradHaloParams p{};
+  p.Cs = cout;
+  p.Cf = cin;
+  p.NB = NB;
+  p.H = H;
+  p.W = W;
+  p.tiles_x = (W + 15) / 16;
+  p.tiles_y = (H + 3) / 4;
+  p.k_tiles_total = NB * p.tiles_x * p.tiles_y;
+  p.s_tiles = cout / 64;
+  p.f_tiles = cin / 64;
+  if (splits <= 0) {
+    const int tiles = p.s_tiles * p.f_tiles;
+    splits = (2 * device_num_sms() + tiles - 1) / tiles;
+    if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits;
+  p.dw = scratch;
+  View vs{static_cast<bf16*>(const_cast<void*>(dy)), NB, H, W, cout, dy_pitch};
+  View vf{static_cast<bf16*>(const_cast<void*>(x)), NB, H, W, cin, x_pitch};
+  int rc = make_act_map(&p.s_map, vs, 6, 0, 0, 0, 18);
+  if (rc) return rc;
+  rc = make_act_map(&p.f_map, vf, 4);
+  if (rc) return rc;
+  if (splits > 1) CRIMAC_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 9 * static_cast<size_t>(cout) * cin, st));
+  CRIMAC_CHECK_CUDA(launch_wgrad_halo(p, st));
+  CRIMAC_CHECK_CUDA(launch_wgrad_unpack(scratch, dw, cout, cin, 9, 0, st));
   return 0;
 }

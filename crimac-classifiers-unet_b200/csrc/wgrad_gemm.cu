@@ -193,6 +193,169 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ scratch, float* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3-conv weight gradient, all nine taps per CTA.
+//   dW[co][ci][ky][kx] = sum_q dY[q - (ky-1, kx-1)][co] * X[q][ci]
+// k-step = a 4x16-pixel tile q of X (fixed operand, GEMM-N, 64 ci) plus ONE 6x18-pixel halo tile of dY (GEMM-M, 64 co).
+// Tap (ky,kx) is the view of the halo tile starting at row (2-ky)*18 + (2-kx): the SWIZZLE_128B pattern is a pure
+// function of the shared-memory address, so an MN-major descriptor may start at any 128-byte row.  Two taps are
+// stacked along M (rows 0-63 / 64-127 of the MMA = two "64-channel boxes" LBO bytes apart), which fills the 128-row
+// tensor-core tile although only 64 output channels are live: 5 MMA groups (the 5th repeats tap 1 in its lower half,
+// discarded) cover 9 taps.  TMEM: 5 accumulators x 64 fp32 columns.  Operand traffic per k-step: 13.5 KB + 8 KB for
+// 20 MMAs (640 cycles) instead of 9 x 24 KB.
+constexpr int WH_HALO_W = 18, WH_HALO_H = 6;
+constexpr int WH_HALO_BYTES = WH_HALO_W * WH_HALO_H * 128;  // 13824
+constexpr int WH_HALO_SLOT = 14336;                          // padded to a multiple of 1024
+constexpr int WH_FIXED_BYTES = 64 * 128;                     // 8192
+constexpr int WH_STAGE = WH_HALO_SLOT + WH_FIXED_BYTES;
+constexpr int WH_STAGES = 8;
+constexpr int WH_SMEM = WH_STAGES * WH_STAGE + 256 + 1024;
+constexpr int WH_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* aux = smem + WH_STAGES * WH_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + WH_STAGES;
+  uint64_t* acc_bar = empty_bar + WH_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int f_tile = blockIdx.x % p.f_tiles;
+  const int s_tile = blockIdx.x / p.f_tiles;
+  const int split = blockIdx.y;
+  const int kt_per = (p.k_tiles_total + p.splits - 1) / p.splits;
+  const int kt_begin = split * kt_per;
+  const int kt_end = min(p.k_tiles_total, kt_begin + kt_per);
+  const int ksteps = kt_end - kt_begin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.s_map);
+    ptx::prefetch_tmap(&p.f_map);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WH_STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(acc_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr_smem, WH_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // tap pairs (first -> MMA rows 0..63, second -> rows 64..127); halo row offsets grow from first to second
+  constexpr int PA[5] = {8, 6, 4, 2, 1};
+  constexpr int PB[5] = {7, 5, 3, 1, 0};
+
+  if (ksteps > 0) {
+    if (warp == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        int u = kt;
+        const int tx = u % p.tiles_x;
+        u /= p.tiles_x;
+        const int ty = u % p.tiles_y;
+        const int img = u / p.tiles_y;
+        const int x0 = tx * 16, y0 = ty * 4;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sh = smem + stage * WH_STAGE;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], WH_HALO_BYTES + WH_FIXED_BYTES);
+        ptx::tma_load_4d(sh, &p.s_map, &full_bar[stage], s_tile * 64, x0 - 1, y0 - 1, img);
+        ptx::tma_load_4d(sh + WH_HALO_SLOT, &p.f_map, &full_bar[stage], f_tile * 64, x0, y0, img);
+        if (++stage == WH_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);
+      // per pair: descriptor (without start address) and the byte offset of the first tap's view
+      uint64_t dtmpl[5];
+      uint32_t off16[5];
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {
+        const int oa = ((2 - PA[g] / 3) * WH_HALO_W + (2 - PA[g] % 3)) * 128;
+        const int ob = ((2 - PB[g] / 3) * WH_HALO_W + (2 - PB[g] % 3)) * 128;
+        dtmpl[g] = ptx::make_smem_desc(0, ob - oa, 1024);
+        off16[g] = oa >> 4;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sh = ptx::smem_u32(smem + stage * WH_STAGE);
+        const uint32_t sh16 = sh >> 4;
+        const uint64_t bdesc0 = ptx::make_smem_desc(sh + WH_HALO_SLOT, WH_FIXED_BYTES, 1024);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(r * 128);          // 16 pixels * 128 B = 2048 B
+          const uint32_t row16 = sh16 + static_cast<uint32_t>(r * WH_HALO_W * 8);  // halo row pitch 18 * 128 B
+#pragma unroll
+          for (int g = 0; g < 5; ++g)
+            ptx::umma_bf16(tmem_base + g * 64, dtmpl[g] + row16 + off16[g], bdesc, idesc, (ks | r) != 0);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        if (++stage == WH_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      ptx::umma_commit(acc_bar);
+    } else if (warp >= 4) {
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      const int half = m >> 6;
+      const int co = s_tile * 64 + (m & 63);
+      ptx::mbar_wait(acc_bar, 0);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < 5; ++g) {
+        const int tap = half ? PB[g] : PA[g];
+        const bool live = !(g == 4 && half == 0);  // lower half of the last group repeats tap 1
+        float* row = p.dw + (static_cast<long>(tap) * p.Cs + co) * p.Cf + f_tile * 64;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 64 + chunk * 32, v);
+          ptx::tmem_ld_wait();
+          if (live) {
+            if (p.splits == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(row + chunk * 32 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                red_add_v4(row + chunk * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, WH_TMEM_COLS);
+  }
+}
+
 template <int BLOCK_N>
 cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   using Cfg = WgCfg<BLOCK_N>;
@@ -215,6 +378,18 @@ cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t st
   if (block_n == 128) return launch_wg<128>(p, stream);
   if (block_n == 256) return launch_wg<256>(p, stream);
   return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(p.s_tiles * p.f_tiles, p.splits);
+  wgrad_halo_kernel<<<grid, 256, WH_SMEM, stream>>>(p);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,

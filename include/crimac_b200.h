@@ -114,6 +114,8 @@ int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, int cin, int 
                     float* head_out, int n_classes, int head_softmax, int block_n, void* stream);
 int crimac_op_wgrad(int mode, const void* f, int f_pitch, int m_total, const void* t, int t_pitch, int n_total, int NB,
                     int H, int W, float* scratch, float* dw, int splits, int block_n, void* stream);
+int crimac_op_wgrad_halo(const void* dy, int dy_pitch, int cout, const void* x, int x_pitch, int cin, int NB, int H, int W,
+                         float* scratch, float* dw, int splits, void* stream);
 int crimac_dbg_umma(const void* image_dev, int image_bytes, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                     int n_mma, int a_step_bytes, int b_step_bytes, float* out_dev, int N, void* stream);
 int crimac_dbg_tma_box(const void* x_dev, int NB, int H, int W, int C, int pitch, int box_h, int sub, int ky, int kx,

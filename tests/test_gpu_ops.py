@@ -144,6 +144,25 @@ def test_weight_gradient_conv3x3(env, NB, H, W, Cin, Cout, splits):
     assert (dw - wr.grad).abs().max().item() <= 1e-4 * (NB * H * W) ** 0.5 * 4
 
 
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,splits", [(2, 32, 32, 64, 64, 1), (2, 32, 32, 128, 64, 4),
+                                                    (2, 16, 16, 256, 128, 0), (1, 32, 32, 64, 192, 3),
+                                                    (1, 20, 24, 64, 128, 2), (2, 64, 64, 64, 64, 0)])
+def test_weight_gradient_conv3x3_all_taps_halo(env, NB, H, W, Cin, Cout, splits):
+    """The production 3x3 weight-gradient kernel: nine taps per CTA from one halo tile, taps paired along M."""
+    L, lib, dev = env
+    torch.manual_seed(6)
+    x = torch.randn(NB, H, W, Cin, device=dev).bfloat16()
+    dy = torch.randn(NB, H, W, Cout, device=dev).bfloat16()
+    scratch = torch.empty(9 * Cout * Cin, device=dev)
+    dw = torch.zeros(Cout, Cin, 3, 3, device=dev)
+    L.check(lib.crimac_op_wgrad_halo(L.ptr(dy), Cout, Cout, L.ptr(x), Cin, Cin, NB, H, W, L.ptr(scratch), L.ptr(dw),
+                                     splits, L.stream_ptr()), "crimac_op_wgrad_halo")
+    torch.cuda.synchronize()
+    wr = torch.zeros(Cout, Cin, 3, 3, device=dev, requires_grad=True)
+    F.conv2d(_nchw(x), wr, padding=1).backward(_nchw(dy))
+    assert (dw - wr.grad).abs().max().item() <= 1e-4 * (NB * H * W) ** 0.5 * 4
+
+
 def test_weight_gradient_conv_transpose(env):
     L, lib, dev = env
     torch.manual_seed(5)

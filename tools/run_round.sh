@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 1200 python -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_gpu.log 2>&1
+timeout 1200 python -m pytest tests -q -m gpu -s > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 --profile-out gpurun_out/breakdown_train.csv > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err
@@ -13,15 +13,18 @@ timeout 300 python bench.py --mode infer --steps 20 --warmup 3 --no-cpu-baseline
 echo "bench infer exit $?"; cat gpurun_out/bench_infer.json; tail -5 gpurun_out/bench_infer.err
 cat gpurun_out/breakdown_infer.csv
 if [ "$1" == "ncu" ]; then
-  # launch list of one short bench run (serialised, cold-cache: compare SHARES); then a full capture of the top kernels
+  # launch list of one short bench run (serialised, cold-cache: compare SHARES); then full captures of the top kernels
   CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain.log 2>&1 && \
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 600 --csv --log-file gpurun_out/launches_train.csv $CMD > gpurun_out/ncu_list.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 600 --csv --log-file gpurun_out/launches_train.csv $CMD > gpurun_out/ncu_list.log 2>&1
   echo "ncu list exit $?"
   $CMD > gpurun_out/plain2.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -s 30 -c 3 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_conv.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm_kernel -c 11 -o gpurun_out/prof_conv $CMD > gpurun_out/ncu_conv.log 2>&1
   echo "ncu conv exit $?"
   $CMD > gpurun_out/plain3.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_gemm_kernel -s 25 -c 3 -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu_wgrad.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:wgrad_halo_kernel|wgrad_gemm_kernel" -c 6 -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu_wgrad.log 2>&1
   echo "ncu wgrad exit $?"
+  $CMD > gpurun_out/plain4.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:first_conv|bn_bwd|head_bwd|bn_apply|pool_bwd" -c 12 -o gpurun_out/prof_elem $CMD > gpurun_out/ncu_elem.log 2>&1
+  echo "ncu elem exit $?"
 fi
