@@ -346,22 +346,23 @@ __global__ void ce_finalize_kernel(const double* partials, int nblocks, float* o
 // ============================================================================ 1x1 head backward
 // dAct[p][c] = s * sum_k dl[k][p] W[k][c];  dW[k][c] = s * sum_p dl[k][p] act[p][c];  db[k] = s * sum_p dl[k][p]
 // (s = *gscale or 1).  One block = 128 pixels per iteration; partials per block, summed by head_bwd_finalize.
-__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ dlogits, const float* gscale,
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dlogits, const float* gscale,
                                                        View act, const float* __restrict__ hw, int ncls, View dact,
                                                        float* partials) {
+  constexpr int TPB = 256;
   __shared__ float s_w[CRIMAC_MAX_CLASSES * 64];
-  __shared__ float s_dl[128][CRIMAC_MAX_CLASSES + 1];
-  __shared__ __align__(16) bf16 s_act[128][72];
-  for (int i = threadIdx.x; i < ncls * 64; i += 128) s_w[i] = hw[i];
+  __shared__ float s_dl[TPB][CRIMAC_MAX_CLASSES + 1];
+  __shared__ __align__(16) bf16 s_act[TPB][72];
+  for (int i = threadIdx.x; i < ncls * 64; i += TPB) s_w[i] = hw[i];
   const float s = gscale ? *gscale : 1.f;
   const long HW = static_cast<long>(act.H) * act.W;
   const long total = act.N * HW;
-  const int c = threadIdx.x & 63, half = threadIdx.x >> 6;
+  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;  // dW phase: channel c over pixels [part*64, part*64+64)
   float accw[CRIMAC_MAX_CLASSES], accb[CRIMAC_MAX_CLASSES];
 #pragma unroll
   for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) accw[k] = accb[k] = 0.f;
   __syncthreads();
-  for (long base = static_cast<long>(blockIdx.x) * 128; base < total; base += static_cast<long>(gridDim.x) * 128) {
+  for (long base = static_cast<long>(blockIdx.x) * TPB; base < total; base += static_cast<long>(gridDim.x) * TPB) {
     const long p = base + threadIdx.x;
     const bool valid = p < total;
     float dl[CRIMAC_MAX_CLASSES];
@@ -371,11 +372,13 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
       dl[k] = (valid && k < ncls) ? s * dlogits[(n * ncls + k) * HW + r] : 0.f;
       if (k < ncls) s_dl[threadIdx.x][k] = dl[k];
     }
+    uint4 av[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      av[g] = valid ? *reinterpret_cast<const uint4*>(act.ptr + p * act.pitch + g * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (valid) u = *reinterpret_cast<const uint4*>(act.ptr + p * act.pitch + g * 8);
-      *reinterpret_cast<uint4*>(&s_act[threadIdx.x][g * 8]) = u;
+      *reinterpret_cast<uint4*>(&s_act[threadIdx.x][g * 8]) = av[g];
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -388,7 +391,8 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
       if (valid) store8(dact.ptr + p * dact.pitch + g * 8, o);
     }
     __syncthreads();
-    for (int q = half * 64; q < half * 64 + 64; ++q) {
+#pragma unroll 4
+    for (int q = part * 64; q < part * 64 + 64; ++q) {
       const float a = __bfloat162float(s_act[q][c]);
 #pragma unroll
       for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
@@ -400,8 +404,8 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
     }
     __syncthreads();
   }
-  // partial layout per block: [2 halves][ncls*64 + ncls]
-  float* dst = partials + (static_cast<long>(blockIdx.x) * 2 + half) * (ncls * 64 + ncls);
+  // partial layout per block: [4 parts][ncls*64 + ncls]
+  float* dst = partials + (static_cast<long>(blockIdx.x) * 4 + part) * (ncls * 64 + ncls);
 #pragma unroll
   for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
     if (k < ncls) {
@@ -553,13 +557,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, 
           const float xh = (r[j] - mu[j]) * is[j];
           o[j] = sc[j] * (gg - k1[j] - xh * k2[j]);
         }
-        const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                                    pack_bf16x2(o[6], o[7]));
-        *reinterpret_cast<uint4*>(draw.ptr + p * draw.pitch + g * 8) = pk;
-        // bias gradient from the rounded values, as the wgrad / dgrad kernels will see them
-        const float2 a = unpack_bf16x2(pk.x), b = unpack_bf16x2(pk.y), cc = unpack_bf16x2(pk.z), dd = unpack_bf16x2(pk.w);
-        acc[0][0] += a.x; acc[0][1] += a.y; acc[0][2] += b.x; acc[0][3] += b.y;
-        acc[0][4] += cc.x; acc[0][5] += cc.y; acc[0][6] += dd.x; acc[0][7] += dd.y;
+        store8(draw.ptr + p * draw.pitch + g * 8, o);
+        // conv-bias gradient = sum of dRaw: exactly zero in exact arithmetic (BN removes the bias); summed from the
+        // fp32 values so that, like the reference, only cancellation noise is left
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0][j] += o[j];
       }
     }
   }
@@ -635,31 +637,34 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(View act, View dpool,
 }
 
 // ============================================================================ first conv weight gradient
-// dW[co][ci][tap] = sum_p dRaw[p][co] * x[p + tap][ci]   (fp32 NCHW input, Cin = #frequencies)
+// dW[co][ci][tap] = sum_p dRaw[p][co] * x[p + tap][ci]   (fp32 NCHW input, Cin = #frequencies, K = 9*Cin <= 72)
+// Register-tiled: a thread owns 4 output channels x KPT taps (36-72 accumulators) for one quarter of the tile's
+// pixels: per pixel 1 LDS.64 (4 bf16 gradients) + KPT broadcast LDS feed 4*KPT FFMAs.  Partial rows:
+// partials[(block*4 + pixel_lane)][64*K].
 template <int CIN>
 __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const float* __restrict__ x, View draw, int NB, int H,
                                                                int W, float* partials) {
   constexpr int K = CIN * 9;
-  constexpr int KPT = (K + 3) / 4;  // k's per thread (4 thread groups of 64 output channels)
-  __shared__ float s_x[CIN][TILE_H + 2][TILE_W + 2];
+  constexpr int KPT = (K + 3) / 4;
+  constexpr int XW = TILE_W + 2, XH = TILE_H + 2;
+  __shared__ float s_x[CIN * XH * XW];
   __shared__ __align__(16) bf16 s_d[TILE_M][72];
-  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  const int pl = threadIdx.x >> 6, u = threadIdx.x & 63, cg = u & 15, kg = u >> 4;
   int off[KPT];
-  bool kvalid[KPT];
 #pragma unroll
   for (int j = 0; j < KPT; ++j) {
     const int k = kg * KPT + j;
-    kvalid[j] = k < K;
-    const int kk = kvalid[j] ? k : 0;
+    const int kk = k < K ? k : 0;
     const int ci = kk / 9, tap = kk % 9;
-    off[j] = (ci * (TILE_H + 2) + tap / 3) * (TILE_W + 2) + tap % 3;
+    off[j] = (ci * XH + tap / 3) * XW + tap % 3;
   }
-  float acc[KPT];
+  float acc[4][KPT];
 #pragma unroll
-  for (int j = 0; j < KPT; ++j) acc[j] = 0.f;
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) acc[c][j] = 0.f;
   const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
   const int total = NB * tiles_x * tiles_y;
-  const float* sx = &s_x[0][0][0];
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     int t = tile;
     const int tx = t % tiles_x;
@@ -667,33 +672,43 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const float* __re
     const int ty = t % tiles_y;
     const int img = t / tiles_y;
     const int y0 = ty * TILE_H, x0 = tx * TILE_W;
-    for (int i = threadIdx.x; i < CIN * (TILE_H + 2) * (TILE_W + 2); i += 256) {
-      const int xx = i % (TILE_W + 2), yy = (i / (TILE_W + 2)) % (TILE_H + 2), ci = i / ((TILE_W + 2) * (TILE_H + 2));
+    for (int i = threadIdx.x; i < CIN * XH * XW; i += 256) {
+      const int xx = i % XW, yy = (i / XW) % XH, ci = i / (XW * XH);
       const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-      (&s_x[0][0][0])[i] =
-          (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(&x[((static_cast<long>(img) * CIN + ci) * H + gy) * W + gx]) : 0.f;
+      s_x[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(&x[((static_cast<long>(img) * CIN + ci) * H + gy) * W + gx]) : 0.f;
     }
     for (int i = threadIdx.x; i < TILE_M * 8; i += 256) {
       const int pix = i >> 3, g = i & 7;
       const int gy = y0 + (pix >> 4), gx = x0 + (pix & 15);
-      uint4 u = make_uint4(0, 0, 0, 0);
+      uint4 v = make_uint4(0, 0, 0, 0);
       if (gy < H && gx < W)
-        u = *reinterpret_cast<const uint4*>(draw.ptr + ((static_cast<long>(img) * H + gy) * W + gx) * draw.pitch + g * 8);
-      *reinterpret_cast<uint4*>(&s_d[pix][g * 8]) = u;
+        v = *reinterpret_cast<const uint4*>(draw.ptr + ((static_cast<long>(img) * H + gy) * W + gx) * draw.pitch + g * 8);
+      *reinterpret_cast<uint4*>(&s_d[pix][g * 8]) = v;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int pix = 0; pix < TILE_M; ++pix) {
-      const float d = __bfloat162float(s_d[pix][co]);
-      const int pb = (pix >> 4) * (TILE_W + 2) + (pix & 15);
+#pragma unroll 2
+    for (int i = 0; i < TILE_M / 4; ++i) {
+      const int pix = pl * (TILE_M / 4) + i;
+      const uint2 dv = *reinterpret_cast<const uint2*>(&s_d[pix][cg * 4]);
+      const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+      const int pb = (pix >> 4) * XW + (pix & 15);
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) acc[j] = fmaf(d, sx[pb + off[j]], acc[j]);
+      for (int j = 0; j < KPT; ++j) {
+        const float xv = s_x[pb + off[j]];
+        acc[0][j] = fmaf(d01.x, xv, acc[0][j]);
+        acc[1][j] = fmaf(d01.y, xv, acc[1][j]);
+        acc[2][j] = fmaf(d23.x, xv, acc[2][j]);
+        acc[3][j] = fmaf(d23.y, xv, acc[3][j]);
+      }
     }
     __syncthreads();
   }
+  float* dst = partials + (static_cast<long>(blockIdx.x) * 4 + pl) * 64 * K;
 #pragma unroll
-  for (int j = 0; j < KPT; ++j)
-    if (kvalid[j]) partials[static_cast<long>(blockIdx.x) * 64 * K + co * K + kg * KPT + j] = acc[j];
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < KPT; ++j)
+      if (kg * KPT + j < K) dst[(cg * 4 + c) * K + kg * KPT + j] = acc[c][j];
 }
 
 // ============================================================================ weight packing (fp32 params -> bf16 GEMM operands)
@@ -760,7 +775,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 #define FW(C)                                                                                       \
   if (cin == C) {                                                                                   \
     first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
-    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 31) / 32, 256, 0, st>>>(partials, grid, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr); \
+    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 31) / 32, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
   FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
@@ -810,11 +825,11 @@ int head_bwd_blocks() { return 148 * 4; }
 cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act, const float* hw, int ncls, View dact,
                             float* partials, float* dw, float* db, int accumulate, cudaStream_t st) {
   const long px = static_cast<long>(act.N) * act.H * act.W;
-  int blocks = grid_for(px, 128);
+  int blocks = grid_for(px, 256);
   if (blocks > head_bwd_blocks()) blocks = head_bwd_blocks();
-  head_bwd_kernel<<<blocks, 128, 0, st>>>(dlogits, gscale, act, hw, ncls, dact, partials);
+  head_bwd_kernel<<<blocks, 256, 0, st>>>(dlogits, gscale, act, hw, ncls, dact, partials);
   const int per = ncls * 64 + ncls;
-  head_bwd_finalize_kernel<<<(per + 127) / 128, 128, 0, st>>>(partials, blocks * 2, ncls, dw, db, accumulate);
+  head_bwd_finalize_kernel<<<(per + 127) / 128, 128, 0, st>>>(partials, blocks * 4, ncls, dw, db, accumulate);
   return cudaGetLastError();
 }
 

@@ -276,8 +276,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     c->red_partials = bump.arr<float>(static_cast<size_t>(reduce_blocks()) * 2 * cmax);
     c->c1c2 = bump.arr<float>(2 * cmax);
     c->wg_scratch = bump.arr<float>(static_cast<size_t>(9) * cmax * cmax);
-    c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 2 * (cfg.n_classes * 64 + cfg.n_classes));
-    c->fc_partials = bump.arr<float>(static_cast<size_t>(first_conv_wgrad_blocks()) * 64 * cfg.in_channels * 9);
+    c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 4 * (cfg.n_classes * 64 + cfg.n_classes));
+    c->fc_partials = bump.arr<float>(static_cast<size_t>(first_conv_wgrad_blocks()) * 4 * 64 * cfg.in_channels * 9);
     c->ce_partials = bump.arr<double>(static_cast<size_t>(ce_blocks()) * 2);
     const size_t lg = static_cast<size_t>(B) * cfg.n_classes * cfg.height * cfg.width;
     c->logits = bump.arr<float>(lg);

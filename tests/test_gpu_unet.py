@@ -78,7 +78,7 @@ def test_golden_depth2_from_reference(M, golden_dir):
     with torch.no_grad():
         lg = m(x)
     ref_lg = torch.from_numpy(g["eval_logits"])                  # this fixture has a x8 head: logits span +-12
-    assert (lg.cpu() - ref_lg).abs().max().item() < 1e-2 * ref_lg.abs().max().item()
+    assert (lg.cpu() - ref_lg).abs().max().item() < 2e-2 * ref_lg.abs().max().item()
     m.train()
     loss = m.train_step_fused(x, y, torch.tensor(O.CLASS_WEIGHTS, device=dev))
     assert abs(loss.item() - float(g["loss"])) < 2e-3 * float(g["loss"])
