@@ -13,9 +13,11 @@
 //     - ConvTranspose2d backward-data as a 4-"tap" GEMM, one sub-sampled tensor map per (ky,kx)
 //     - the fused 1x1 head + softmax epilogue           (unet.py:284,342; pipeline.py:218)
 //
-// Warp roles (256 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
-// w4..w7 = epilogue (thread t <-> TMEM lane <-> pixel t of the tile).  Two TMEM accumulator stages let
-// the epilogue of tile i overlap the main loop of tile i+1.
+// Warp roles (384 threads): w0 = TMA producer, w1 = MMA issuer (one thread), w2 = TMEM allocator,
+// w4..w11 = epilogue: warp w reads TMEM lane quarter w%4 (lane <-> pixel of the tile) and owns every second
+// 32-column chunk of the accumulator, so two warps per SM sub-partition hide each other's TMEM / shuffle latency.
+// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.  With one chunk per
+// warp (Cout = 64 layers) the train-mode BatchNorm statistics stay in registers for the CTA's lifetime.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "devfn.cuh"
@@ -34,24 +36,37 @@ constexpr int HALO_SLOT = 23552;                   // padded to a multiple of 10
 template <int BLOCK_N, bool HALO = false>
 struct ConvCfg {
   static constexpr int A_BYTES = TILE_M * KBLK * 2;
-  static constexpr int B_BYTES = BLOCK_N * KBLK * 2;
+  static constexpr int B_BYTES = BLOCK_N * KBLK * 2;   // weights of one tap x 64 input channels
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  // halo rings
+  // halo rings: NA activation halo tiles; NB weight stages of TPS taps each (one mbarrier round trip and one
+  // tcgen05.commit per TPS*4 MMAs: the single issuing thread, not the tensor pipe, is the scarce resource for narrow N)
   static constexpr int NA = (BLOCK_N == 256) ? 2 : 3;
-  static constexpr int NB = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 7 : 12);
-  static constexpr int OPERAND_BYTES = HALO ? (NA * HALO_SLOT + NB * B_BYTES) : (STAGES * STAGE_BYTES);
+  static constexpr int TPS = (BLOCK_N == 256) ? 1 : 3;
+  static constexpr int NB = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int BSTAGE_BYTES = TPS * B_BYTES;
+  static constexpr int OPERAND_BYTES = HALO ? (NA * HALO_SLOT + NB * BSTAGE_BYTES) : (STAGES * STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int MAX_STAT_CH = 1024;  // per-CTA running channel sums (EPI_STATS), all n-tiles
+  static constexpr int MAX_STAT_CH = 4 * BLOCK_N;  // per-CTA running channel sums (EPI_STATS) over all n-tiles
+  static constexpr int HEAD_BYTES = (BLOCK_N == 64) ? ((CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 +
+                                                       2 * TILE_M * CRIMAC_MAX_CLASSES * 4 /*partial-logit exchange*/)
+                                                    : 0;
   static constexpr int AUX_BYTES = 512 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
-                                   (CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 + 2 * MAX_STAT_CH * 4;
+                                   2 * MAX_STAT_CH * 4 + HEAD_BYTES;
   static constexpr int SMEM_BYTES = OPERAND_BYTES + AUX_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+  static_assert(9 % TPS == 0, "taps per weight stage must divide 9");
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// epilogue warps: 4 TMEM lane quarters x EPI_COLGROUPS column groups
+constexpr int EPI_COLGROUPS = 2;
+constexpr int EPI_WARPS = 4 * EPI_COLGROUPS;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int CONV_THREADS = 128 + EPI_THREADS;
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 template <int BLOCK_N, int EPI, bool HALO>
-__global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N, HALO>;
   constexpr int TW = HALO ? 8 : TILE_W;    // tile width (pings)
   constexpr int TH = HALO ? 16 : TILE_H;   // tile height (range rows)
@@ -69,8 +84,9 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_affine = reinterpret_cast<float*>(aux + 512);  // [2 acc stages][scale BLOCK_N | shift BLOCK_N]
   float* s_red = s_affine + 4 * BLOCK_N;                  // [4 warps][2][BLOCK_N]
-  float* s_head = s_red + 8 * BLOCK_N;                    // [ncls][64] + [ncls]
-  float* s_acc = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2][n_total] CTA-lifetime channel sums
+  float* s_acc = s_red + 8 * BLOCK_N;                     // [2][n_total] CTA-lifetime channel sums
+  float* s_head = s_acc + 2 * Cfg::MAX_STAT_CH;           // [ncls][64] + [ncls]           (BLOCK_N == 64 only)
+  float* s_hx = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2 acc stages][TILE_M][classes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +106,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 128);
+      ptx::mbar_init(&tmem_empty[s], EPI_THREADS);
     }
     ptx::fence_barrier_init();
   }
@@ -99,11 +115,11 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
     ptx::tmem_relinquish();
   }
   if (EPI == EPI_STATS && warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 2 * p.n_tiles * BLOCK_N; i += 128) s_acc[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 2 * p.n_tiles * BLOCK_N; i += EPI_THREADS) s_acc[i] = 0.f;
   }
   if (EPI == EPI_HEAD && warp >= 4) {
     const int e = threadIdx.x - 128;
-    for (int i = e; i < p.n_classes * 64; i += 128) s_head[i] = p.head_w[i];
+    for (int i = e; i < p.n_classes * 64; i += EPI_THREADS) s_head[i] = p.head_w[i];
     if (e < p.n_classes) s_head[CRIMAC_MAX_CLASSES * 64 + e] = p.head_b[e];
   }
   ptx::tc_fence_before();
@@ -116,7 +132,9 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // elect.sync (not lane == 0): the compiler then knows a single thread runs the loop and emits the uniform-datapath
+    // TMA / MMA / commit instructions straight, without a per-instruction active-thread serialisation loop
+    if (ptx::elect_one()) {
       int stage = 0, bstage = 0;
       uint32_t phase = 0, bphase = 0;
       (void)bstage;
@@ -138,19 +156,21 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
               stage = 0;
               phase ^= 1u;
             }
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tg = 0; tg < 9 / Cfg::TPS; ++tg) {
               ptx::mbar_wait(&bempty_bar[bstage], bphase ^ 1u);
-              ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], Cfg::B_BYTES);
-              ptx::tma_load_2d(smem + Cfg::NA * HALO_SLOT + bstage * Cfg::B_BYTES, &p.b_map, &bfull_bar[bstage],
-                               tap * p.cin + cb * KBLK, n0);
+              ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], Cfg::BSTAGE_BYTES);
+              uint8_t* sb = smem + Cfg::NA * HALO_SLOT + bstage * Cfg::BSTAGE_BYTES;
+#pragma unroll
+              for (int t = 0; t < Cfg::TPS; ++t)
+                ptx::tma_load_2d(sb + t * Cfg::B_BYTES, &p.b_map, &bfull_bar[bstage],
+                                 (tg * Cfg::TPS + t) * p.cin + cb * KBLK, n0);
               if (++bstage == Cfg::NB) {
                 bstage = 0;
                 bphase ^= 1u;
               }
             }
           }
-          continue;
-        }
+        } else {
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy = 0, dx = 0, mi = 0;
           if (p.tap_mode == 0) {
@@ -174,11 +194,12 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
             }
           }
         }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
       int stage = 0, bstage = 0;
       uint32_t phase = 0, bphase = 0;
@@ -192,20 +213,31 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         if constexpr (HALO) {
+          // descriptor templates: everything but the 14-bit start-address field (shared memory addresses are < 256 KB,
+          // so adding (address >> 4) never carries out of the field)
+          const uint64_t adesc0 = ptx::make_smem_desc(0, 16, HALO_W * 128);
+          const uint64_t bdesc0 = ptx::make_smem_desc(0, 16, 1024);
+          const uint32_t sa16 = ptx::smem_u32(smem) >> 4;
+          const uint32_t sb16 = (ptx::smem_u32(smem) + Cfg::NA * HALO_SLOT) >> 4;
           for (int cb = 0; cb < cblocks; ++cb) {
             ptx::mbar_wait(&full_bar[stage], phase);
-            const uint32_t sa = ptx::smem_u32(smem + stage * HALO_SLOT);
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t adesc = adesc0 + (sa16 + stage * (HALO_SLOT >> 4));
+#pragma unroll
+            for (int tg = 0; tg < 9 / Cfg::TPS; ++tg) {
               ptx::mbar_wait(&bfull_bar[bstage], bphase);
               ptx::tc_fence_after();
-              const uint32_t sb = ptx::smem_u32(smem + Cfg::NA * HALO_SLOT + bstage * Cfg::B_BYTES);
-              // output pixel (ty,tx) reads halo pixel (ty+ky, tx+kx): first row (ky*10+kx), row groups 10 pixels apart
-              const uint64_t adesc = ptx::make_smem_desc(sa + ((tap / 3) * HALO_W + tap % 3) * 128, 16, HALO_W * 128);
-              const uint64_t bdesc = ptx::make_smem_desc(sb, 16, 1024);
+              const uint64_t bdesc = bdesc0 + (sb16 + bstage * (Cfg::BSTAGE_BYTES >> 4));
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k)
-                ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) != 0);
+              for (int t = 0; t < Cfg::TPS; ++t) {
+                const int tap = tg * Cfg::TPS + t;
+                // output pixel (ty,tx) reads halo pixel (ty+ky, tx+kx): first row (ky*10+kx), row groups 10 pixels apart
+                const uint32_t aoff = (((tap / 3) * HALO_W + tap % 3) * 128) >> 4;
+                const uint32_t boff = (t * Cfg::B_BYTES) >> 4;
+#pragma unroll
+                for (int k = 0; k < KBLK / 16; ++k)
+                  ptx::umma_bf16(d_tmem, adesc + (aoff + 2 * k), bdesc + (boff + 2 * k), idesc,
+                                 (tap | k) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
+              }
               ptx::umma_commit(&bempty_bar[bstage]);
               if (++bstage == Cfg::NB) {
                 bstage = 0;
@@ -218,9 +250,7 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
               phase ^= 1u;
             }
           }
-          ptx::umma_commit(&tmem_full[as]);
-          continue;
-        }
+        } else {
         for (int ks = 0; ks < ksteps; ++ks) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -238,23 +268,47 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
             phase ^= 1u;
           }
         }
+        }
         ptx::umma_commit(&tmem_full[as]);
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int e = threadIdx.x - 128;  // 0..127
-    const int q = warp & 3;           // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;      // tile row <-> pixel
+    // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column groups =====================
+    const int e = threadIdx.x - 128;      // 0..255
+    const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware: warp id % 4)
+    const int h = (warp - 4) >> 2;        // column group: this warp owns the 32-column chunks h, h+2, ...
+    const int r = q * 32 + lane;          // tile row <-> pixel
     const int py = HALO ? (r >> 3) : (r >> 4), px = HALO ? (r & 7) : (r & 15);
     constexpr int POOL_Y_XOR = HALO ? 8 : 16;  // lane distance of the vertical 2x2-pool partner
+    constexpr int NCHUNK = BLOCK_N / 32;
+    // one n-tile for the whole kernel: scale/shift are loaded once, and with one chunk per warp the BN statistics
+    // stay in per-thread registers until the CTA has finished all of its tiles (no shuffles in the tile loop)
+    const bool fixed_n = (p.n_tiles == 1);
+    const bool run_stats = (EPI == EPI_STATS) && (NCHUNK == EPI_COLGROUPS) && fixed_n;
+    float r1[32], r2[32];
+    if (EPI == EPI_STATS && NCHUNK == EPI_COLGROUPS) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r1[j] = r2[j] = 0.f;
+    }
+    auto load_affine = [&](int as, int n0) {
+      float* sc = s_affine + as * 2 * BLOCK_N;
+      float* sh = sc + BLOCK_N;
+      for (int i = e; i < BLOCK_N; i += EPI_THREADS) {
+        sc[i] = p.scale ? p.scale[n0 + i] : 1.0f;
+        // ConvTranspose scatter: N index = (ky,kx,co) and the bias is per co
+        sh[i] = p.shift ? p.shift[p.convt_cout > 0 ? (n0 + i) % p.convt_cout : n0 + i] : 0.0f;
+      }
+    };
+    if (fixed_n) {
+      load_affine(0, 0);
+      epi_bar();
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
-      const int m_tile_id = tile / p.n_tiles;
-      int m_tile = m_tile_id;
+      int m_tile = tile / p.n_tiles;
       const int tx = m_tile % p.tiles_x;
       m_tile /= p.tiles_x;
       const int ty = m_tile % p.tiles_y;
@@ -263,14 +317,14 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       const int y = ty * TH + py, x = tx * TW + px;
       const bool valid = (y < p.H) && (x < p.W);
 
-      float* sc = s_affine + as * 2 * BLOCK_N;
-      float* sh = sc + BLOCK_N;
-      for (int i = e; i < BLOCK_N; i += 128) {
-        sc[i] = p.scale ? p.scale[n0 + i] : 1.0f;
-        // ConvTranspose scatter: N index = (ky,kx,co) and the bias is per co
-        sh[i] = p.shift ? p.shift[p.convt_cout > 0 ? (n0 + i) % p.convt_cout : n0 + i] : 0.0f;
+      if (!fixed_n) {
+        load_affine(as, n0);
+        epi_bar();
+      } else if (EPI == EPI_STATS && !run_stats) {
+        epi_bar();  // the previous tile's s_red rows have been consumed
       }
-      epi_bar();
+      const float* sc = s_affine + (fixed_n ? 0 : as) * 2 * BLOCK_N;
+      const float* sh = sc + BLOCK_N;
 
       ptx::mbar_wait(&tmem_full[as], aphase);
       ptx::tc_fence_after();
@@ -278,21 +332,30 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       float logit[CRIMAC_MAX_CLASSES];
       if (EPI == EPI_HEAD) {
 #pragma unroll
-        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] = (k < p.n_classes) ? s_head[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
+        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+          logit[k] = (h == 0 && k < p.n_classes) ? s_head[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
       }
 
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      for (int chunk = h; chunk < NCHUNK; chunk += EPI_COLGROUPS) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + chunk * 32, v);
         ptx::tmem_ld_wait();
         const int ng = n0 + chunk * 32;
         float f[32];
+        const float4* sc4 = reinterpret_cast<const float4*>(sc + chunk * 32);
+        const float4* sh4 = reinterpret_cast<const float4*>(sh + chunk * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(v[j]) * sc[chunk * 32 + j] + sh[chunk * 32 + j];
-          if (EPI != EPI_STATS && p.relu) a = fmaxf(a, 0.f);
-          f[j] = a;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 s = sc4[j4], t = sh4[j4];
+          f[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), s.x, t.x);
+          f[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), s.y, t.y);
+          f[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), s.z, t.z);
+          f[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), s.w, t.w);
+        }
+        if (EPI != EPI_STATS && p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         uint32_t pk[16];
 #pragma unroll
@@ -345,20 +408,30 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
 
         if (EPI == EPI_STATS) {
           // statistics of the bf16-rounded values the BN-apply pass will read back
-          float s1[32], s2[32];
+          if (NCHUNK == EPI_COLGROUPS && run_stats) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 t = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&pk[j]));
-            const float a = valid ? t.x : 0.f, b = valid ? t.y : 0.f;
-            s1[2 * j] = a;
-            s1[2 * j + 1] = b;
-            s2[2 * j] = a * a;
-            s2[2 * j + 1] = b * b;
+            for (int j = 0; j < 16; ++j) {
+              const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
+              r1[2 * j] += t.x;
+              r1[2 * j + 1] += t.y;
+              r2[2 * j] = fmaf(t.x, t.x, r2[2 * j]);
+              r2[2 * j + 1] = fmaf(t.y, t.y, r2[2 * j + 1]);
+            }
+          } else {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
+              s1[2 * j] = t.x;
+              s1[2 * j + 1] = t.y;
+              s2[2 * j] = t.x * t.x;
+              s2[2 * j + 1] = t.y * t.y;
+            }
+            xpose_reduce(s1, lane);
+            xpose_reduce(s2, lane);
+            s_red[(q * 2 + 0) * BLOCK_N + chunk * 32 + lane] = s1[0];
+            s_red[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = s2[0];
           }
-          xpose_reduce(s1, lane);
-          xpose_reduce(s2, lane);
-          s_red[(q * 2 + 0) * BLOCK_N + chunk * 32 + lane] = s1[0];
-          s_red[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = s2[0];
         }
       }
 
@@ -366,10 +439,10 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[as]);
 
-      if (EPI == EPI_STATS) {
+      if (EPI == EPI_STATS && !run_stats) {
         epi_bar();
         const int n_total = p.n_tiles * BLOCK_N;
-        for (int c = e; c < BLOCK_N; c += 128) {
+        for (int c = e; c < BLOCK_N; c += EPI_THREADS) {
           float a = 0.f, b = 0.f;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -382,37 +455,70 @@ __global__ void __launch_bounds__(256, 1) conv_igemm_kernel(const __grid_constan
         }
       }
 
-      if (EPI == EPI_HEAD && valid) {
-        if (p.head_softmax) {
-          float mx = logit[0];
-#pragma unroll
-          for (int k = 1; k < CRIMAC_MAX_CLASSES; ++k)
-            if (k < p.n_classes) mx = fmaxf(mx, logit[k]);
-          float sum = 0.f;
+      if (EPI == EPI_HEAD) {
+        // the two column groups each hold the head's dot product over their 32 channels: group 1 hands its part over
+        float* xch = s_hx + (as * TILE_M + r) * CRIMAC_MAX_CLASSES;
+        if (h == 1) {
 #pragma unroll
           for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-            if (k < p.n_classes) {
-              logit[k] = __expf(logit[k] - mx);
-              sum += logit[k];
-            }
-          const float inv = 1.f / sum;
-#pragma unroll
-          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] *= inv;
+            if (k < p.n_classes) xch[k] = logit[k];
         }
+        epi_bar();
+        if (h == 0 && valid) {
 #pragma unroll
-        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-          if (k < p.n_classes)
-            p.head_out[((static_cast<long>(img) * p.n_classes + k) * p.H + y) * p.W + x] = logit[k];
+          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+            if (k < p.n_classes) logit[k] += xch[k];
+          if (p.head_softmax) {
+            float mx = logit[0];
+#pragma unroll
+            for (int k = 1; k < CRIMAC_MAX_CLASSES; ++k)
+              if (k < p.n_classes) mx = fmaxf(mx, logit[k]);
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+              if (k < p.n_classes) {
+                logit[k] = __expf(logit[k] - mx);
+                sum += logit[k];
+              }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] *= inv;
+          }
+#pragma unroll
+          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+            if (k < p.n_classes)
+              p.head_out[((static_cast<long>(img) * p.n_classes + k) * p.H + y) * p.W + x] = logit[k];
+        }
+      }
+    }
+
+    if (EPI == EPI_STATS) {
+      // one partial row per CTA: stats[blockIdx.x][2][n_total]; bn_finalize sums gridDim.x rows
+      const int n_total = p.n_tiles * BLOCK_N;
+      const int n2 = 2 * n_total;
+      if (NCHUNK == EPI_COLGROUPS && run_stats) {
+        xpose_reduce(r1, lane);
+        xpose_reduce(r2, lane);
+        s_red[(q * 2 + 0) * BLOCK_N + h * 32 + lane] = r1[0];
+        s_red[(q * 2 + 1) * BLOCK_N + h * 32 + lane] = r2[0];
+        epi_bar();
+        for (int c = e; c < BLOCK_N; c += EPI_THREADS) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            a += s_red[(w * 2 + 0) * BLOCK_N + c];
+            b += s_red[(w * 2 + 1) * BLOCK_N + c];
+          }
+          p.stats[static_cast<long>(blockIdx.x) * n2 + c] = a;
+          p.stats[static_cast<long>(blockIdx.x) * n2 + n_total + c] = b;
+        }
+      } else {
+        epi_bar();
+        for (int i = e; i < n2; i += EPI_THREADS) p.stats[static_cast<long>(blockIdx.x) * n2 + i] = s_acc[i];
       }
     }
   }
 
-  if (EPI == EPI_STATS && warp >= 4) {
-    // one partial row per CTA: stats[blockIdx.x][2][n_total]; bn_finalize sums gridDim.x rows
-    const int n2 = 2 * p.n_tiles * BLOCK_N;
-    epi_bar();
-    for (int i = threadIdx.x - 128; i < n2; i += 128) p.stats[static_cast<long>(blockIdx.x) * n2 + i] = s_acc[i];
-  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -431,8 +537,9 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  if (EPI == EPI_STATS && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
 

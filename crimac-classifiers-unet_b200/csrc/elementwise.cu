@@ -151,20 +151,32 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           float* running_var, long long* num_batches_tracked,
                                                           float momentum, float eps, float* scale, float* shift,
                                                           float* save_mean, float* save_invstd) {
-  __shared__ double sh[2][8][32];
-  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // block = 8 channels x 32 row-lanes: short dependent load chains (the kernel is pure latency)
+  __shared__ double sh[2][32][8];
+  const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   double s1 = 0.0, s2 = 0.0;
-  if (c < C)
-    for (int t = tl; t < m_tiles; t += 8) {
-      s1 += partials[static_cast<long>(t) * 2 * C + c];
-      s2 += partials[static_cast<long>(t) * 2 * C + C + c];
+  if (c < C) {
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains; partial rows are few and O(1e4) each
+    int t = tl;
+    for (; t + 32 < m_tiles; t += 64) {
+      a0 += partials[static_cast<long>(t) * 2 * C + c];
+      b0 += partials[static_cast<long>(t) * 2 * C + C + c];
+      a1 += partials[static_cast<long>(t + 32) * 2 * C + c];
+      b1 += partials[static_cast<long>(t + 32) * 2 * C + C + c];
     }
+    if (t < m_tiles) {
+      a0 += partials[static_cast<long>(t) * 2 * C + c];
+      b0 += partials[static_cast<long>(t) * 2 * C + C + c];
+    }
+    s1 = static_cast<double>(a0) + static_cast<double>(a1);
+    s2 = static_cast<double>(b0) + static_cast<double>(b1);
+  }
   sh[0][tl][cl] = s1;
   sh[1][tl][cl] = s2;
   __syncthreads();
   if (tl == 0 && c < C) {
-    for (int t = 1; t < 8; ++t) {
+    for (int t = 1; t < 32; ++t) {
       s1 += sh[0][t][cl];
       s2 += sh[1][t][cl];
     }
@@ -345,73 +357,90 @@ __global__ void ce_finalize_kernel(const double* partials, int nblocks, float* o
 
 // ============================================================================ 1x1 head backward
 // dAct[p][c] = s * sum_k dl[k][p] W[k][c];  dW[k][c] = s * sum_p dl[k][p] act[p][c];  db[k] = s * sum_p dl[k][p]
-// (s = *gscale or 1).  One block = 128 pixels per iteration; partials per block, summed by head_bwd_finalize.
+// (s = *gscale or 1).  A thread owns one 8-channel group for its lifetime (8 threads per pixel: every warp access is
+// 512 contiguous bytes) and keeps its dW partial sums in registers; per-block partials are summed by
+// head_bwd_finalize.
+template <int NCLS>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dlogits, const float* gscale,
-                                                       View act, const float* __restrict__ hw, int ncls, View dact,
+                                                       View act, const float* __restrict__ hw, View dact,
                                                        float* partials) {
-  constexpr int TPB = 256;
-  __shared__ float s_w[CRIMAC_MAX_CLASSES * 64];
-  __shared__ float s_dl[TPB][CRIMAC_MAX_CLASSES + 1];
-  __shared__ __align__(16) bf16 s_act[TPB][72];
-  for (int i = threadIdx.x; i < ncls * 64; i += TPB) s_w[i] = hw[i];
+  __shared__ float s_part[8][NCLS * 64 + NCLS];
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float s = gscale ? *gscale : 1.f;
   const long HW = static_cast<long>(act.H) * act.W;
   const long total = act.N * HW;
-  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;  // dW phase: channel c over pixels [part*64, part*64+64)
-  float accw[CRIMAC_MAX_CLASSES], accb[CRIMAC_MAX_CLASSES];
+  float w[NCLS][8], accw[NCLS][8], accb[NCLS];
 #pragma unroll
-  for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) accw[k] = accb[k] = 0.f;
-  __syncthreads();
-  for (long base = static_cast<long>(blockIdx.x) * TPB; base < total; base += static_cast<long>(gridDim.x) * TPB) {
-    const long p = base + threadIdx.x;
-    const bool valid = p < total;
-    float dl[CRIMAC_MAX_CLASSES];
-    const long n = valid ? p / HW : 0, r = valid ? p - n * HW : 0;
+  for (int k = 0; k < NCLS; ++k) {
+    ldg8f(hw + k * 64 + g * 8, w[k]);
+    accb[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) {
-      dl[k] = (valid && k < ncls) ? s * dlogits[(n * ncls + k) * HW + r] : 0.f;
-      if (k < ncls) s_dl[threadIdx.x][k] = dl[k];
+    for (int j = 0; j < 8; ++j) accw[k][j] = 0.f;
+  }
+  const long stride = static_cast<long>(gridDim.x) * 32;
+  for (long p0 = static_cast<long>(blockIdx.x) * 32 + pl; p0 < total; p0 += 2 * stride) {
+    float dl[2][NCLS], a[2][8];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long p = p0 + u * stride;
+      ok[u] = p < total;
+      const long n = ok[u] ? p / HW : 0, r = ok[u] ? p - n * HW : 0;
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) dl[u][k] = ok[u] ? s * __ldg(&dlogits[(n * NCLS + k) * HW + r]) : 0.f;
+      if (ok[u]) {
+        load8(act.ptr + p * act.pitch + g * 8, a[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[u][j] = 0.f;
+      }
     }
-    uint4 av[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g)
-      av[g] = valid ? *reinterpret_cast<const uint4*>(act.ptr + p * act.pitch + g * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      *reinterpret_cast<uint4*>(&s_act[threadIdx.x][g * 8]) = av[g];
+    for (int u = 0; u < 2; ++u) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float a = 0.f;
+        float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-          if (k < ncls) a = fmaf(dl[k], s_w[k * 64 + g * 8 + j], a);
-        o[j] = a;
-      }
-      if (valid) store8(dact.ptr + p * dact.pitch + g * 8, o);
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int q = part * 64; q < part * 64 + 64; ++q) {
-      const float a = __bfloat162float(s_act[q][c]);
-#pragma unroll
-      for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-        if (k < ncls) {
-          const float d = s_dl[q][k];
-          accw[k] = fmaf(d, a, accw[k]);
-          if (c == 0) accb[k] += d;
+        for (int k = 0; k < NCLS; ++k) {
+          t = fmaf(dl[u][k], w[k][j], t);
+          accw[k][j] = fmaf(dl[u][k], a[u][j], accw[k][j]);
         }
-    }
-    __syncthreads();
-  }
-  // partial layout per block: [4 parts][ncls*64 + ncls]
-  float* dst = partials + (static_cast<long>(blockIdx.x) * 4 + part) * (ncls * 64 + ncls);
+        o[j] = t;
+      }
 #pragma unroll
-  for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-    if (k < ncls) {
-      dst[k * 64 + c] = accw[k];
-      if (c == 0) dst[ncls * 64 + k] = accb[k];
+      for (int k = 0; k < NCLS; ++k) accb[k] += dl[u][k];
+      if (ok[u]) store8(dact.ptr + (p0 + u * stride) * dact.pitch + g * 8, o);
     }
+  }
+  // lanes g, g+8, g+16, g+24 of a warp hold the same channel group
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      accw[k][j] += __shfl_xor_sync(0xffffffffu, accw[k][j], 8);
+      accw[k][j] += __shfl_xor_sync(0xffffffffu, accw[k][j], 16);
+    }
+    accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], 8);
+    accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_part[warp][k * 64 + g * 8 + j] = accw[k][j];
+      if (g == 0) s_part[warp][NCLS * 64 + k] = accb[k];
+    }
+  }
+  __syncthreads();
+  constexpr int PER = NCLS * 64 + NCLS;
+  for (int i = threadIdx.x; i < PER; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += s_part[wv][i];
+    partials[static_cast<long>(blockIdx.x) * PER + i] = t;
+  }
 }
 __global__ void head_bwd_finalize_kernel(const float* partials, int nparts, int ncls, float* dw, float* db,
                                          int accumulate) {
@@ -496,23 +525,39 @@ template <int NQ>
 __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* __restrict__ partials, int nparts, int C,
                                                                    double count, float* out0, float* out1,
                                                                    int accumulate, float* c1, float* c2) {
-  __shared__ double sh[NQ][8][32];
-  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // block = 8 channels x 32 part-lanes (short dependent load chains)
+  __shared__ double sh[NQ][32][8];
+  const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   double a[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) a[q] = 0.0;
-  if (c < C)
-    for (int i = tl; i < nparts; i += 8)
+  if (c < C) {
+    float f0[NQ], f1[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) a[q] += partials[(static_cast<long>(i) * NQ + q) * C + c];
+    for (int q = 0; q < NQ; ++q) f0[q] = f1[q] = 0.f;
+    int i = tl;
+    for (; i + 32 < nparts; i += 64) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        f0[q] += partials[(static_cast<long>(i) * NQ + q) * C + c];
+        f1[q] += partials[(static_cast<long>(i + 32) * NQ + q) * C + c];
+      }
+    }
+    if (i < nparts) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) f0[q] += partials[(static_cast<long>(i) * NQ + q) * C + c];
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) a[q] = static_cast<double>(f0[q]) + static_cast<double>(f1[q]);
+  }
 #pragma unroll
   for (int q = 0; q < NQ; ++q) sh[q][tl][cl] = a[q];
   __syncthreads();
   if (tl == 0 && c < C) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
-      for (int t = 1; t < 8; ++t) a[q] += sh[q][t][cl];
+      for (int t = 1; t < 32; ++t) a[q] += sh[q][t][cl];
     out0[c] = accumulate ? out0[c] + static_cast<float>(a[0]) : static_cast<float>(a[0]);
     if (NQ == 2) {
       out1[c] = accumulate ? out1[c] + static_cast<float>(a[NQ - 1]) : static_cast<float>(a[NQ - 1]);
@@ -775,7 +820,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 #define FW(C)                                                                                       \
   if (cin == C) {                                                                                   \
     first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
-    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 31) / 32, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr); \
+    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
   FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
@@ -786,7 +831,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double count, const float* gamma,
                                const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
                                float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(partials, m_tiles, C, count, gamma, beta, rm, rv, nbt, momentum,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, m_tiles, C, count, gamma, beta, rm, rv, nbt, momentum,
                                                     eps, scale, shift, save_mean, save_invstd);
   return cudaGetLastError();
 }
@@ -825,11 +870,15 @@ int head_bwd_blocks() { return 148 * 4; }
 cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act, const float* hw, int ncls, View dact,
                             float* partials, float* dw, float* db, int accumulate, cudaStream_t st) {
   const long px = static_cast<long>(act.N) * act.H * act.W;
-  int blocks = grid_for(px, 256);
+  if (act.C != 64) return cudaErrorInvalidValue;
+  int blocks = grid_for(px, 64);
   if (blocks > head_bwd_blocks()) blocks = head_bwd_blocks();
-  head_bwd_kernel<<<blocks, 256, 0, st>>>(dlogits, gscale, act, hw, ncls, dact, partials);
+#define HB(K)                                                                                        \
+  if (ncls == K) head_bwd_kernel<K><<<blocks, 256, 0, st>>>(dlogits, gscale, act, hw, dact, partials);
+  HB(1) HB(2) HB(3) HB(4) HB(5) HB(6) HB(7) HB(8)
+#undef HB
   const int per = ncls * 64 + ncls;
-  head_bwd_finalize_kernel<<<(per + 127) / 128, 128, 0, st>>>(partials, blocks * 4, ncls, dw, db, accumulate);
+  head_bwd_finalize_kernel<<<(per + 127) / 128, 128, 0, st>>>(partials, blocks, ncls, dw, db, accumulate);
   return cudaGetLastError();
 }
 
@@ -852,11 +901,11 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
   bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, partials);
-  partial_sum_finalize_kernel<2><<<(C + 31) / 32, 256, 0, st>>>(partials, grid, C, count, dbeta, dgamma, accumulate, c1c2,
+  partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, count, dbeta, dgamma, accumulate, c1c2,
                                                                 c1c2 + C);
   bn_bwd_apply_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C,
                                                                   draw, partials);
-  partial_sum_finalize_kernel<1><<<(C + 31) / 32, 256, 0, st>>>(partials, grid, C, 1.0, dbias, nullptr, accumulate, nullptr,
+  partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, dbias, nullptr, accumulate, nullptr,
                                                                 nullptr);
   return cudaGetLastError();
 }
@@ -866,7 +915,7 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
   const int grid = reduce_grid(v);
   const int ppb = 256 / (C / 8);
   view_colsum_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(v, partials);
-  partial_sum_finalize_kernel<1><<<(C + 31) / 32, 256, 0, st>>>(partials, grid, C, 1.0, out, nullptr, accumulate, nullptr,
+  partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, out, nullptr, accumulate, nullptr,
                                                                 nullptr);
   return cudaGetLastError();
 }

@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (ksteps > 0) {
-    if (warp == 0 && lane == 0) {
+    // single-thread roles are chosen with elect.sync so that the compiler emits the uniform-datapath TMA / MMA
+    // instructions without per-instruction active-thread loops
+    if (warp == 0) {
+      if (ptx::elect_one()) {
       // ===================== TMA producer =====================
       int dy = 0, dx = 0, mi = 0;
       if (p.tap_mode == 0) {
@@ -117,7 +120,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const __grid_constan
           phase ^= 1u;
         }
       }
-    } else if (warp == 1 && lane == 0) {
+      }
+    } else if (warp == 1) {
+      if (ptx::elect_one()) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
       int stage = 0;
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const __grid_constan
         }
       }
       ptx::umma_commit(acc_bar);
+      }
     } else if (warp >= 4) {
       // ===================== epilogue: TMEM -> red.add into [tap][m][n] scratch =====================
       const int q = warp & 3;
@@ -257,7 +263,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
   constexpr int PB[5] = {7, 5, 3, 1, 0};
 
   if (ksteps > 0) {
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+      if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = kt_begin; kt < kt_end; ++kt) {
@@ -277,7 +284,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
           phase ^= 1u;
         }
       }
-    } else if (warp == 1 && lane == 0) {
+      }
+    } else if (warp == 1) {
+      if (ptx::elect_one()) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);
       // per pair: descriptor (without start address) and the byte offset of the first tap's view
       uint64_t dtmpl[5];
@@ -312,6 +321,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
         }
       }
       ptx::umma_commit(acc_bar);
+      }
     } else if (warp >= 4) {
       const int q = warp & 3;
       const int m = q * 32 + lane;
