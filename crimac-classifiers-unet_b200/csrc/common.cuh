@@ -31,7 +31,9 @@ enum EpiMode : int {
 
 struct ConvParams {
   CUtensorMap a_map[4];  // activations; 3x3 / 1x1 use map 0, convT backward-data uses one map per (ky,kx)
-  CUtensorMap b_map;     // packed weights [N_total][taps*cin] bf16, K contiguous
+  CUtensorMap b_map;     // packed weights [N_total][taps*cin] bf16, K contiguous (b_mn: the forward matrix, box {64,64})
+  int b_mn;              // 1: backward-data on forward-packed weights (B operand MN-major); see conv_igemm.cu
+  int b_tap_cols;        // b_mn, 3x3: columns per tap of the forward matrix (= its Cin = this GEMM's N_total)
   int taps;              // 9, 1 or 4
   int tap_mode;          // 0: tap -> (dy,dx) offsets on map 0 (3x3: tap=ky*3+kx; 1 tap: centre); 1: tap -> map index
   int halo;              // 1: 3x3 conv with the 16x8 tile / halo-box main loop (a_map[0] = box {64,10,18,1})

@@ -65,7 +65,7 @@ constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int CONV_THREADS = 128 + EPI_THREADS;
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
-template <int BLOCK_N, int EPI, bool HALO>
+template <int BLOCK_N, int EPI, bool HALO, bool BMN>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N, HALO>;
   constexpr int TW = HALO ? 8 : TILE_W;    // tile width (pings)
@@ -161,9 +161,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
               ptx::mbar_arrive_expect_tx(&bfull_bar[bstage], Cfg::BSTAGE_BYTES);
               uint8_t* sb = smem + Cfg::NA * HALO_SLOT + bstage * Cfg::BSTAGE_BYTES;
 #pragma unroll
-              for (int t = 0; t < Cfg::TPS; ++t)
-                ptx::tma_load_2d(sb + t * Cfg::B_BYTES, &p.b_map, &bfull_bar[bstage],
-                                 (tg * Cfg::TPS + t) * p.cin + cb * KBLK, n0);
+              for (int t = 0; t < Cfg::TPS; ++t) {
+                const int tap = tg * Cfg::TPS + t;
+                if constexpr (BMN) {
+                  // backward-data reads the FORWARD-packed weights [Cout][tap][Cin] as an MN-major operand: N = Cin is
+                  // contiguous, the reduction rows (Cout) are 9*Cin elements apart; the kernel is rotated: tap -> 8-tap
+#pragma unroll
+                  for (int b = 0; b < BLOCK_N / 64; ++b)
+                    ptx::tma_load_2d(sb + t * Cfg::B_BYTES + b * 8192, &p.b_map, &bfull_bar[bstage],
+                                     (8 - tap) * p.b_tap_cols + n0 + b * 64, cb * KBLK);
+                } else {
+                  ptx::tma_load_2d(sb + t * Cfg::B_BYTES, &p.b_map, &bfull_bar[bstage], tap * p.cin + cb * KBLK, n0);
+                }
+              }
               if (++bstage == Cfg::NB) {
                 bstage = 0;
                 bphase ^= 1u;
@@ -187,7 +197,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
             uint8_t* sb = sa + Cfg::A_BYTES;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             ptx::tma_load_4d(sa, &p.a_map[mi], &full_bar[stage], cb * KBLK, x0 + dx, y0 + dy, img);
-            ptx::tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.cin + cb * KBLK, n0);
+            if constexpr (BMN) {
+              // ConvTranspose backward-data on the forward-packed weights [(kk,co)][Cin]: N = Cin contiguous,
+              // reduction rows = (tap, co)
+#pragma unroll
+              for (int b = 0; b < BLOCK_N / 64; ++b)
+                ptx::tma_load_2d(sb + b * 8192, &p.b_map, &full_bar[stage], n0 + b * 64, tap * p.cin + cb * KBLK);
+            } else {
+              ptx::tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.cin + cb * KBLK, n0);
+            }
             if (++stage == Cfg::STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -200,7 +218,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BLOCK_N, 0, BMN ? 1 : 0);
+      // K-major B: +32 B per 16-element k-slice inside the 128-byte swizzle row.  MN-major B (BMN): 64-channel boxes
+      // LBO = 8192 B apart, 16 reduction rows further = +2048 B
+      constexpr uint32_t B_KSTEP16 = BMN ? 128 : 2;
       int stage = 0, bstage = 0;
       uint32_t phase = 0, bphase = 0;
       (void)bstage;
@@ -216,7 +237,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
           // descriptor templates: everything but the 14-bit start-address field (shared memory addresses are < 256 KB,
           // so adding (address >> 4) never carries out of the field)
           const uint64_t adesc0 = ptx::make_smem_desc(0, 16, HALO_W * 128);
-          const uint64_t bdesc0 = ptx::make_smem_desc(0, 16, 1024);
+          const uint64_t bdesc0 = BMN ? ptx::make_smem_desc(0, 8192, 1024) : ptx::make_smem_desc(0, 16, 1024);
           const uint32_t sa16 = ptx::smem_u32(smem) >> 4;
           const uint32_t sb16 = (ptx::smem_u32(smem) + Cfg::NA * HALO_SLOT) >> 4;
           for (int cb = 0; cb < cblocks; ++cb) {
@@ -235,7 +256,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
                 const uint32_t boff = (t * Cfg::B_BYTES) >> 4;
 #pragma unroll
                 for (int k = 0; k < KBLK / 16; ++k)
-                  ptx::umma_bf16(d_tmem, adesc + (aoff + 2 * k), bdesc + (boff + 2 * k), idesc,
+                  ptx::umma_bf16(d_tmem, adesc + (aoff + 2 * k), bdesc + (boff + B_KSTEP16 * k), idesc,
                                  (tap | k) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
               }
               ptx::umma_commit(&bempty_bar[bstage]);
@@ -256,11 +277,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = ptx::make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = ptx::make_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
+          const uint64_t bdesc = BMN ? ptx::make_smem_desc(sa + Cfg::A_BYTES, 8192, 1024)
+                                     : ptx::make_smem_desc(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < KBLK / 16; ++k) {
             // +32 bytes (= 16 bf16) along K inside the 128-byte swizzle row: start-address field += 2
-            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + B_KSTEP16 * k, idesc, (ks | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::STAGES) {
@@ -527,10 +549,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   }
 }
 
-template <int BLOCK_N, int EPI, bool HALO>
+template <int BLOCK_N, int EPI, bool HALO, bool BMN>
 cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, HALO>;
-  auto kern = conv_igemm_kernel<BLOCK_N, EPI, HALO>;
+  auto kern = conv_igemm_kernel<BLOCK_N, EPI, HALO, BMN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -548,12 +570,19 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
 // BLOCK_N in {64,128,256}; p.n_tiles*BLOCK_N == N_total must hold.
 cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num_sms, cudaStream_t stream) {
   if (p.halo && p.taps != 9) return cudaErrorInvalidValue;
+  if (p.b_mn && (epi != EPI_STORE || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
 #define CASE(BN, EP)                                                               \
-  if (block_n == BN && epi == EP)                                                  \
-    return p.halo ? launch_one<BN, EP, true>(p, num_sms, stream) : launch_one<BN, EP, false>(p, num_sms, stream);
+  if (block_n == BN && epi == EP && !p.b_mn)                                       \
+    return p.halo ? launch_one<BN, EP, true, false>(p, num_sms, stream) : launch_one<BN, EP, false, false>(p, num_sms, stream);
   CASE(64, EPI_STORE) CASE(128, EPI_STORE) CASE(256, EPI_STORE)
   CASE(64, EPI_STATS) CASE(128, EPI_STATS) CASE(256, EPI_STATS)
   CASE(64, EPI_HEAD)
 #undef CASE
+#define CASE_MN(BN)                                                                \
+  if (block_n == BN && p.b_mn)                                                     \
+    return p.halo ? launch_one<BN, EPI_STORE, true, true>(p, num_sms, stream)      \
+                  : launch_one<BN, EPI_STORE, false, true>(p, num_sms, stream);
+  CASE_MN(64) CASE_MN(128) CASE_MN(256)
+#undef CASE_MN
   return cudaErrorInvalidValue;
 }

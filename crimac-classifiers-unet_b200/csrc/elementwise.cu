@@ -442,6 +442,186 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     partials[static_cast<long>(blockIdx.x) * PER + i] = t;
   }
 }
+// ============================================================================ fused head + cross-entropy + head backward
+// The fused train step (crimac_train_step) never materialises logits: one pass over the last activation computes the
+// 1x1 head (unet.py:342), the class-weighted CE (pipeline.py:135-138,176) and the head's backward.  The loss
+// normaliser 1/sum_w is only known after the whole batch has been reduced, so dAct, dW, db are produced UNNORMALISED;
+// head_ce_finalize scales dW/db and publishes 1/sum_w, which the last layer's BatchNorm backward folds in (it is
+// linear in its incoming gradient).  Thread mapping as head_bwd_kernel: 8 threads per pixel, 8 channels each.
+template <int NCLS>
+__global__ void __launch_bounds__(256) head_ce_fused_kernel(View act, const float* __restrict__ hw,
+                                                            const float* __restrict__ hb,
+                                                            const long long* __restrict__ labels,
+                                                            const float* __restrict__ cw, long long ignore_index,
+                                                            View dact, float* partials, double* loss_partials) {
+  constexpr int PER = NCLS * 64 + NCLS;
+  __shared__ float s_part[8][PER];
+  __shared__ double s_loss[8][2];
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long total = static_cast<long>(act.N) * act.H * act.W;
+  float w[NCLS][8], accw[NCLS][8], accb[NCLS], bias[NCLS], wcls[NCLS];
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) {
+    ldg8f(hw + k * 64 + g * 8, w[k]);
+    bias[k] = hb[k];
+    wcls[k] = cw[k];
+    accb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accw[k][j] = 0.f;
+  }
+  double la = 0.0, lb = 0.0;
+  const long stride = static_cast<long>(gridDim.x) * 32;
+  for (long p0 = static_cast<long>(blockIdx.x) * 32 + pl; p0 < total; p0 += 2 * stride) {
+    float a[2][8];
+    long long y[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long p = p0 + u * stride;
+      ok[u] = p < total;  // uniform over the 8 threads of a pixel
+      y[u] = ok[u] ? labels[p] : ignore_index;
+      if (ok[u]) {
+        load8(act.ptr + p * act.pitch + g * 8, a[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float z[NCLS];
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t = fmaf(a[u][j], w[k][j], t);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        z[k] = t + bias[k];
+      }
+      float mx = z[0];
+#pragma unroll
+      for (int k = 1; k < NCLS; ++k) mx = fmaxf(mx, z[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) sum += expf(z[k] - mx);
+      const float lse = mx + logf(sum);
+      const bool use = ok[u] && (y[u] != ignore_index) && y[u] >= 0 && y[u] < NCLS;
+      float wy = 0.f, zy = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k)
+        if (use && y[u] == k) {
+          wy = wcls[k];
+          zy = z[k];
+        }
+      float dl[NCLS];
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) dl[k] = wy * (expf(z[k] - lse) - ((use && y[u] == k) ? 1.f : 0.f));
+      if (g == 0) {
+        if (use) la += static_cast<double>(wy) * static_cast<double>(lse - zy);
+        lb += wy;
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) {
+          t = fmaf(dl[k], w[k][j], t);
+          accw[k][j] = fmaf(dl[k], a[u][j], accw[k][j]);
+        }
+        o[j] = t;
+      }
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) accb[k] += dl[k];
+      if (ok[u]) store8(dact.ptr + (p0 + u * stride) * dact.pitch + g * 8, o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      accw[k][j] += __shfl_xor_sync(0xffffffffu, accw[k][j], 8);
+      accw[k][j] += __shfl_xor_sync(0xffffffffu, accw[k][j], 16);
+    }
+    accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], 8);
+    accb[k] += __shfl_xor_sync(0xffffffffu, accb[k], 16);
+  }
+  la += __shfl_xor_sync(0xffffffffu, la, 8);
+  la += __shfl_xor_sync(0xffffffffu, la, 16);
+  lb += __shfl_xor_sync(0xffffffffu, lb, 8);
+  lb += __shfl_xor_sync(0xffffffffu, lb, 16);
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_part[warp][k * 64 + g * 8 + j] = accw[k][j];
+      if (g == 0) s_part[warp][NCLS * 64 + k] = accb[k];
+    }
+    if (g == 0) {
+      s_loss[warp][0] = la;
+      s_loss[warp][1] = lb;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PER; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += s_part[wv][i];
+    partials[static_cast<long>(blockIdx.x) * PER + i] = t;
+  }
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int wv = 0; wv < 8; ++wv) t += s_loss[wv][threadIdx.x];
+    loss_partials[2 * blockIdx.x + threadIdx.x] = t;
+  }
+}
+// out3 = {loss, 1/sum_w, sum_w}; dw, db = (1/sum_w) * sum over blocks of the unnormalised partials.
+// Block = 8 gradient elements x 32 block-lanes; every block re-derives sum_w (cheap) so that one launch suffices.
+__global__ void __launch_bounds__(256) head_ce_finalize_kernel(const float* __restrict__ partials,
+                                                               const double* __restrict__ loss_partials, int nblocks,
+                                                               int ncls, float* dw, float* db, float* out3) {
+  __shared__ double s_a[256], s_b[256];
+  __shared__ float s_g[32][8];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) {
+    a += loss_partials[2 * i];
+    b += loss_partials[2 * i + 1];
+  }
+  s_a[threadIdx.x] = a;
+  s_b[threadIdx.x] = b;
+  const int per = ncls * 64 + ncls;
+  const int el = threadIdx.x & 7, bl = threadIdx.x >> 3;
+  const int i = blockIdx.x * 8 + el;
+  float t = 0.f;
+  if (i < per)
+    for (int blk = bl; blk < nblocks; blk += 32) t += partials[static_cast<long>(blk) * per + i];
+  s_g[bl][el] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (static_cast<int>(threadIdx.x) < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  a = s_a[0];
+  b = s_b[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out3[0] = static_cast<float>(a / b);  // all-ignored batch -> NaN, as the reference
+    out3[1] = static_cast<float>(1.0 / b);
+    out3[2] = static_cast<float>(b);
+  }
+  if (bl == 0 && i < per) {
+    double g = 0.0;
+    for (int l = 0; l < 32; ++l) g += s_g[l][el];
+    const float v = static_cast<float>(g / b);
+    if (i < ncls * 64) dw[i] = v; else db[i - ncls * 64] = v;
+  }
+}
+
 __global__ void head_bwd_finalize_kernel(const float* partials, int nparts, int ncls, float* dw, float* db,
                                          int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -524,7 +704,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dact, View raw,
 template <int NQ>
 __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* __restrict__ partials, int nparts, int C,
                                                                    double count, float* out0, float* out1,
-                                                                   int accumulate, float* c1, float* c2) {
+                                                                   int accumulate, float* c1, float* c2,
+                                                                   const float* gscale) {
   // block = 8 channels x 32 part-lanes (short dependent load chains)
   __shared__ double sh[NQ][32][8];
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
@@ -555,9 +736,12 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
   for (int q = 0; q < NQ; ++q) sh[q][tl][cl] = a[q];
   __syncthreads();
   if (tl == 0 && c < C) {
+    const double gs = gscale ? static_cast<double>(*gscale) : 1.0;  // incoming gradient was produced unnormalised
 #pragma unroll
-    for (int q = 0; q < NQ; ++q)
+    for (int q = 0; q < NQ; ++q) {
       for (int t = 1; t < 32; ++t) a[q] += sh[q][t][cl];
+      a[q] *= gs;
+    }
     out0[c] = accumulate ? out0[c] + static_cast<float>(a[0]) : static_cast<float>(a[0]);
     if (NQ == 2) {
       out1[c] = accumulate ? out1[c] + static_cast<float>(a[NQ - 1]) : static_cast<float>(a[NQ - 1]);
@@ -573,7 +757,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, 
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ c1, const float* __restrict__ c2,
-                                                           View draw, float* partials) {
+                                                           const float* gscale, View draw, float* partials) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
@@ -584,6 +768,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, 
   ldg8f(invstd + g * 8, is);
   ldg8f(c1 + g * 8, k1);
   ldg8f(c2 + g * 8, k2);
+  const float gs = gscale ? *gscale : 1.f;
   float acc[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
@@ -598,7 +783,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, 
         load8(raw.ptr + p * raw.pitch + g * 8, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] : 0.f;
+          const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] * gs : 0.f;
           const float xh = (r[j] - mu[j]) * is[j];
           o[j] = sc[j] * (gg - k1[j] - xh * k2[j]);
         }
@@ -757,31 +942,46 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const float* __re
 }
 
 // ============================================================================ weight packing (fp32 params -> bf16 GEMM operands)
-// conv (Cout,Cin,3,3) -> fwd [Cout][tap][Cin] and bwd-data [Cin][8-tap][Cout]
-__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int Cout, int Cin, bf16* fwd, bf16* bwd) {
-  const long total = static_cast<long>(Cout) * Cin * 9;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    // i indexes the fwd layout (ci fastest) so the bf16 writes of the forward operand are coalesced
-    const int ci = static_cast<int>(i % Cin);
-    const int tap = static_cast<int>((i / Cin) % 9);
-    const int co = static_cast<int>(i / (static_cast<long>(Cin) * 9));
-    const bf16 v = __float2bfloat16(w[(static_cast<long>(co) * Cin + ci) * 9 + tap]);
-    if (fwd) fwd[i] = v;
-    if (bwd) bwd[(static_cast<long>(ci) * 9 + (8 - tap)) * Cout + co] = v;
+// ONE launch per layer kind for the whole network (the parameters change every optimisation step, so packing is on the
+// training hot path).  Both kernels go through shared memory so that the fp32 reads and the bf16 writes are coalesced.
+// Backward-data needs no second copy: it reads these forward-packed matrices as an MN-major operand (conv_igemm.cu).
+//
+// conv (Cout,Cin,3,3) -> [Cout][tap][Cin].  Work item = one output channel x up to 256 input channels.
+__global__ void __launch_bounds__(256) pack_conv3x3_all_kernel(const __grid_constant__ PackTable t) {
+  __shared__ float s[256 * 9];
+  int li = 0;
+  while (li + 1 < t.n && static_cast<int>(blockIdx.x) >= t.e[li + 1].item0) ++li;
+  const PackEntry& L = t.e[li];
+  const int chunks = (L.cin + 255) / 256;
+  const int item = blockIdx.x - L.item0;
+  const int co = item / chunks, ci0 = (item % chunks) * 256;
+  const int n = min(256, L.cin - ci0);
+  const float* src = L.w + (static_cast<long>(co) * L.cin + ci0) * 9;
+  for (int i = threadIdx.x; i < n * 9; i += 256) s[i] = src[i];
+  __syncthreads();
+  bf16* dst = L.out + static_cast<long>(co) * 9 * L.cin + ci0;
+  const int half = n >> 1;  // Cin is a multiple of 64
+  for (int j = threadIdx.x; j < 9 * half; j += 256) {
+    const int tap = j / half, c = (j - tap * half) * 2;
+    *reinterpret_cast<uint32_t*>(dst + static_cast<long>(tap) * L.cin + c) = pack_bf16x2(s[c * 9 + tap], s[(c + 1) * 9 + tap]);
   }
 }
-// convT (Cin,Cout,2,2) -> fwd [(kk*Cout+co)][Cin] and bwd-data [Cin][(kk*Cout+co)]
-__global__ void pack_convt_kernel(const float* __restrict__ w, int Cin, int Cout, bf16* fwd, bf16* bwd) {
-  const long total = static_cast<long>(Cin) * Cout * 4;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % Cin);
-    const int co = static_cast<int>((i / Cin) % Cout);
-    const int kk = static_cast<int>(i / (static_cast<long>(Cin) * Cout));
-    const bf16 v = __float2bfloat16(w[(static_cast<long>(ci) * Cout + co) * 4 + kk]);
-    if (fwd) fwd[i] = v;
-    if (bwd) bwd[static_cast<long>(ci) * 4 * Cout + kk * Cout + co] = v;
+// convT (Cin,Cout,2,2) -> [(kk*Cout+co)][Cin].  Work item = 32 input channels x 8 output channels (x 4 taps).
+__global__ void __launch_bounds__(256) pack_convt_all_kernel(const __grid_constant__ PackTable t) {
+  __shared__ float s[32][33];
+  int li = 0;
+  while (li + 1 < t.n && static_cast<int>(blockIdx.x) >= t.e[li + 1].item0) ++li;
+  const PackEntry& L = t.e[li];  // cin = Cin, cout = Cout
+  const int item = blockIdx.x - L.item0;
+  const int cgroups = L.cout / 8;
+  const int ci0 = (item / cgroups) * 32, co0 = (item % cgroups) * 8;
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  for (int r = row; r < 32; r += 8)  // 32 consecutive floats (co0..co0+7, kk 0..3) of input channel ci0 + r
+    s[r][lane] = L.w[(static_cast<long>(ci0 + r) * L.cout + co0) * 4 + lane];
+  __syncthreads();
+  for (int j = row; j < 32; j += 8) {  // j = co_local*4 + kk
+    const int co = co0 + (j >> 2), kk = j & 3;
+    L.out[(static_cast<long>(kk) * L.cout + co) * L.cin + ci0 + lane] = __float2bfloat16(s[lane][j]);
   }
 }
 
@@ -820,7 +1020,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 #define FW(C)                                                                                       \
   if (cin == C) {                                                                                   \
     first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
-    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr); \
+    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
   FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
@@ -882,6 +1082,22 @@ cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act,
   return cudaGetLastError();
 }
 
+cudaError_t launch_head_ce_fused(View act, const float* hw, const float* hb, int ncls, const long long* labels,
+                                 const float* cw, long long ignore_index, View dact, float* partials,
+                                 double* loss_partials, float* dw, float* db, float* out3, cudaStream_t st) {
+  const long px = static_cast<long>(act.N) * act.H * act.W;
+  if (act.C != 64) return cudaErrorInvalidValue;
+  int blocks = grid_for(px, 64);
+  if (blocks > head_bwd_blocks()) blocks = head_bwd_blocks();
+#define HC(K)                                                                                                       \
+  if (ncls == K)                                                                                                    \
+    head_ce_fused_kernel<K><<<blocks, 256, 0, st>>>(act, hw, hb, labels, cw, ignore_index, dact, partials, loss_partials);
+  HC(1) HC(2) HC(3) HC(4) HC(5) HC(6) HC(7) HC(8)
+#undef HC
+  head_ce_finalize_kernel<<<(ncls * 64 + ncls + 7) / 8, 256, 0, st>>>(partials, loss_partials, blocks, ncls, dw, db, out3);
+  return cudaGetLastError();
+}
+
 int reduce_blocks() { return 148 * 4; }  // 4 blocks of 256 threads per SM
 static int reduce_grid(const View& v) {
   const int ppb = 256 / (v.C / 8);
@@ -894,7 +1110,7 @@ static int reduce_grid(const View& v) {
 // scratch: partials, at least reduce_blocks()*2*C floats; c1c2: 2*C floats.
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                          float* partials, float* c1c2, cudaStream_t st) {
+                          float* partials, float* c1c2, const float* gscale, cudaStream_t st) {
   const int C = raw.C;
   if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
   const int grid = reduce_grid(raw);
@@ -902,11 +1118,11 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
   bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, partials);
   partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, count, dbeta, dgamma, accumulate, c1c2,
-                                                                c1c2 + C);
+                                                                c1c2 + C, gscale);
   bn_bwd_apply_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C,
-                                                                  draw, partials);
+                                                                  gscale, draw, partials);
   partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, dbias, nullptr, accumulate, nullptr,
-                                                                nullptr);
+                                                                nullptr, nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
@@ -916,7 +1132,7 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
   const int ppb = 256 / (C / 8);
   view_colsum_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(v, partials);
   partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, out, nullptr, accumulate, nullptr,
-                                                                nullptr);
+                                                                nullptr, nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st) {
@@ -924,11 +1140,22 @@ cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cud
   pool_bwd_add_kernel<<<grid_for(items, 256), 256, 0, st>>>(act, dpool, dskip, dact);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_conv3x3(const float* w, int Cout, int Cin, bf16* fwd, bf16* bwd, cudaStream_t st) {
-  pack_conv3x3_kernel<<<grid_for(static_cast<long>(Cout) * Cin * 9, 256), 256, 0, st>>>(w, Cout, Cin, fwd, bwd);
+cudaError_t launch_pack_conv3x3_all(PackTable& t, cudaStream_t st) {
+  int items = 0;
+  for (int i = 0; i < t.n; ++i) {
+    t.e[i].item0 = items;
+    items += t.e[i].cout * ((t.e[i].cin + 255) / 256);
+  }
+  if (items > 0) pack_conv3x3_all_kernel<<<items, 256, 0, st>>>(t);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_convt(const float* w, int Cin, int Cout, bf16* fwd, bf16* bwd, cudaStream_t st) {
-  pack_convt_kernel<<<grid_for(static_cast<long>(Cin) * Cout * 4, 256), 256, 0, st>>>(w, Cin, Cout, fwd, bwd);
+cudaError_t launch_pack_convt_all(PackTable& t, cudaStream_t st) {
+  int items = 0;
+  for (int i = 0; i < t.n; ++i) {
+    if (t.e[i].cin % 32 != 0 || t.e[i].cout % 8 != 0) return cudaErrorInvalidValue;
+    t.e[i].item0 = items;
+    items += (t.e[i].cin / 32) * (t.e[i].cout / 8);
+  }
+  if (items > 0) pack_convt_all_kernel<<<items, 256, 0, st>>>(t);
   return cudaGetLastError();
 }

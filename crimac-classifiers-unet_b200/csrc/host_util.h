@@ -36,6 +36,19 @@ cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t st
 cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream);
 cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,
                                 cudaStream_t stream);
+// every layer's scratch -> PyTorch-layout gradient in one launch; the scratch is zeroed behind the read
+struct UnpackEntry {
+  float* scratch;  // [taps][mn]
+  float* dw;       // [mn][taps]
+  long mn;
+  int taps;
+  int item0;
+};
+struct UnpackTable {
+  int n;
+  UnpackEntry e[24];
+};
+cudaError_t launch_wgrad_unpack_all(UnpackTable& t, cudaStream_t stream);
 
 int device_num_sms();
 
@@ -69,11 +82,27 @@ cudaError_t launch_ce(const float* logits, const long long* labels, const float*
 int head_bwd_blocks();
 cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act, const float* hw, int ncls, View dact,
                             float* partials, float* dw, float* db, int accumulate, cudaStream_t st);
+// fused train step: 1x1 head + weighted CE + head backward in one pass; dact/dw/db relative to the UNNORMALISED loss
+// gradient, out3 = {loss, 1/sum_w, sum_w}; loss_partials: head_bwd_blocks()*2 doubles
+cudaError_t launch_head_ce_fused(View act, const float* hw, const float* hb, int ncls, const long long* labels,
+                                 const float* cw, long long ignore_index, View dact, float* partials,
+                                 double* loss_partials, float* dw, float* db, float* out3, cudaStream_t st);
 int reduce_blocks();
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                          float* partials, float* c1c2, cudaStream_t st);
+                          float* partials, float* c1c2, const float* gscale, cudaStream_t st);
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st);
 cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st);
-cudaError_t launch_pack_conv3x3(const float* w, int Cout, int Cin, bf16* fwd, bf16* bwd, cudaStream_t st);
-cudaError_t launch_pack_convt(const float* w, int Cin, int Cout, bf16* fwd, bf16* bwd, cudaStream_t st);
+// fp32 parameters -> bf16 GEMM operands for every layer of one kind in ONE launch (item0 is filled by the launcher)
+struct PackEntry {
+  const float* w;
+  bf16* out;
+  int cout, cin;
+  int item0;
+};
+struct PackTable {
+  int n;
+  PackEntry e[24];
+};
+cudaError_t launch_pack_conv3x3_all(PackTable& t, cudaStream_t st);  // (Cout,Cin,3,3) -> [Cout][tap][Cin]
+cudaError_t launch_pack_convt_all(PackTable& t, cudaStream_t st);    // (Cin,Cout,2,2) -> [(kk*Cout+co)][Cin]

@@ -39,22 +39,24 @@ struct Conv3 {
   int s_w = 0, s_b = 0, s_g = 0, s_beta = 0, s_rm = 0, s_rv = 0, s_nbt = 0;
   int g_w = 0, g_b = 0, g_g = 0, g_beta = 0;
   View in{}, raw{}, act{}, pool{}, gin{};
-  bf16 *w_fwd = nullptr, *w_bwd = nullptr;
+  bf16* w_fwd = nullptr;  // backward-data reads the same matrix as an MN-major operand
   float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
   int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
   ConvParams fwd{}, dgrad{};
   WgradHaloParams wg{};   // all-taps halo kernel (wide, shallow layers)
   WgradParams wg_tap{};   // one-tap-per-CTA kernel (deep layers: few pixels, many channels)
   bool wg_use_halo = true;
+  float* wg_scratch = nullptr;  // [9][cout][cin] fp32, zero between steps
 };
 struct ConvT {
   int cin = 0, cout = 0, level_in = 0;
   int s_w = 0, s_b = 0, g_w = 0, g_b = 0;
   View in{}, out{}, gout{}, gin{};
-  bf16 *w_fwd = nullptr, *w_bwd = nullptr;
+  bf16* w_fwd = nullptr;  // backward-data reads the same matrix as an MN-major operand
   int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
   ConvParams fwd{}, dgrad{};
   WgradParams wg{};
+  float* wg_scratch = nullptr;  // [4][cin][cout] fp32, zero between steps
 };
 
 int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
@@ -75,7 +77,9 @@ struct crimac_ctx {
   float* stats = nullptr;
   float* red_partials = nullptr;
   float* c1c2 = nullptr;
-  float* wg_scratch = nullptr;
+  float* wg_arena = nullptr;   // all layers' weight-gradient scratch, contiguous
+  size_t wg_arena_bytes = 0;
+  bool wg_dirty = true;        // scratch may hold partial sums (first use, or a failed backward)
   float* head_partials = nullptr;
   float* fc_partials = nullptr;
   double* ce_partials = nullptr;
@@ -240,7 +244,6 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   for (Conv3& L : c->conv) {
     if (!L.first) {
       L.w_fwd = bump.arr<bf16>(static_cast<size_t>(L.cout) * 9 * L.cin);
-      if (train) L.w_bwd = bump.arr<bf16>(static_cast<size_t>(L.cout) * 9 * L.cin);
     }
     L.scale = bump.arr<float>(L.cout);
     L.shift = bump.arr<float>(L.cout);
@@ -255,7 +258,6 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   }
   for (ConvT& U : c->up) {
     U.w_fwd = bump.arr<bf16>(static_cast<size_t>(U.cin) * U.cout * 4);
-    if (train) U.w_bwd = bump.arr<bf16>(static_cast<size_t>(U.cin) * U.cout * 4);
     U.bn_fwd = pick_bn(4 * U.cout);
     U.bn_bwd = pick_bn(U.cin);
     U.bn_wg = pick_bn(U.cout);
@@ -275,7 +277,25 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     c->stats = bump.arr<float>(max_stats);
     c->red_partials = bump.arr<float>(static_cast<size_t>(reduce_blocks()) * 2 * cmax);
     c->c1c2 = bump.arr<float>(2 * cmax);
-    c->wg_scratch = bump.arr<float>(static_cast<size_t>(9) * cmax * cmax);
+    {
+      // one contiguous arena, one region per layer: the unpack kernel re-zeroes behind itself, so no per-layer memset
+      size_t total = 0;
+      for (Conv3& L : c->conv)
+        if (!L.first) total += static_cast<size_t>(9) * L.cout * L.cin;
+      for (ConvT& U : c->up) total += static_cast<size_t>(4) * U.cin * U.cout;
+      c->wg_arena = bump.arr<float>(total);
+      c->wg_arena_bytes = total * sizeof(float);
+      float* q = c->wg_arena;
+      for (Conv3& L : c->conv)
+        if (!L.first) {
+          L.wg_scratch = q;
+          if (q) q += static_cast<size_t>(9) * L.cout * L.cin;
+        }
+      for (ConvT& U : c->up) {
+        U.wg_scratch = q;
+        if (q) q += static_cast<size_t>(4) * U.cin * U.cout;
+      }
+    }
     c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 4 * (cfg.n_classes * 64 + cfg.n_classes));
     c->fc_partials = bump.arr<float>(static_cast<size_t>(first_conv_wgrad_blocks()) * 4 * 64 * cfg.in_channels * 9);
     c->ce_partials = bump.arr<double>(static_cast<size_t>(ce_blocks()) * 2);
@@ -330,7 +350,6 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     p.tiles_y = (H + 3) / 4;
     p.m_tiles = (m_total + 127) / 128;
     p.n_tiles = n_total / bn;
-    p.dw = c->wg_scratch;
   };
   int rc;
   for (Conv3& L : c->conv) {
@@ -353,7 +372,9 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         p.cin = L.cout;
         geom(p, H, W, L.cin, L.bn_bwd);
         if ((rc = conv_map(p, gr))) return rc;
-        if ((rc = make_weight_map(&p.b_map, L.w_bwd, L.cin, 9 * L.cout, L.bn_bwd))) return rc;
+        p.b_mn = 1;
+        p.b_tap_cols = L.cin;
+        if ((rc = make_weight_map(&p.b_map, L.w_fwd, L.cout, 9 * L.cin, 64))) return rc;
         p.out = L.gin.ptr;
         p.out_pitch = L.gin.pitch;
         WgradHaloParams& w = L.wg;
@@ -365,7 +386,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         w.tiles_y = (H + 3) / 4;
         w.s_tiles = L.cout / 64;
         w.f_tiles = L.cin / 64;
-        w.dw = c->wg_scratch;
+        w.dw = L.wg_scratch;
         if ((rc = make_act_map(&w.s_map, gr, 6, 0, 0, 0, 18))) return rc;
         if ((rc = make_act_map(&w.f_map, L.in, 4))) return rc;
         // measured on B200 (profiles/): the 64x64-channel halo tiles win up to Cout*Cin = 256*128, beyond that the
@@ -373,6 +394,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         L.wg_use_halo = static_cast<long>(L.cout) * L.cin <= 256L * 128L;
         WgradParams& wt = L.wg_tap;
         wgeom(wt, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
+        wt.dw = L.wg_scratch;
         if ((rc = make_act_map(&wt.a_map, gr, 4))) return rc;
         if ((rc = make_act_map(&wt.b_map[0], L.in, 4))) return rc;
       }
@@ -399,11 +421,13 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       geom(d, H, W, U.cin, U.bn_bwd);
       for (int kk = 0; kk < 4; ++kk)
         if ((rc = make_act_map(&d.a_map[kk], U.gout, TILE_H, 1, kk >> 1, kk & 1))) return rc;
-      if ((rc = make_weight_map(&d.b_map, U.w_bwd, U.cin, 4 * U.cout, U.bn_bwd))) return rc;
+      d.b_mn = 1;
+      if ((rc = make_weight_map(&d.b_map, U.w_fwd, 4 * U.cout, U.cin, 64))) return rc;
       d.out = U.gin.ptr;
       d.out_pitch = U.gin.pitch;
       WgradParams& w = U.wg;
       wgeom(w, H, W, U.cin, U.cout, U.bn_wg, 4, 1);
+      w.dw = U.wg_scratch;
       if ((rc = make_act_map(&w.a_map, U.in, 4))) return rc;
       for (int kk = 0; kk < 4; ++kk)
         if ((rc = make_act_map(&w.b_map[kk], U.gout, 4, 1, kk >> 1, kk & 1))) return rc;
@@ -461,39 +485,19 @@ double igemm_flops_n(const ConvParams& p, int n_total) {
   return 2.0 * p.NB * static_cast<double>(p.H) * p.W * n_total * p.taps * p.cin;
 }
 
-int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, float* dw, cudaStream_t st) {
+// The weight-gradient GEMMs accumulate (red.add) into their layer's zeroed scratch; crimac_backward turns all of them
+// into PyTorch-layout gradients with ONE unpack launch at its end.
+int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, cudaStream_t st) {
   set_batch(w, nb);
-  const double wbytes = sizeof(float) * w.taps * static_cast<double>(w.M_total) * w.N_total;
-  if (w.splits > 1) {
-    ProfScope ps("wgrad_zero", 0, wbytes, st);
-    CRIMAC_CHECK_CUDA(cudaMemsetAsync(w.dw, 0, static_cast<size_t>(wbytes), st));
-  }
-  {
-    ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.M_total * w.N_total * w.taps, 0, st);
-    CRIMAC_CHECK_CUDA(launch_wgrad_gemm(w, bn, st));
-  }
-  {
-    ProfScope ps("wgrad_unpack", 0, 2 * wbytes, st);
-    CRIMAC_CHECK_CUDA(launch_wgrad_unpack(w.dw, dw, w.M_total, w.N_total, w.taps, 0, st));
-  }
+  ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.M_total * w.N_total * w.taps, 0, st);
+  CRIMAC_CHECK_CUDA(launch_wgrad_gemm(w, bn, st));
   return 0;
 }
 
-int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, float* dw, cudaStream_t st) {
+int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, cudaStream_t st) {
   set_batch(w, nb);
-  const double wbytes = sizeof(float) * 9.0 * w.Cs * w.Cf;
-  if (w.splits > 1) {
-    ProfScope ps("wgrad_zero", 0, wbytes, st);
-    CRIMAC_CHECK_CUDA(cudaMemsetAsync(w.dw, 0, static_cast<size_t>(wbytes), st));
-  }
-  {
-    ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * 9, 0, st);
-    CRIMAC_CHECK_CUDA(launch_wgrad_halo(w, st));
-  }
-  {
-    ProfScope ps("wgrad_unpack", 0, 2 * wbytes, st);
-    CRIMAC_CHECK_CUDA(launch_wgrad_unpack(w.dw, dw, w.Cs, w.Cf, 9, 0, st));
-  }
+  ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * 9, 0, st);
+  CRIMAC_CHECK_CUDA(launch_wgrad_halo(w, st));
   return 0;
 }
 
@@ -562,23 +566,26 @@ extern "C" int crimac_prepare(crimac_ctx* c, const void* const* state, int train
   if (rc) return rc;
   CRIMAC_REQUIRE(!train || c->cfg.train, "context was created without train=1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ProfScope ps("pack_weights", 0, 0, st, static_cast<int>(c->conv.size() + c->up.size()));
-  for (Conv3& L : c->conv) {
-    if (!L.first)
-      CRIMAC_CHECK_CUDA(launch_pack_conv3x3(S<float>(state, L.s_w), L.cout, L.cin, L.w_fwd, train ? L.w_bwd : nullptr, st));
-    if (!train)
+  {
+    ProfScope ps("pack_weights", 0, 0, st, 2);
+    PackTable t3{}, tt{};
+    for (Conv3& L : c->conv)
+      if (!L.first) t3.e[t3.n++] = PackEntry{S<float>(state, L.s_w), L.w_fwd, L.cout, L.cin, 0};
+    for (ConvT& U : c->up) tt.e[tt.n++] = PackEntry{S<float>(state, U.s_w), U.w_fwd, U.cout, U.cin, 0};
+    CRIMAC_CHECK_CUDA(launch_pack_conv3x3_all(t3, st));
+    CRIMAC_CHECK_CUDA(launch_pack_convt_all(tt, st));
+  }
+  if (!train)
+    for (Conv3& L : c->conv)
       CRIMAC_CHECK_CUDA(launch_bn_fold_eval(S<float>(state, L.s_g), S<float>(state, L.s_beta), S<float>(state, L.s_rm),
                                             S<float>(state, L.s_rv), S<float>(state, L.s_b), 1e-5f, L.cout, L.scale,
                                             L.shift, st));
-  }
-  for (ConvT& U : c->up)
-    CRIMAC_CHECK_CUDA(launch_pack_convt(S<float>(state, U.s_w), U.cin, U.cout, U.w_fwd, train ? U.w_bwd : nullptr, st));
   c->prepared_mode = train ? 1 : 0;
   return 0;
 }
 
 static int forward_impl(crimac_ctx* c, const void* const* state, const float* x, int nb, float* out, int softmax,
-                        bool train, cudaStream_t st) {
+                        bool train, cudaStream_t st, bool skip_head = false) {
   const int sms = device_num_sms();
   const int D = c->D;
   const int last = c->dec2[D - 2];
@@ -672,7 +679,7 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
     if ((rc = run_conv(c->dec1[j]))) return rc;
     if ((rc = run_conv(c->dec2[j]))) return rc;
   }
-  if (train) {
+  if (train && !skip_head) {
     ProfScope ps("head_fwd", 0, static_cast<double>(nb) * c->cfg.height * c->cfg.width * (128.0 + 4.0 * c->cfg.n_classes), st);
     CRIMAC_CHECK_CUDA(launch_head_fwd(with_batch(c->conv[last].act, nb), S<float>(state, c->s_head_w),
                                       S<float>(state, c->s_head_b), c->cfg.n_classes, out, st));
@@ -713,15 +720,18 @@ extern "C" int crimac_loss(crimac_ctx* c, const float* logits, const int64_t* la
   return 0;
 }
 
-extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const float* x, const float* dlogits,
-                               const float* gscale, int nb, float* const* grads, void* stream) {
-  int rc = check_call(c, state, nb);
-  if (rc) return rc;
-  CRIMAC_REQUIRE(c->cfg.train && c->prepared_mode == 1, "backward needs a train context after forward_train");
-  CRIMAC_REQUIRE(x && dlogits && grads, "NULL tensor");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// head_done: the fused head/CE kernel has already written the UNNORMALISED gradient of the last activation into GA and
+// the head's own gradients; gscale (1/sum_w) is then folded into the last layer's BatchNorm backward.
+static int backward_impl(crimac_ctx* c, const void* const* state, const float* x, const float* dlogits,
+                         const float* gscale, int nb, float* const* grads, cudaStream_t st, bool head_done) {
+  int rc;
   const int sms = device_num_sms();
   const int D = c->D;
+  if (c->wg_dirty) {
+    ProfScope ps("wgrad_zero", 0, static_cast<double>(c->wg_arena_bytes), st);
+    CRIMAC_CHECK_CUDA(cudaMemsetAsync(c->wg_arena, 0, c->wg_arena_bytes, st));
+  }
+  c->wg_dirty = true;  // cleared by the unpack launch at the end
 
   // BN/ReLU backward of layer idx (dA in GA) -> dRaw in GR; then wgrad (+ dgrad into L.gin)
   auto conv_bwd = [&](int idx) -> int {
@@ -733,15 +743,15 @@ extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const fl
     {
       ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 4);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
-                                      grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2, st));
+                                      grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2,
+                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, st));
     }
     if (L.first) {
       ProfScope ps("first_conv_wgrad", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st, 2);
       CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, dr, L.cin, c->fc_partials, grads[L.g_w], 0, st));
       return 0;
     }
-    int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, grads[L.g_w], st)
-                          : wgrad_run(c, L.wg_tap, L.bn_wg, nb, grads[L.g_w], st);
+    int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, st) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, st);
     if (r) return r;
     if (L.gin.ptr != nullptr) {
       ConvParams p = L.dgrad;
@@ -754,7 +764,7 @@ extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const fl
 
   // head
   const int last = c->dec2[D - 2];
-  {
+  if (!head_done) {
     Conv3& L = c->conv[last];
     View dact{c->GA, nb, c->cfg.height, c->cfg.width, 64, 64};
     ProfScope ps("head_bwd", 0, static_cast<double>(nb) * c->cfg.height * c->cfg.width * (256.0 + 4.0 * c->cfg.n_classes), st, 2);
@@ -771,7 +781,7 @@ extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const fl
       ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, st, 2);
       CRIMAC_CHECK_CUDA(launch_view_colsum(with_batch(U.gout, nb), c->red_partials, grads[U.g_b], 0, st));
     }
-    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, grads[U.g_w], st))) return rc;
+    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, st))) return rc;
     ConvParams p = U.dgrad;
     set_batch(p, nb);
     ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
@@ -791,7 +801,25 @@ extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const fl
     if ((rc = conv_bwd(c->enc2[l]))) return rc;
     if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
   }
+  {
+    UnpackTable t{};
+    for (Conv3& L : c->conv)
+      if (!L.first) t.e[t.n++] = UnpackEntry{L.wg_scratch, grads[L.g_w], static_cast<long>(L.cout) * L.cin, 9, 0};
+    for (ConvT& U : c->up) t.e[t.n++] = UnpackEntry{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, 4, 0};
+    ProfScope ps("wgrad_unpack", 0, 3.0 * static_cast<double>(c->wg_arena_bytes), st);
+    CRIMAC_CHECK_CUDA(launch_wgrad_unpack_all(t, st));
+    c->wg_dirty = false;
+  }
   return 0;
+}
+
+extern "C" int crimac_backward(crimac_ctx* c, const void* const* state, const float* x, const float* dlogits,
+                               const float* gscale, int nb, float* const* grads, void* stream) {
+  int rc = check_call(c, state, nb);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(c->cfg.train && c->prepared_mode == 1, "backward needs a train context after forward_train");
+  CRIMAC_REQUIRE(x && dlogits && grads, "NULL tensor");
+  return backward_impl(c, state, x, dlogits, gscale, nb, grads, static_cast<cudaStream_t>(stream), false);
 }
 
 extern "C" int crimac_train_step(crimac_ctx* c, const void* const* state, const float* x, const int64_t* labels,
@@ -799,8 +827,22 @@ extern "C" int crimac_train_step(crimac_ctx* c, const void* const* state, const 
                                  void* stream) {
   int rc = crimac_prepare(c, state, 1, stream);
   if (rc) return rc;
-  if ((rc = crimac_forward_train(c, state, x, nb, c->logits, stream))) return rc;
+  CRIMAC_REQUIRE(x && labels && class_w && grads, "NULL tensor");
+  CRIMAC_REQUIRE(nb >= 1 && nb <= c->cfg.max_batch, "nb must be in 1..max_batch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // forward without the head: logits are never materialised on the fused path
+  if ((rc = forward_impl(c, state, x, nb, nullptr, 0, true, st, /*skip_head=*/true))) return rc;
   float* l3 = loss3 ? loss3 : c->loss3;
-  if ((rc = crimac_loss(c, c->logits, labels, class_w, ignore_index, nb, l3, c->dlogits, stream))) return rc;
-  return crimac_backward(c, state, x, c->dlogits, l3 + 1, nb, grads, stream);
+  {
+    const int last = c->dec2[c->D - 2];
+    const double px = static_cast<double>(nb) * c->cfg.height * c->cfg.width;
+    View dact{c->GA, nb, c->cfg.height, c->cfg.width, 64, 64};
+    ProfScope ps("head_ce_fused", 0, px * (256.0 + 8.0), st, 2);
+    CRIMAC_CHECK_CUDA(launch_head_ce_fused(with_batch(c->conv[last].act, nb), S<float>(state, c->s_head_w),
+                                           S<float>(state, c->s_head_b), c->cfg.n_classes,
+                                           reinterpret_cast<const long long*>(labels), class_w, ignore_index, dact,
+                                           c->head_partials, c->ce_partials, grads[c->g_head_w], grads[c->g_head_b], l3,
+                                           st));
+  }
+  return backward_impl(c, state, x, nullptr, l3 + 1, nb, grads, st, /*head_done=*/true);
 }

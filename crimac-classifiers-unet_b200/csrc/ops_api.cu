@@ -21,7 +21,12 @@ extern "C" int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, in
                                int out_pitch, int convt_cout, void* pool_out, int pool_pitch, float* stats,
                                const float* head_w, const float* head_b, float* head_out, int n_classes,
                                int head_softmax, int block_n, void* stream) {
-  CRIMAC_REQUIRE(mode >= 0 && mode <= 3, "mode");
+  CRIMAC_REQUIRE(mode >= 0 && mode <= 5, "mode");
+  // modes 4 / 5: backward-data of a 3x3 conv / ConvTranspose reading the FORWARD-packed weights as an MN-major operand
+  // (w = [Cout][9*Cin] resp. [(kk,co)][Cin] of the forward layer; n_total = the forward layer's Cin)
+  const bool b_mn = (mode == 4 || mode == 5);
+  if (mode == 4) mode = 0;
+  if (mode == 5) mode = 2;
   const bool halo = (mode == 0);  // mode 3 = 3x3 conv through the plain 9-box main loop (kept for A/B measurements)
   if (mode == 3) mode = 0;
   CRIMAC_REQUIRE(cin % 64 == 0, "cin must be a multiple of 64");
@@ -50,7 +55,16 @@ extern "C" int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, in
     int rc = halo ? make_act_map(&p.a_map[0], v, 18, 0, 0, 0, 10) : make_act_map(&p.a_map[0], v, TILE_H);
     if (rc) return rc;
   }
-  int rc = make_weight_map(&p.b_map, static_cast<const bf16*>(w), n_total, p.taps * cin, bn);
+  int rc;
+  if (b_mn) {
+    CRIMAC_REQUIRE(stats == nullptr && head_w == nullptr, "backward-data has the plain store epilogue");
+    p.b_mn = 1;
+    p.b_tap_cols = n_total;
+    rc = (mode == 0) ? make_weight_map(&p.b_map, static_cast<const bf16*>(w), cin, 9 * n_total, 64)
+                     : make_weight_map(&p.b_map, static_cast<const bf16*>(w), 4 * cin, n_total, 64);
+  } else {
+    rc = make_weight_map(&p.b_map, static_cast<const bf16*>(w), n_total, p.taps * cin, bn);
+  }
   if (rc) return rc;
   p.out = static_cast<bf16*>(out);
   p.out_pitch = out_pitch;

@@ -11,7 +11,7 @@
 // per 64-channel block, 64 k-rows of 128 bytes.  One CTA owns one (m-tile, n-tile, tap) output tile over one
 // split of the pixel range; partial tiles are accumulated with vectorised red.global.add.f32 into a
 // [tap][m][n] fp32 scratch which a small kernel then permutes into PyTorch's (m, n, kh, kw) layout.
-#include "common.cuh"
+#include "host_util.h"
 #include "ptx.cuh"
 
 namespace {
@@ -366,6 +366,35 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
   }
 }
 
+// All layers in one launch at the end of backward: scratch [taps][M*N] -> dw [M*N][taps], and the scratch is left
+// ZEROED for the next step's red.add accumulation (no memset launches).  Work item = 1024 (m,n) pairs of one layer.
+__global__ void __launch_bounds__(256) wgrad_unpack_all_kernel(const __grid_constant__ UnpackTable t) {
+  __shared__ float s[256 * 9];
+  int li = 0;
+  while (li + 1 < t.n && static_cast<int>(blockIdx.x) >= t.e[li + 1].item0) ++li;
+  const UnpackEntry& L = t.e[li];
+  const long base = static_cast<long>(blockIdx.x - L.item0) * 1024;
+  for (int u = 0; u < 4; ++u) {
+    const long i0 = base + u * 256;
+    if (i0 >= L.mn) break;
+    const int n = static_cast<int>(min(256L, L.mn - i0));
+    // coalesced read (and zero) of each tap plane, transposed through shared memory into contiguous [pair][tap] rows
+    if (static_cast<int>(threadIdx.x) < n) {
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp)
+        if (tp < L.taps) {
+          float* src = L.scratch + tp * L.mn + i0 + threadIdx.x;
+          s[threadIdx.x * L.taps + tp] = *src;
+          *src = 0.f;
+        }
+    }
+    __syncthreads();
+    float* dst = L.dw + i0 * L.taps;
+    for (int j = threadIdx.x; j < n * L.taps; j += 256) dst[j] = s[j];
+    __syncthreads();
+  }
+}
+
 template <int BLOCK_N>
 cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   using Cfg = WgCfg<BLOCK_N>;
@@ -408,5 +437,15 @@ cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, i
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_unpack_kernel<<<blocks, 256, 0, stream>>>(scratch, dw, M, N, taps, accumulate);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad_unpack_all(UnpackTable& t, cudaStream_t stream) {
+  int items = 0;
+  for (int i = 0; i < t.n; ++i) {
+    t.e[i].item0 = items;
+    items += static_cast<int>((t.e[i].mn + 1023) / 1024);
+  }
+  if (items > 0) wgrad_unpack_all_kernel<<<items, 256, 0, stream>>>(t);
   return cudaGetLastError();
 }

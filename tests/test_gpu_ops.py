@@ -109,12 +109,16 @@ def test_conv_transpose_forward_scatter_and_backward_data(env):
     xr = _nchw(x).clone().requires_grad_(True)
     F.conv_transpose2d(xr, w.float(), b, stride=2).backward(_nchw(dy))
     _close(_nchw(dx), xr.grad)
+    # the product path: backward-data straight from the FORWARD-packed weights (MN-major B operand), no second packing
+    dx2 = torch.zeros_like(dx)
+    _igemm(env, 5, dy, wp, Cin, None, None, 0, dx2, Cin, H=H, W=W)
+    _close(_nchw(dx2), xr.grad)
 
 
-def test_conv3x3_backward_data(env):
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 32, 32, 128, 64), (1, 16, 16, 256, 512), (2, 24, 40, 64, 128)])
+def test_conv3x3_backward_data(env, NB, H, W, Cin, Cout):
     dev = env[2]
     torch.manual_seed(3)
-    NB, H, W, Cin, Cout = 2, 32, 32, 128, 64
     w = (torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin ** 0.5)).bfloat16()
     dy = torch.randn(NB, H, W, Cout, device=dev).bfloat16()
     wd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, 9 * Cout).contiguous()
@@ -123,6 +127,11 @@ def test_conv3x3_backward_data(env):
     xr = torch.randn(NB, Cin, H, W, device=dev, requires_grad=True)
     F.conv2d(xr, w.float(), padding=1).backward(_nchw(dy))
     _close(_nchw(dx), xr.grad)
+    # the product path: the FORWARD-packed weights [Cout][tap][Cin] read as an MN-major operand, taps rotated in-kernel
+    wf = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    dx2 = torch.zeros_like(dx)
+    _igemm(env, 4, dy, wf, Cin, None, None, 0, dx2, Cin)
+    _close(_nchw(dx2), xr.grad)
 
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,splits", [(2, 32, 32, 64, 64, 1), (2, 32, 32, 128, 128, 4),
