@@ -31,11 +31,45 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "survey"],
+                    help="train = BASELINE configs[1]/[2] (headline); infer = forward+softmax; survey = configs[3] sliding window")
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--in-ch", type=int, default=4, help="frequencies (configs[4] stress: 6)")
+    ap.add_argument("--size", type=int, default=256, help="patch height = width (configs[4] stress: 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event breakdown of one step here")
     return ap.parse_args()
+
+
+def unet_gflop(in_ch, size, train):
+    """Algorithmic GFLOP per patch (2*MACs of convs, convT, head) - SURVEY.md App. A generalised to (in_ch, size)."""
+    px = size * size
+    fwd, first = 0.0, 2.0 * px * 64 * 9 * in_ch
+    fwd += first
+    ch = [64, 128, 256, 512, 1024]
+    for l in range(5):
+        p = px / 4 ** l
+        if l > 0:
+            fwd += 2.0 * p * ch[l] * 9 * ch[l - 1]
+        fwd += 2.0 * p * ch[l] * 9 * ch[l]
+    for l in range(3, -1, -1):
+        p = px / 4 ** l
+        fwd += 2.0 * (p / 4) * (4 * ch[l]) * ch[l + 1]      # ConvTranspose2d
+        fwd += 2.0 * p * ch[l] * 9 * (2 * ch[l])            # conv1 on the concat
+        fwd += 2.0 * p * ch[l] * 9 * ch[l]
+    fwd += 2.0 * px * 3 * 64
+    return (3 * fwd - first) / 1e9 if train else fwd / 1e9
+
+
+def committed_traffic(mode):
+    """DRAM bytes of the dominant kernel family for one step, from the committed ncu --set full capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "conv_igemm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(mode)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -151,10 +185,14 @@ def run_b200(args):
     from crimac_unet_b200.trainer import Trainer
 
     B = args.batch
+    C, S = args.in_ch, args.size
     torch.manual_seed(0)
-    model = M.UNet_Baseline(3, 4).to(dev)
-    x = O.synthetic_echogram(B, 4, 256, 256, seed=100 + rank, device=dev)
-    y = O.synthetic_labels(B, 256, 256, seed=200 + rank, device=dev)
+    model = M.UNet_Baseline(3, C).to(dev)
+    if args.mode == "survey":
+        return run_survey(args, model, dev, rank, world, E)
+    x = O.synthetic_echogram(B, C, S, S, seed=100 + rank, device=dev)
+    y = O.synthetic_labels(B, S, S, seed=200 + rank, device=dev)
+    standard = (C == 4 and S == 256)
 
     def sync_all():
         if world > 1:
@@ -166,11 +204,11 @@ def run_b200(args):
         trainer = Trainer(model, lr=0.005, momentum=0.95)
         trainer.broadcast_parameters(0)
         step = lambda xx, yy: trainer.step(xx, yy)
-        gflop = GFLOP_TRAIN
+        gflop = GFLOP_TRAIN if standard else unet_gflop(C, S, True)
     else:
         model.eval()
         step = lambda xx, yy: model.predict_proba(xx)
-        gflop = GFLOP_INFER
+        gflop = GFLOP_INFER if standard else unet_gflop(C, S, False)
 
     def timed(fn, k):
         sync_all()
@@ -215,7 +253,7 @@ def run_b200(args):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps) / args.steps
         h2d = xh.numel() * 4 + (yh.numel() * 8 if args.mode == "train" else 0)
-        d2h = 4 if args.mode == "train" else B * 2 * 256 * 256 * 2
+        d2h = 4 if args.mode == "train" else B * 2 * S * S * 2
         e2e_value = world * B / (ms_e2e * 1e-3)
 
         # ---- per-kernel breakdown of one more step (CUDA events around every launch, on the launching stream)
@@ -238,7 +276,9 @@ def run_b200(args):
     dom_name, dom = max(((k, a) for k, a in fam.items() if a[1] > 0), key=lambda kv: kv[1][0])
     achieved = dom[1] / (dom[0] * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                "traffic": committed_traffic(args.mode) if (standard and B == 32) else None,
+                "traffic_note": "DRAM bytes read+written by this kernel family in ONE step (sum over its launches), ncu --set full capture summarised in profiles/conv_igemm_traffic.json",
                 "peak_source": peaks["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "launches_per_step": dom[3], "ms_per_step_in_kernel": dom[0], "share_of_step": dom[0] / step_kernel_ms,
                 "whole_step_tflops": value / world * gflop / 1e3, "whole_step_frac_of_burst_peak": value / world * gflop / 1e3 / peaks["tflops_burst"]}
@@ -253,7 +293,7 @@ def run_b200(args):
                 f.write(f"{name},{ms:.4f},{fl / 1e9:.3f},{fl / max(ms, 1e-9) / 1e9:.1f},{by / max(ms, 1e-9) / 1e6:.1f}\n")
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and standard:
         pps, cores, dt = cpu_train_patches_per_s(4, reps=2, warm=1)
         cpu_baseline = {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port",
                         "sample": f"oracle port of the reference train step, fp32 torch CPU, batch 4 (of 32), 1 warm-up + 2 timed steps, {dt:.2f} s/step"}
@@ -264,7 +304,7 @@ def run_b200(args):
             "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (fp32 accumulate; first conv, BN statistics, head, loss in fp32)", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.mode == "train" else "UNet inference, batch %d of 4x256x256" % B,
+            "config": {"workload": (WORKLOAD if standard and B == 32 else "UNet training fwd+bwd, batch %d of %dx%dx%d per GPU" % (B, C, S, S)) if args.mode == "train" else "UNet inference, batch %d of %dx%dx%d" % (B, C, S, S),
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single GPU",
                        "step": "weight re-pack + forward + weighted CE + backward" + (" + NCCL all-reduce of the 124 MB gradient arena" if world > 1 else "") + " + fused SGD-momentum update" if args.mode == "train" else "forward + softmax",
                        "l2": "per-step working set (activations + gradients) is ~6 GB >> 126 MB L2; no explicit flush"},
@@ -276,6 +316,93 @@ def run_b200(args):
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_survey(args, model, dev, rank, world, E):
+    """BASELINE configs[3]: sliding-window whole-echogram inference (save_predict.py:137-220) on a synthetic 4-frequency
+    survey, preload_n_pings = 20000, 256 range bins, sharded by ping range.  A step = one preload chunk (186 patches):
+    patch gather + dB transform, U-Net forward + softmax, overlap-stitch into (2, range, pings) fp16 - all on device."""
+    import math
+    import torch
+    import torch.distributed as dist
+    from crimac_unet_b200.predict import SurveyPredictor
+    R, NP = 256, 20000
+    n_chunks = max(args.steps, 1)
+    P = NP * n_chunks                      # this rank's ping range (weak scaling: every rank owns n_chunks chunks)
+    model.eval()
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    sv = torch.pow(10.0, torch.rand((args.in_ch, R, P), device=dev, generator=g) * 7.0 - 9.0)
+    sv[torch.rand((args.in_ch, R, P), device=dev, generator=g) < 1e-3] = float("nan")
+    pings = torch.arange(P, device=dev)
+    seabed = (200 + 20 * torch.sin(2 * math.pi * pings / 5000)).to(torch.int32)
+    sp = SurveyPredictor(model, patch_hw=(256, 256), overlap=20, preload_n_pings=NP, batch_size=args.batch)
+    def chunk(i, sv_dev, ping0):
+        s, e = i * NP, (i + 1) * NP
+        grid, _ = sp.chunk_geometry(s, e, R, P, seabed_max=220)
+        o = sp.predict_chunk(sv_dev, ping0, grid, s, e, seabed=seabed[s:e].contiguous())   # fresh zeroed (2,R,NP) fp16
+        return grid.shape[0], o
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        npatch, last = chunk(0, sv, 0)
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_chunks):
+        chunk(i, sv, 0)
+    e1.record()
+    sync_all()
+    launches = E.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * n_chunks * npatch / (ms * 1e-3)
+    # end to end: the chunk's pings come from pinned host memory, the stitched fp16 chunk goes back to the host
+    svh = sv[:, :, :NP + 512].cpu().pin_memory()
+    outh = torch.empty((2, R, NP), dtype=torch.float16).pin_memory()
+    svd = torch.empty_like(sv[:, :, :NP + 512])
+    sync_all()
+    e0.record()
+    for i in range(n_chunks):
+        svd.copy_(svh, non_blocking=True)
+        _, o = chunk(0, svd, 0)
+        outh.copy_(o, non_blocking=True)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * n_chunks * npatch / (t.item() * 1e-3)
+    written = float((last != 0).float().mean().item())
+    if rank == 0:
+        peaks = measured_peaks()
+        print(json.dumps({
+            "metric": "U-Net 256x256 patches/s, sliding-window survey inference (preprocess + forward + stitch)",
+            "value": value, "unit": "patches/s", "n_gpus": world, "steps": n_chunks, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / n_chunks, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (fp32 accumulate; first conv, head, softmax in fp32; fp16 output)", "data": "synthetic",
+            "config": {"workload": "configs[3]: sliding-window inference, %d-ping chunks x 256 range bins, %d patches per chunk, batch %d, sharded by ping range (%d chunks per GPU)" % (NP, npatch, args.batch, n_chunks),
+                       "pings_per_s": value / npatch * NP, "fraction_of_output_pixels_written": written,
+                       "l2": "each chunk reads 82 MB of sv and ~1.5 GB of activations >> 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": svh.numel() * 4, "d2h_bytes_per_step": outh.numel() * 2,
+                    "api": "SurveyPredictor.predict_chunk; pinned host sv chunk -> device, stitched fp16 chunk -> host"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": value / world * GFLOP_INFER / 1e3,
+                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": value / world * GFLOP_INFER / 1e3 / peaks["tflops_sustained"],
+                         "traffic": None, "note": "whole-chunk figure (all kernels incl. preprocess and stitch) against the sustained bf16 peak"},
+            "cpu_baseline": None}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -472,30 +472,32 @@ __global__ void __launch_bounds__(256) head_ce_fused_kernel(View act, const floa
   }
   double la = 0.0, lb = 0.0;
   const long stride = static_cast<long>(gridDim.x) * 32;
-  for (long p0 = static_cast<long>(blockIdx.x) * 32 + pl; p0 < total; p0 += 2 * stride) {
-    float a[2][8];
-    long long y[2];
-    bool ok[2];
+  constexpr int U = 4;  // pixels per thread in flight (the kernel is bound by load latency, not by bandwidth or math)
+  for (long p0 = static_cast<long>(blockIdx.x) * 32 + pl; p0 < total; p0 += U * stride) {
+    uint4 av[U];
+    long long y[U];
+    bool ok[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       ok[u] = p < total;  // uniform over the 8 threads of a pixel
       y[u] = ok[u] ? labels[p] : ignore_index;
-      if (ok[u]) {
-        load8(act.ptr + p * act.pitch + g * 8, a[u]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[u][j] = 0.f;
-      }
+      av[u] = ok[u] ? *reinterpret_cast<const uint4*>(act.ptr + p * act.pitch + g * 8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
+      float a[8];
+      {
+        const float2 a0 = unpack_bf16x2(av[u].x), a1 = unpack_bf16x2(av[u].y), a2 = unpack_bf16x2(av[u].z),
+                     a3 = unpack_bf16x2(av[u].w);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+      }
       float z[NCLS];
 #pragma unroll
       for (int k = 0; k < NCLS; ++k) {
         float t = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t = fmaf(a[u][j], w[k][j], t);
+        for (int j = 0; j < 8; ++j) t = fmaf(a[j], w[k][j], t);
         t += __shfl_xor_sync(0xffffffffu, t, 1);
         t += __shfl_xor_sync(0xffffffffu, t, 2);
         t += __shfl_xor_sync(0xffffffffu, t, 4);
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(256) head_ce_fused_kernel(View act, const floa
 #pragma unroll
         for (int k = 0; k < NCLS; ++k) {
           t = fmaf(dl[k], w[k][j], t);
-          accw[k][j] = fmaf(dl[k], a[u][j], accw[k][j]);
+          accw[k][j] = fmaf(dl[k], a[j], accw[k][j]);
         }
         o[j] = t;
       }

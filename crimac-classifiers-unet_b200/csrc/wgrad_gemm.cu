@@ -380,12 +380,17 @@ __global__ void __launch_bounds__(256) wgrad_unpack_all_kernel(const __grid_cons
     const int n = static_cast<int>(min(256L, L.mn - i0));
     // coalesced read (and zero) of each tap plane, transposed through shared memory into contiguous [pair][tap] rows
     if (static_cast<int>(threadIdx.x) < n) {
+      // all loads first (independent, in flight together), then the zero stores: the compiler must not be forced to
+      // order each load behind the previous tap's store to the same array
+      float* src = L.scratch + i0 + threadIdx.x;
+      float g[9];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) g[tp] = (tp < L.taps) ? __ldcs(src + tp * L.mn) : 0.f;
 #pragma unroll
       for (int tp = 0; tp < 9; ++tp)
         if (tp < L.taps) {
-          float* src = L.scratch + tp * L.mn + i0 + threadIdx.x;
-          s[threadIdx.x * L.taps + tp] = *src;
-          *src = 0.f;
+          src[tp * L.mn] = 0.f;
+          s[threadIdx.x * L.taps + tp] = g[tp];
         }
     }
     __syncthreads();
