@@ -120,6 +120,8 @@ ProfScope::~ProfScope() {
 }
 
 extern "C" unsigned long long crimac_launch_count() { return g_launches; }
+bool crimac_profiling() { return g_prof_on; }
+
 extern "C" int crimac_profile_enable(int on) {
   for (ProfRec& r : g_prof) {
     g_event_pool.push_back(r.e0);

@@ -51,6 +51,7 @@ struct UnpackTable {
 cudaError_t launch_wgrad_unpack_all(UnpackTable& t, cudaStream_t stream);
 
 int device_num_sms();
+bool crimac_profiling();  // per-launch event timing is on: kernels are then kept on ONE stream so that times are isolated
 
 // ---- launch accounting + optional per-launch CUDA-event timing (crimac_profile_* in the C-ABI).
 // Every kernel launch of the network-level entry points goes through a Scope: it always counts the launch and, when

@@ -47,6 +47,7 @@ struct Conv3 {
   WgradParams wg_tap{};   // one-tap-per-CTA kernel (deep layers: few pixels, many channels)
   bool wg_use_halo = true;
   float* wg_scratch = nullptr;  // [9][cout][cin] fp32, zero between steps
+  int gr_idx = 0;               // which of the two dRaw buffers this layer's BatchNorm backward writes
 };
 struct ConvT {
   int cin = 0, cout = 0, level_in = 0;
@@ -72,7 +73,11 @@ struct crimac_ctx {
   std::vector<int> enc1, enc2, dec1, dec2;  // indices into conv
   int s_head_w = 0, s_head_b = 0, g_head_w = 0, g_head_b = 0;
   // shared scratch
-  bf16 *GA = nullptr, *GR = nullptr, *GP = nullptr;
+  bf16 *GA = nullptr, *GP = nullptr;
+  bf16* GR[2] = {nullptr, nullptr};  // dRaw, double-buffered: layer k's weight gradient overlaps layer k+1's BN backward
+  cudaStream_t side = nullptr;       // weight-gradient GEMMs run here, concurrently with the HBM-bound backward kernels
+  cudaEvent_t ev_draw[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr}, ev_cat = nullptr, ev_join = nullptr;
+  bool overlap = true;
   std::vector<bf16*> dcat;
   float* stats = nullptr;
   float* red_partials = nullptr;
@@ -267,7 +272,20 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   if (train) {
     const size_t lvl0 = static_cast<size_t>(B) * cfg.height * cfg.width * cfg.start_filts;
     c->GA = bump.arr<bf16>(lvl0);
-    c->GR = bump.arr<bf16>(lvl0);
+    c->GR[0] = bump.arr<bf16>(lvl0);
+    c->GR[1] = bump.arr<bf16>(lvl0);
+    {
+      // backward visits the convs in this order; consecutive layers alternate between the two dRaw buffers
+      int pos = 0;
+      for (int j = D - 2; j >= 0; --j) {
+        c->conv[c->dec2[j]].gr_idx = (pos++) & 1;
+        c->conv[c->dec1[j]].gr_idx = (pos++) & 1;
+      }
+      for (int l = D - 1; l >= 0; --l) {
+        c->conv[c->enc2[l]].gr_idx = (pos++) & 1;
+        c->conv[c->enc1[l]].gr_idx = (pos++) & 1;
+      }
+    }
     c->GP = bump.arr<bf16>(lvl0 / 4);
     for (int j = 0; j < D - 1; ++j) {
       const int l = D - 2 - j;
@@ -364,7 +382,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       if ((rc = make_weight_map(&p.b_map, L.w_fwd, L.cout, 9 * L.cin, L.bn_fwd))) return rc;
     }
     if (train) {
-      View gr{c->GR, B, H, W, L.cout, L.cout};
+      View gr{c->GR[L.gr_idx], B, H, W, L.cout, L.cout};
       if (!L.first) {
         ConvParams& p = L.dgrad;
         p.taps = 9;
@@ -548,8 +566,18 @@ extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* w
     rc = 1;
   }
   if (rc == 0) rc = build(c, workspace_dev, nullptr, true);
+  if (rc == 0 && cfg->train) {
+    c->overlap = getenv("CRIMAC_NO_OVERLAP") == nullptr;  // A/B switch for measurements
+    cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&c->ev_draw[0], &c->ev_draw[1], &c->ev_wg[0], &c->ev_wg[1], &c->ev_cat, &c->ev_join})
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      crimac_set_error(std::string("side stream / event creation failed: ") + cudaGetErrorString(e));
+      rc = 2;
+    }
+  }
   if (rc) {
-    delete c;
+    crimac_destroy(c);
     return rc;
   }
   *out = c;
@@ -557,6 +585,11 @@ extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* w
 }
 
 extern "C" int crimac_destroy(crimac_ctx* c) {
+  if (c) {
+    for (cudaEvent_t ev : {c->ev_draw[0], c->ev_draw[1], c->ev_wg[0], c->ev_wg[1], c->ev_cat, c->ev_join})
+      if (ev) cudaEventDestroy(ev);
+    if (c->side) cudaStreamDestroy(c->side);
+  }
   delete c;
   return 0;
 }
@@ -727,6 +760,13 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   int rc;
   const int sms = device_num_sms();
   const int D = c->D;
+  const bool saved_overlap = c->overlap;
+  struct Restore {
+    crimac_ctx* c;
+    bool v;
+    ~Restore() { c->overlap = v; }
+  } restore{c, saved_overlap};
+  if (crimac_profiling()) c->overlap = false;  // isolated per-kernel timings
   if (c->wg_dirty) {
     ProfScope ps("wgrad_zero", 0, static_cast<double>(c->wg_arena_bytes), st);
     CRIMAC_CHECK_CUDA(cudaMemsetAsync(c->wg_arena, 0, c->wg_arena_bytes, st));
@@ -738,27 +778,39 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     Conv3& L = c->conv[idx];
     const int H = level_h(c, L.level), W = level_w(c, L.level);
     View da{c->GA, nb, H, W, L.cout, L.cout};
-    View dr{c->GR, nb, H, W, L.cout, L.cout};
+    View dr{c->GR[L.gr_idx], nb, H, W, L.cout, L.cout};
     const double px = static_cast<double>(nb) * H * W;
+    // the weight gradient that last read this dRaw buffer (two layers ago) must have finished
+    if (c->overlap) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_wg[L.gr_idx], 0));
     {
       ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 4);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
                                       grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2,
                                       (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, st));
     }
-    if (L.first) {
-      ProfScope ps("first_conv_wgrad", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st, 2);
-      CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, dr, L.cin, c->fc_partials, grads[L.g_w], 0, st));
-      return 0;
-    }
-    int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, st) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, st);
-    if (r) return r;
-    if (L.gin.ptr != nullptr) {
+    if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_draw[L.gr_idx], st));
+    // backward-data first (critical path, issued first so that it is scheduled first) ...
+    if (!L.first && L.gin.ptr != nullptr) {
       ConvParams p = L.dgrad;
       set_batch(p, nb);
       ProfScope ps("conv3x3_dgrad", igemm_flops_n(p, L.cin), px * 2.0 * (L.cin + L.cout), st);
       CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_bwd, EPI_STORE, sms, st));
     }
+    // ... then the weight gradient: tensor-bound and off the critical path -> side stream, where it overlaps the
+    // HBM-bound BatchNorm / pooling backward kernels of the following layers (dRaw is double-buffered for this)
+    cudaStream_t ws = st;
+    if (c->overlap) {
+      CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->side, c->ev_draw[L.gr_idx], 0));
+      ws = c->side;
+    }
+    if (L.first) {
+      ProfScope ps("first_conv_wgrad", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), ws, 2);
+      CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, dr, L.cin, c->fc_partials, grads[L.g_w], 0, ws));
+    } else {
+      int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, ws) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, ws);
+      if (r) return r;
+    }
+    if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_wg[L.gr_idx], c->side));
     return 0;
   };
 
@@ -781,11 +833,15 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, st, 2);
       CRIMAC_CHECK_CUDA(launch_view_colsum(with_batch(U.gout, nb), c->red_partials, grads[U.g_b], 0, st));
     }
-    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, st))) return rc;
-    ConvParams p = U.dgrad;
-    set_batch(p, nb);
-    ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
-    CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));  // -> GA (grad of the convT input)
+    if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_cat, st));
+    {
+      ConvParams p = U.dgrad;
+      set_batch(p, nb);
+      ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));  // -> GA (grad of the convT input)
+    }
+    if (c->overlap) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->side, c->ev_cat, 0));
+    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, c->overlap ? c->side : st))) return rc;
   }
   // encoder, deepest level first
   for (int l = D - 1; l >= 0; --l) {
@@ -800,6 +856,10 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     }
     if ((rc = conv_bwd(c->enc2[l]))) return rc;
     if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
+  }
+  if (c->overlap) {
+    CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_join, c->side));
+    CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
   }
   {
     UnpackTable t{};
