@@ -210,47 +210,67 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 }
 
 // ============================================================================ BN apply + ReLU (+pool)
+// A thread owns one 8-channel group (its scale/shift stay in registers) and strides over pixels: no per-element index
+// division, several independent 16-byte loads in flight.
 template <bool POOL>
 __global__ void __launch_bounds__(256) bn_apply_kernel(View raw, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, View act, View pool) {
-  const int groups = raw.C >> 3;
-  const int Ho = POOL ? raw.H >> 1 : raw.H, Wo = POOL ? raw.W >> 1 : raw.W;
-  const long total = static_cast<long>(raw.N) * Ho * Wo * groups;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
-    long pix = i / groups;
-    const int xo = static_cast<int>(pix % Wo);
-    pix /= Wo;
-    const int yo = static_cast<int>(pix % Ho);
-    const int n = static_cast<int>(pix / Ho);
-    float sc[8], sh[8];
-    ldg8f(scale + g * 8, sc);
-    ldg8f(shift + g * 8, sh);
-    if (!POOL) {
-      const long p = (static_cast<long>(n) * raw.H + yo) * raw.W + xo;
-      float v[8];
-      load8(raw.ptr + p * raw.pitch + g * 8, v);
+  const int groups = raw.C >> 3, ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  float sc[8], sh[8];
+  ldg8f(scale + g * 8, sc);
+  ldg8f(shift + g * 8, sh);
+  const unsigned stride = gridDim.x * ppb;
+  if (!POOL) {
+    const unsigned npix = static_cast<unsigned>(raw.N) * raw.H * raw.W;
+    constexpr int U = 4;
+    for (unsigned p0 = blockIdx.x * ppb + pl; p0 < npix; p0 += U * stride) {
+      uint4 rv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
-      store8(act.ptr + p * act.pitch + g * 8, v);
-    } else {
+      for (int u = 0; u < U; ++u) {
+        const unsigned p = p0 + u * stride;
+        rv[u] = p < npix ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + static_cast<size_t>(p) * raw.pitch + g * 8))
+                         : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned p = p0 + u * stride;
+        if (p < npix) {
+          const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float2 r = unpack_bf16x2(rw[h]);
+            pk[h] = pack_bf16x2(fmaxf(fmaf(r.x, sc[2 * h], sh[2 * h]), 0.f), fmaxf(fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]), 0.f));
+          }
+          store16(act.ptr + static_cast<size_t>(p) * act.pitch + g * 8, pk);
+        }
+      }
+    }
+  } else {
+    const unsigned Ho = raw.H >> 1, Wo = raw.W >> 1;
+    const unsigned npool = static_cast<unsigned>(raw.N) * Ho * Wo;
+    for (unsigned pp = blockIdx.x * ppb + pl; pp < npool; pp += stride) {
+      const unsigned q = pp / Wo, xo = pp - q * Wo, n = q / Ho, yo = q - n * Ho;
+      const size_t p00 = (static_cast<size_t>(n) * raw.H + 2 * yo) * raw.W + 2 * xo;
+      uint4 rv[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        rv[w] = __ldcs(reinterpret_cast<const uint4*>(raw.ptr + (p00 + (w >> 1) * raw.W + (w & 1)) * raw.pitch + g * 8));
       uint32_t mx[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long p = (static_cast<long>(n) * raw.H + 2 * yo + (q >> 1)) * raw.W + 2 * xo + (q & 1);
-        float v[8];
-        load8(raw.ptr + p * raw.pitch + g * 8, v);
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t rw[4] = {rv[w].x, rv[w].y, rv[w].z, rv[w].w};
+        uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
-        uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                          pack_bf16x2(v[6], v[7])};
-        store16(act.ptr + p * act.pitch + g * 8, pk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mx[j] = q == 0 ? pk[j] : bf16x2_max(mx[j], pk[j]);
+        for (int h = 0; h < 4; ++h) {
+          const float2 r = unpack_bf16x2(rw[h]);
+          pk[h] = pack_bf16x2(fmaxf(fmaf(r.x, sc[2 * h], sh[2 * h]), 0.f), fmaxf(fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]), 0.f));
+          mx[h] = w == 0 ? pk[h] : bf16x2_max(mx[h], pk[h]);
+        }
+        store16(act.ptr + (p00 + (w >> 1) * raw.W + (w & 1)) * act.pitch + g * 8, pk);
       }
-      const long pp = (static_cast<long>(n) * Ho + yo) * Wo + xo;
-      store16(pool.ptr + pp * pool.pitch + g * 8, mx);
+      store16(pool.ptr + static_cast<size_t>(pp) * pool.pitch + g * 8, mx);
     }
   }
 }
@@ -654,48 +674,44 @@ __device__ __forceinline__ void block_channel_sums(const float (&acc)[NQ][8], in
   }
 }
 
-// phase 1: g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * xhat
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dact, View raw, const float* __restrict__ scale,
-                                                            const float* __restrict__ shift,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, float* partials) {
+// phase 1: g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * raw.  (sum g * xhat is derived from the two
+// by the finalize kernel: invstd * (sum g*raw - mean * sum g); the kernel then needs only two per-channel constants
+// in registers, which doubles its occupancy - it is bound by the bytes it keeps in flight.)
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, View raw, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, float* partials) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
-  float sc[8], sh[8], mu[8], is[8];
+  float sc[8], sh[8];
   ldg8f(scale + g * 8, sc);
   ldg8f(shift + g * 8, sh);
-  ldg8f(mean + g * 8, mu);
-  ldg8f(invstd + g * 8, is);
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  long p = static_cast<long>(blockIdx.x) * ppb + pl;
-  // two pixels per iteration: four independent 16-byte loads in flight per thread
-  for (; p + stride < npix; p += 2 * stride) {
-    float d0[8], r0[8], d1[8], r1[8];
-    load8(dact.ptr + p * dact.pitch + g * 8, d0);
-    load8(raw.ptr + p * raw.pitch + g * 8, r0);
-    load8(dact.ptr + (p + stride) * dact.pitch + g * 8, d1);
-    load8(raw.ptr + (p + stride) * raw.pitch + g * 8, r1);
+  constexpr int U = 4;  // pixels per iteration: 2*U independent 16-byte loads in flight per thread
+  for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
+    uint4 dv[U], rv[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float g0 = fmaf(r0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
-      const float g1 = fmaf(r1[j], sc[j], sh[j]) > 0.f ? d1[j] : 0.f;
-      acc[0][j] += g0 + g1;
-      acc[1][j] += g0 * (r0[j] - mu[j]) * is[j] + g1 * (r1[j] - mu[j]) * is[j];
+    for (int u = 0; u < U; ++u) {
+      const long p = p0 + u * stride;
+      const bool ok = p < npix;
+      dv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
+      rv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
     }
-  }
-  if (p < npix) {
-    float d0[8], r0[8];
-    load8(dact.ptr + p * dact.pitch + g * 8, d0);
-    load8(raw.ptr + p * raw.pitch + g * 8, r0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float g0 = fmaf(r0[j], sc[j], sh[j]) > 0.f ? d0[j] : 0.f;
-      acc[0][j] += g0;
-      acc[1][j] += g0 * (r0[j] - mu[j]) * is[j];
+    for (int u = 0; u < U; ++u) {
+      const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 d = unpack_bf16x2(dw[h]), r = unpack_bf16x2(rw[h]);
+        const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d.x : 0.f;
+        const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d.y : 0.f;
+        acc[0][2 * h] += g0;
+        acc[0][2 * h + 1] += g1;
+        acc[1][2 * h] = fmaf(g0, r.x, acc[1][2 * h]);
+        acc[1][2 * h + 1] = fmaf(g1, r.y, acc[1][2 * h + 1]);
+      }
     }
   }
   block_channel_sums<2>(acc, C, g, pl, ppb, partials);
@@ -707,7 +723,8 @@ template <int NQ>
 __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* __restrict__ partials, int nparts, int C,
                                                                    double count, float* out0, float* out1,
                                                                    int accumulate, float* c1, float* c2,
-                                                                   const float* gscale) {
+                                                                   const float* gscale, const float* mean,
+                                                                   const float* invstd) {
   // block = 8 channels x 32 part-lanes (short dependent load chains)
   __shared__ double sh[NQ][32][8];
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
@@ -744,6 +761,9 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
       for (int t = 1; t < 32; ++t) a[q] += sh[q][t][cl];
       a[q] *= gs;
     }
+    // BN backward: the second partial is sum g*raw; sum g*xhat = invstd * (sum g*raw - mean * sum g)
+    if (NQ == 2 && mean != nullptr)
+      a[NQ - 1] = static_cast<double>(invstd[c]) * (a[NQ - 1] - static_cast<double>(mean[c]) * a[0]);
     out0[c] = accumulate ? out0[c] + static_cast<float>(a[0]) : static_cast<float>(a[0]);
     if (NQ == 2) {
       out1[c] = accumulate ? out1[c] + static_cast<float>(a[NQ - 1]) : static_cast<float>(a[NQ - 1]);
@@ -753,41 +773,61 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
   }
 }
 
-// phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) -> bf16; partial = sum dRaw (= the conv-bias gradient)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dact, View raw, const float* __restrict__ scale,
-                                                           const float* __restrict__ shift,
-                                                           const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd,
-                                                           const float* __restrict__ c1, const float* __restrict__ c2,
-                                                           const float* gscale, View draw, float* partials) {
+// phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) = A*g + B*raw + K per channel -> bf16; partial = sum dRaw (= the
+// conv-bias gradient)
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View raw, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd,
+                                                              const float* __restrict__ c1, const float* __restrict__ c2,
+                                                              const float* gscale, View draw, float* partials) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
-  float sc[8], sh[8], mu[8], is[8], k1[8], k2[8];
-  ldg8f(scale + g * 8, sc);
-  ldg8f(shift + g * 8, sh);
-  ldg8f(mean + g * 8, mu);
-  ldg8f(invstd + g * 8, is);
-  ldg8f(c1 + g * 8, k1);
-  ldg8f(c2 + g * 8, k2);
-  const float gs = gscale ? *gscale : 1.f;
+  float sc[8], sh[8], cb[8], ck[8], ca[8];
+  {
+    float mu[8], is[8], k1[8], k2[8];
+    ldg8f(scale + g * 8, sc);
+    ldg8f(shift + g * 8, sh);
+    ldg8f(mean + g * 8, mu);
+    ldg8f(invstd + g * 8, is);
+    ldg8f(c1 + g * 8, k1);
+    ldg8f(c2 + g * 8, k2);
+    const float gs = gscale ? *gscale : 1.f;  // the incoming gradient was produced unnormalised (fused head/CE)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ca[j] = sc[j] * gs;
+      cb[j] = -sc[j] * k2[j] * is[j];
+      ck[j] = -sc[j] * k1[j] - cb[j] * mu[j];
+    }
+  }
   float acc[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += 2 * stride) {
+  constexpr int U = 4;
+  for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
+    uint4 dv[U], rv[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
+      const long p = p0 + u * stride;
+      const bool ok = p < npix;
+      dv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
+      rv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       if (p < npix) {
-        float d[8], r[8], o[8];
-        load8(dact.ptr + p * dact.pitch + g * 8, d);
-        load8(raw.ptr + p * raw.pitch + g * 8, r);
+        const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+        float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = fmaf(r[j], sc[j], sh[j]) > 0.f ? d[j] * gs : 0.f;
-          const float xh = (r[j] - mu[j]) * is[j];
-          o[j] = sc[j] * (gg - k1[j] - xh * k2[j]);
+        for (int h = 0; h < 4; ++h) {
+          const float2 d = unpack_bf16x2(dw[h]), r = unpack_bf16x2(rw[h]);
+          const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d.x : 0.f;
+          const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d.y : 0.f;
+          o[2 * h] = fmaf(ca[2 * h], g0, fmaf(cb[2 * h], r.x, ck[2 * h]));
+          o[2 * h + 1] = fmaf(ca[2 * h + 1], g1, fmaf(cb[2 * h + 1], r.y, ck[2 * h + 1]));
         }
         store8(draw.ptr + p * draw.pitch + g * 8, o);
         // conv-bias gradient = sum of dRaw: exactly zero in exact arithmetic (BN removes the bias); summed from the
@@ -1022,7 +1062,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 #define FW(C)                                                                                       \
   if (cin == C) {                                                                                   \
     first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
-    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr, nullptr); \
+    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr, nullptr, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
   FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
@@ -1044,12 +1084,15 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
   return cudaGetLastError();
 }
 cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, cudaStream_t st) {
+  if (raw.C % 8 != 0 || raw.C / 8 > 256) return cudaErrorInvalidValue;
+  if (static_cast<long>(raw.N) * raw.H * raw.W > 0x7fffffffL) return cudaErrorInvalidValue;  // 32-bit pixel index
+  const int ppb = 256 / (raw.C / 8);
   if (pool.ptr != nullptr) {
-    const long items = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2) * (raw.C / 8);
-    bn_apply_kernel<true><<<grid_for(items, 256), 256, 0, st>>>(raw, scale, shift, act, pool);
+    const long items = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2);
+    bn_apply_kernel<true><<<grid_for(items, ppb), 256, 0, st>>>(raw, scale, shift, act, pool);
   } else {
-    const long items = static_cast<long>(raw.N) * raw.H * raw.W * (raw.C / 8);
-    bn_apply_kernel<false><<<grid_for(items, 256), 256, 0, st>>>(raw, scale, shift, act, pool);
+    const long items = static_cast<long>(raw.N) * raw.H * raw.W;
+    bn_apply_kernel<false><<<grid_for((items + 3) / 4, ppb), 256, 0, st>>>(raw, scale, shift, act, pool);
   }
   return cudaGetLastError();
 }
@@ -1118,13 +1161,13 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int grid = reduce_grid(raw);
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
-  bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, partials);
+  bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
   partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, count, dbeta, dgamma, accumulate, c1c2,
-                                                                c1c2 + C, gscale);
+                                                                c1c2 + C, gscale, mean, invstd);
   bn_bwd_apply_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C,
                                                                   gscale, draw, partials);
   partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, dbias, nullptr, accumulate, nullptr,
-                                                                nullptr, nullptr);
+                                                                nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
@@ -1134,7 +1177,7 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
   const int ppb = 256 / (C / 8);
   view_colsum_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(v, partials);
   partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, out, nullptr, accumulate, nullptr,
-                                                                nullptr, nullptr);
+                                                                nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st) {
