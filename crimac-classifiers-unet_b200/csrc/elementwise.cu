@@ -6,6 +6,7 @@
 // All activation tensors are NHWC bf16 "views" (pointer, pitch) so that concat buffers are written/read in place.
 #include "host_util.h"
 #include "devfn.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -1037,13 +1038,29 @@ inline int grid_for(long work_items, int threads) {
 }  // namespace
 
 // ---------------------------------------------------------------------------- launchers (used by net_api.cu / ops_api2.cu)
-int first_conv_grid(int NB, int H, int W) {
+// The first conv runs on the tensor cores (first_conv_tc.cu) for up to 7 frequencies; the fp32 CUDA-core kernels below
+// remain for 8 frequencies and as the A/B reference (CRIMAC_FC_CUDACORE=1).
+static bool first_conv_use_tc(int cin) {
+  static const bool off = getenv("CRIMAC_FC_CUDACORE") != nullptr;
+  return !off && cin <= 7;
+}
+static int first_conv_cc_grid(int NB, int H, int W) {
   const int tiles = NB * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
   return tiles < 148 * 8 ? tiles : 148 * 8;
 }
+int first_conv_grid(int NB, int cin, int H, int W) {
+  return first_conv_use_tc(cin) ? first_conv_tc_grid(NB, H, W) : first_conv_cc_grid(NB, H, W);
+}
+size_t first_conv_wgrad_partial_floats(int cin) {
+  const size_t cc = static_cast<size_t>(first_conv_wgrad_blocks()) * 4 * 64 * cin * 9;
+  const size_t tc = static_cast<size_t>(256) * 128 * 64;  // >= number of SMs partial tiles
+  return cc > tc ? cc : tc;
+}
 cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
                               int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st) {
-  const int grid = first_conv_grid(NB, H, W);
+  if (first_conv_use_tc(cin))
+    return launch_first_conv_tc(x, w, scale, shift, relu, NB, cin, H, W, out, out_pitch, stats, st);
+  const int grid = first_conv_cc_grid(NB, H, W);
 #define FC(C)                                                                                                   \
   if (cin == C) {                                                                                               \
     first_conv_kernel<C><<<grid, 64, 0, st>>>(x, w, scale, shift, relu, NB, H, W, out, out_pitch, stats);       \
@@ -1057,6 +1074,7 @@ cudaError_t launch_first_conv(const float* x, const float* w, const float* scale
 int first_conv_wgrad_blocks() { return 148 * 2; }
 cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
                                     cudaStream_t st) {
+  if (first_conv_use_tc(cin)) return launch_first_conv_wgrad_tc(x, draw, cin, partials, dw, accumulate, st);
   const int tiles = draw.N * ((draw.H + TILE_H - 1) / TILE_H) * ((draw.W + TILE_W - 1) / TILE_W);
   const int grid = tiles < first_conv_wgrad_blocks() ? tiles : first_conv_wgrad_blocks();
 #define FW(C)                                                                                       \

@@ -66,8 +66,16 @@ struct ProfScope {
 // ---- CUDA-core kernels (elementwise.cu)
 cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
                               int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st);
-int first_conv_grid(int NB, int H, int W);  // = rows of the statistics partials the kernel writes
+int first_conv_grid(int NB, int cin, int H, int W);  // = rows of the statistics partials the kernel writes
 int first_conv_wgrad_blocks();
+size_t first_conv_wgrad_partial_floats(int cin);  // scratch the weight-gradient launcher needs
+// tensor-core variants (first_conv_tc.cu), cin <= 7; the launchers above dispatch to them
+int first_conv_tc_grid(int NB, int H, int W);
+cudaError_t launch_first_conv_tc(const float* x, const float* w, const float* scale, const float* shift, int relu,
+                                 int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats,
+                                 cudaStream_t st);
+cudaError_t launch_first_conv_wgrad_tc(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
+                                       cudaStream_t st);
 cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
                                     cudaStream_t st);
 cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double count, const float* gamma,

@@ -315,7 +315,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       }
     }
     c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 4 * (cfg.n_classes * 64 + cfg.n_classes));
-    c->fc_partials = bump.arr<float>(static_cast<size_t>(first_conv_wgrad_blocks()) * 4 * 64 * cfg.in_channels * 9);
+    c->fc_partials = bump.arr<float>(first_conv_wgrad_partial_floats(cfg.in_channels));
     c->ce_partials = bump.arr<double>(static_cast<size_t>(ce_blocks()) * 2);
     const size_t lg = static_cast<size_t>(B) * cfg.n_classes * cfg.height * cfg.width;
     c->logits = bump.arr<float>(lg);
@@ -631,7 +631,7 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
       const double px = static_cast<double>(nb) * H * W;
       if (L.first) {
         ProfScope ps("first_conv", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st);
-        stat_rows = first_conv_grid(nb, H, W);
+        stat_rows = first_conv_grid(nb, L.cin, H, W);
         CRIMAC_CHECK_CUDA(launch_first_conv(x, S<float>(state, L.s_w), nullptr, S<float>(state, L.s_b), 0, nb, L.cin, H,
                                             W, raw.ptr, raw.pitch, c->stats, st));
       } else {

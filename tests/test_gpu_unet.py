@@ -156,7 +156,10 @@ def test_train_step_vs_oracle(M, depth, B, H, W):
         worst_cos = min(worst_cos, _cos(p.grad, ref_g[name]))
         # closer to the storage-emulating oracle than that oracle is to fp32 (the problem amplifies ANY perturbation,
         # incl. fp32 summation order, by the same factor: see DESIGN.md section 4)
-        assert r_emu <= max(2e-2, 0.75 * floor), (name, r_emu, floor)
+        # "floor" is how far bf16 STORAGE alone moves this gradient (fp32 arithmetic, identical rounding points); the
+        # kernels must stay inside that noise ball, both around the emulated and around the fp32 oracle
+        assert r_emu <= max(2e-2, 1.0 * floor), (name, r_emu, floor)
+        assert _rel(p.grad, ref_g[name]) <= max(2e-2, 1.5 * floor), (name, _rel(p.grad, ref_g[name]), floor)
         assert _cos(p.grad, ref_g[name]) >= 0.8, (name, _cos(p.grad, ref_g[name]))
         assert 0.8 <= (p.grad.norm() / ref_g[name].norm()).item() <= 1.25, name
     print(f"depth {depth}: worst rel-L2 vs bf16-emulated oracle {worst_emu:.4g}; worst cosine vs fp32 oracle {worst_cos:.4f}")
