@@ -127,9 +127,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // register re-allocation between the warpgroups: the TMA / MMA / allocator warps need few registers, the epilogue
+  // warps keep up to 128 BatchNorm accumulators per thread (128 x 56 + 256 x 224 = 64512 <= 65536 registers)
+  // (setmaxnreg sits at the top of each role branch below, with no control-flow merge in between)
+
   const int cblocks = p.cin / KBLK;
   const int ksteps = p.taps * cblocks;
 
+  // Only the variant that keeps 128 BatchNorm accumulators per epilogue thread re-allocates registers between the
+  // warpgroups (128 x 56 + 256 x 224 = 64512 <= 65536); measured: the others run faster with the static 168.
+  constexpr bool REALLOC = (EPI == EPI_STATS) && (BLOCK_N == 128);
+  if (warp < 4) {
+  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     // elect.sync (not lane == 0): the compiler then knows a single thread runs the loop and emits the uniform-datapath
@@ -294,7 +303,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         ptx::umma_commit(&tmem_full[as]);
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column groups =====================
     const int e = threadIdx.x - 128;      // 0..255
     const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware: warp id % 4)
@@ -306,11 +317,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
     // one n-tile for the whole kernel: scale/shift are loaded once, and with one chunk per warp the BN statistics
     // stay in per-thread registers until the CTA has finished all of its tiles (no shuffles in the tile loop)
     const bool fixed_n = (p.n_tiles == 1);
-    const bool run_stats = (EPI == EPI_STATS) && (NCHUNK == EPI_COLGROUPS) && fixed_n;
-    float r1[32], r2[32];
-    if (EPI == EPI_STATS && NCHUNK == EPI_COLGROUPS) {
+    // chunks per warp; with at most two the statistics of all of them fit in registers (the epilogue warps raise their
+    // register allowance with setmaxnreg for this)
+    constexpr int CPW = NCHUNK / EPI_COLGROUPS;
+    constexpr int RUN_CPW = (EPI == EPI_STATS && CPW <= 2) ? CPW : 0;
+    const bool run_stats = (RUN_CPW > 0) && fixed_n;
+    float r1[RUN_CPW > 0 ? RUN_CPW : 1][32], r2[RUN_CPW > 0 ? RUN_CPW : 1][32];
+    if (RUN_CPW > 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r1[j] = r2[j] = 0.f;
+      for (int ci = 0; ci < (RUN_CPW > 0 ? RUN_CPW : 1); ++ci)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r1[ci][j] = r2[ci][j] = 0.f;
     }
     auto load_affine = [&](int as, int n0) {
       float* sc = s_affine + as * 2 * BLOCK_N;
@@ -358,8 +375,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
           logit[k] = (h == 0 && k < p.n_classes) ? s_head[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
       }
 
-#pragma unroll 1
-      for (int chunk = h; chunk < NCHUNK; chunk += EPI_COLGROUPS) {
+      auto chunk_body = [&](const int chunk, float (&ra)[32], float (&rb)[32]) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + chunk * 32, v);
         ptx::tmem_ld_wait();
@@ -430,14 +446,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
 
         if (EPI == EPI_STATS) {
           // statistics of the bf16-rounded values the BN-apply pass will read back
-          if (NCHUNK == EPI_COLGROUPS && run_stats) {
+          if (RUN_CPW > 0 && run_stats) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
-              r1[2 * j] += t.x;
-              r1[2 * j + 1] += t.y;
-              r2[2 * j] = fmaf(t.x, t.x, r2[2 * j]);
-              r2[2 * j + 1] = fmaf(t.y, t.y, r2[2 * j + 1]);
+              ra[2 * j] += t.x;
+              ra[2 * j + 1] += t.y;
+              rb[2 * j] = fmaf(t.x, t.x, rb[2 * j]);
+              rb[2 * j + 1] = fmaf(t.y, t.y, rb[2 * j + 1]);
             }
           } else {
             float s1[32], s2[32];
@@ -455,6 +471,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
             s_red[(q * 2 + 1) * BLOCK_N + chunk * 32 + lane] = s2[0];
           }
         }
+      };
+      if constexpr (RUN_CPW > 0) {
+#pragma unroll
+        for (int ci = 0; ci < RUN_CPW; ++ci) chunk_body(h + ci * EPI_COLGROUPS, r1[ci], r2[ci]);
+      } else {
+#pragma unroll 1
+        for (int chunk = h; chunk < NCHUNK; chunk += EPI_COLGROUPS) chunk_body(chunk, r1[0], r2[0]);
       }
 
       // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -518,11 +541,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       // one partial row per CTA: stats[blockIdx.x][2][n_total]; bn_finalize sums gridDim.x rows
       const int n_total = p.n_tiles * BLOCK_N;
       const int n2 = 2 * n_total;
-      if (NCHUNK == EPI_COLGROUPS && run_stats) {
-        xpose_reduce(r1, lane);
-        xpose_reduce(r2, lane);
-        s_red[(q * 2 + 0) * BLOCK_N + h * 32 + lane] = r1[0];
-        s_red[(q * 2 + 1) * BLOCK_N + h * 32 + lane] = r2[0];
+      if (RUN_CPW > 0 && run_stats) {
+#pragma unroll
+        for (int ci = 0; ci < (RUN_CPW > 0 ? RUN_CPW : 1); ++ci) {
+          xpose_reduce(r1[ci], lane);
+          xpose_reduce(r2[ci], lane);
+          s_red[(q * 2 + 0) * BLOCK_N + (h + ci * EPI_COLGROUPS) * 32 + lane] = r1[ci][0];
+          s_red[(q * 2 + 1) * BLOCK_N + (h + ci * EPI_COLGROUPS) * 32 + lane] = r2[ci][0];
+        }
         epi_bar();
         for (int c = e; c < BLOCK_N; c += EPI_THREADS) {
           float a = 0.f, b = 0.f;
