@@ -37,6 +37,7 @@ struct ConvParams {
   int taps;              // 9, 1 or 4
   int tap_mode;          // 0: tap -> (dy,dx) offsets on map 0 (3x3: tap=ky*3+kx; 1 tap: centre); 1: tap -> map index
   int halo;              // 1: 3x3 conv with the 16x8 tile / halo-box main loop (a_map[0] = box {64,10,18,1})
+  int resident;          // set by the launcher: >0 = weights stay in shared memory, value = number of halo slots
   int cin;               // channels per tap, multiple of 64
   int NB, H, W;          // GEMM-M geometry: output pixels = NB*H*W
   int tiles_x, tiles_y, n_tiles, total_tiles;

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "devfn.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -45,7 +46,11 @@ struct ConvCfg {
   static constexpr int TPS = (BLOCK_N == 256) ? 1 : 3;
   static constexpr int NB = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4);
   static constexpr int BSTAGE_BYTES = TPS * B_BYTES;
-  static constexpr int OPERAND_BYTES = HALO ? (NA * HALO_SLOT + NB * BSTAGE_BYTES) : (STAGES * STAGE_BYTES);
+  // resident-weights variant (narrow layers whose whole weight matrix is <= 144 KB): [weights | 2-3 halo tiles]
+  static constexpr int RES_MAX_B = 147456;
+  static constexpr int RES_BYTES = (BLOCK_N == 256) ? 0 : (RES_MAX_B + 2 * HALO_SLOT);
+  static constexpr int RING_BYTES = NA * HALO_SLOT + NB * BSTAGE_BYTES;
+  static constexpr int OPERAND_BYTES = HALO ? (RING_BYTES > RES_BYTES ? RING_BYTES : RES_BYTES) : (STAGES * STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int MAX_STAT_CH = 4 * BLOCK_N;  // per-CTA running channel sums (EPI_STATS) over all n-tiles
   static constexpr int HEAD_BYTES = (BLOCK_N == 64) ? ((CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 +
@@ -135,10 +140,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   const int ksteps = p.taps * cblocks;
 
   // Only the variant that keeps 128 BatchNorm accumulators per epilogue thread re-allocates registers between the
-  // warpgroups (128 x 56 + 256 x 224 = 64512 <= 65536); measured: the others run faster with the static 168.
+  // warpgroups (128 x 72 + 256 x 216 = 64512 <= 65536); measured: the others run faster with the static 168.
   constexpr bool REALLOC = (EPI == EPI_STATS) && (BLOCK_N == 128);
   if (warp < 4) {
-  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     // elect.sync (not lane == 0): the compiler then knows a single thread runs the loop and emits the uniform-datapath
@@ -148,6 +153,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       uint32_t phase = 0, bphase = 0;
       (void)bstage;
       (void)bphase;
+      if (HALO && p.resident) {
+        // the whole weight matrix is loaded ONCE per CTA (n_tiles == 1) and stays in shared memory: block (tap, cb)
+        // at (tap*cblocks + cb) * B_BYTES.  Per tile only the activation halo tiles move.
+        ptx::mbar_arrive_expect_tx(&bfull_bar[0], 9 * cblocks * Cfg::B_BYTES);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int cb = 0; cb < cblocks; ++cb) {
+            uint8_t* sb = smem + (tap * cblocks + cb) * Cfg::B_BYTES;
+            if constexpr (BMN) {
+#pragma unroll
+              for (int b = 0; b < BLOCK_N / 64; ++b)
+                ptx::tma_load_2d(sb + b * 8192, &p.b_map, &bfull_bar[0], (8 - tap) * p.b_tap_cols + b * 64, cb * KBLK);
+            } else {
+              ptx::tma_load_2d(sb, &p.b_map, &bfull_bar[0], tap * p.cin + cb * KBLK, 0);
+            }
+          }
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int m_tile = tile / p.n_tiles;
@@ -156,6 +177,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         const int ty = m_tile % p.tiles_y;
         const int img = m_tile / p.tiles_y;
         const int x0 = tx * TW, y0 = ty * TH, n0 = n_tile * BLOCK_N;
+        if (HALO && p.resident) {
+          uint8_t* a_base = smem + 9 * cblocks * Cfg::B_BYTES;
+          for (int cb = 0; cb < cblocks; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], HALO_BYTES);
+            ptx::tma_load_4d(a_base + stage * HALO_SLOT, &p.a_map[0], &full_bar[stage], cb * KBLK, x0 - 1, y0 - 1, img);
+            if (++stage == p.resident) {  // p.resident = number of halo slots (2 or 3)
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          continue;
+        }
         if constexpr (HALO) {
           for (int cb = 0; cb < cblocks; ++cb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -242,6 +276,35 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         ptx::mbar_wait(&tmem_empty[as], aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        if (HALO && p.resident) {
+          const uint64_t adesc0 = ptx::make_smem_desc(0, 16, HALO_W * 128);
+          const uint64_t bdesc0 = BMN ? ptx::make_smem_desc(0, 8192, 1024) : ptx::make_smem_desc(0, 16, 1024);
+          const uint32_t sb16 = ptx::smem_u32(smem) >> 4;
+          const uint32_t sa16 = sb16 + ((9 * cblocks * Cfg::B_BYTES) >> 4);
+          if (it == 0) ptx::mbar_wait(&bfull_bar[0], 0);  // weights resident from here on
+          for (int cb = 0; cb < cblocks; ++cb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = adesc0 + (sa16 + stage * (HALO_SLOT >> 4));
+            const uint64_t bdesc = bdesc0 + (sb16 + cb * (Cfg::B_BYTES >> 4));
+            const uint32_t btap16 = static_cast<uint32_t>(cblocks) * (Cfg::B_BYTES >> 4);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t aoff = (((tap / 3) * HALO_W + tap % 3) * 128) >> 4;
+#pragma unroll
+              for (int k = 0; k < KBLK / 16; ++k)
+                ptx::umma_bf16(d_tmem, adesc + (aoff + 2 * k), bdesc + (tap * btap16 + B_KSTEP16 * k), idesc,
+                               (tap | k) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == p.resident) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          ptx::umma_commit(&tmem_full[as]);
+          continue;
+        }
         if constexpr (HALO) {
           // descriptor templates: everything but the 14-bit start-address field (shared memory addresses are < 256 KB,
           // so adding (address >> 4) never carries out of the field)
@@ -305,7 +368,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
     }
   }
   } else {
-    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if constexpr (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column groups =====================
     const int e = threadIdx.x - 128;      // 0..255
     const int q = warp & 3;               // TMEM lane quarter this warp may read (hardware: warp id % 4)
@@ -587,6 +650,16 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   }
   if (EPI == EPI_STATS && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  if (HALO && BLOCK_N != 256) {
+    // resident weights when the whole matrix fits beside two or three halo tiles
+    static const bool off = getenv("CRIMAC_NO_RESIDENT") != nullptr;
+    const int wbytes = 9 * (p.cin / KBLK) * Cfg::B_BYTES;
+    ConvParams q = p;
+    q.resident = 0;
+    if (!off && p.n_tiles == 1 && wbytes <= Cfg::RES_MAX_B) q.resident = (wbytes + 3 * HALO_SLOT <= Cfg::OPERAND_BYTES) ? 3 : 2;
+    kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(q);
+    return cudaGetLastError();
+  }
   kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
