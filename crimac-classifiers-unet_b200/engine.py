@@ -116,6 +116,24 @@ class Context:
         )
 
 
+def forward_infer_fp32(cfg_tuple, state_tensors, x, softmax):
+    """fp32 validation forward (independent CUDA-core implementation). cfg_tuple = (in_ch, n_classes, depth, start_filts)."""
+    L = _lib.load()
+    nb, _, h, w = x.shape
+    cfg = _Config(cfg_tuple[0], cfg_tuple[1], cfg_tuple[2], cfg_tuple[3], nb, h, w, 0)
+    n = ctypes.c_size_t(0)
+    _lib.check(L.crimac_fp32_workspace_bytes(ctypes.byref(cfg), nb, ctypes.byref(n)), "crimac_fp32_workspace_bytes")
+    ws = torch.empty(n.value, dtype=torch.uint8, device=x.device)
+    out = torch.empty((nb, cfg_tuple[1], h, w), dtype=torch.float32, device=x.device)
+    state = (ctypes.c_void_p * len(state_tensors))(*[t.data_ptr() for t in state_tensors])
+    _lib.check(
+        L.crimac_forward_infer_fp32(ctypes.byref(cfg), state, _lib.ptr(x), nb, _lib.ptr(out), int(softmax), _lib.ptr(ws),
+                                    ctypes.c_size_t(n.value), _lib.stream_ptr()),
+        "crimac_forward_infer_fp32",
+    )
+    return out
+
+
 def sgd_step(params_flat, momentum_flat, grads_flat, lr, momentum, gscale=1.0):
     """Fused SGD(momentum) on flat fp32 arenas (reference pipeline.py:156,178)."""
     L = _lib.load()

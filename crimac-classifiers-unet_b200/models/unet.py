@@ -313,6 +313,17 @@ class UNet_Baseline(UNet):
             raise RuntimeError("predict_proba() is an eval-mode call; use model.eval() first")
         return self._infer(x, softmax=True)
 
+    @torch.no_grad()
+    def forward_fp32(self, x, softmax=False):
+        """fp32 VALIDATION mode: the eval forward through an independent plain-fp32 CUDA implementation (no bf16, no
+        tensor cores) - logits, or probabilities with softmax=True.  For 1e-4 parity checks, ~50x slower."""
+        if self.training:
+            raise RuntimeError("forward_fp32() is an eval-mode call; use model.eval() first")
+        x = self._prep_input(x)
+        rt = _runtime()
+        return rt.forward_infer_fp32((self.in_channels, self.n_classes, self.depth, self.start_filts),
+                                     self._state_tensors(), x, softmax)
+
     def train_step_fused(self, x, labels, class_weight, ignore_index=-100):
         """Forward + class-weighted CE + backward in one native call (pipeline.py:171-177).
 

@@ -14,6 +14,7 @@
  *   crimac_preprocess      batch/dataset.py:192-205 + utils/np.py:362-375 + batch/data_transforms/{remove_nan_inf,db_with_limits}.py
  *   crimac_stitch          pipeline_train_predict/save_predict.py:41-65 (fill_out_array) + label masks of
  *                          batch/label_transforms/mask_label_{overlap,seabed}.py
+ *   crimac_forward_infer_fp32   the same forward in plain fp32 (validation mode, 1e-4 parity)
  *   crimac_op_* / crimac_dbg_*   single-kernel entry points used by the parity tests only.
  *
  * Conventions: every function returns 0 on success, 1 for an invalid argument, 2 for a CUDA failure;
@@ -101,6 +102,14 @@ int crimac_preprocess(const float* sv_dev, int F, int R, int P, int data_ping0, 
 int crimac_stitch(const float* probs_dev, int n, int n_classes, int ph, int pw, const int32_t* centres_dev,
                   const uint8_t* nan_dev, const int16_t* labels_dev, const int32_t* seabed_dev, int seabed_pad,
                   int overlap, int ping_start, int Pc, int R, const int32_t* cls, int K, void* out_dev, void* stream);
+
+/* ---- fp32 VALIDATION mode of the eval forward (models/unet.py:327-343 + pipeline.py:218): an independent plain-fp32
+ * CUDA-core implementation reading the fp32 parameters directly (no packing, no tensor cores, no bf16).  ~50x slower
+ * than crimac_forward_infer; for parity checks at 1e-4, not for production.  Stateless: the caller passes a scratch
+ * buffer of crimac_fp32_workspace_bytes(cfg, nb).  cfg->max_batch and cfg->train are ignored. */
+int crimac_fp32_workspace_bytes(const crimac_config* cfg, int nb, size_t* bytes);
+int crimac_forward_infer_fp32(const crimac_config* cfg, const void* const* state, const float* x_dev, int nb,
+                              float* out_dev, int softmax, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- measurement aids (bench.py): launch counter and per-launch CUDA-event timing of the network-level calls */
 unsigned long long crimac_launch_count(void);      /* kernels launched by this process through the library so far */

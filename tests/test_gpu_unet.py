@@ -116,6 +116,32 @@ def test_inference_probabilities_vs_fp32_oracle(M, B, H, W, in_ch):
     assert agree >= 0.99
 
 
+@pytest.mark.parametrize("depth,B,H,W,in_ch", [(5, 2, 128, 128, 4), (3, 2, 40, 72, 6)])
+def test_fp32_validation_mode_matches_oracle_to_1e4(M, depth, B, H, W, in_ch):
+    """north_star: per-pixel class probabilities within 1e-4 in an fp32 validation mode.  forward_fp32 is an independent
+    plain-fp32 CUDA implementation (no bf16, no tensor cores, unfolded BatchNorm) of the same eval forward."""
+    torch.manual_seed(0)
+    m = M.UNet_Baseline(3, in_ch, depth=depth)
+    x = O.synthetic_echogram(B, in_ch, H, W, seed=2)
+    _populate_bn(m, x)
+    m = m.to(dev).eval()
+    x = x.to(dev)
+    with torch.no_grad():
+        ref_logits = O.unet_forward(_state(m), x)
+        ref = O.softmax_probs(ref_logits)
+        got_logits = m.forward_fp32(x)
+        got = m.forward_fp32(x, softmax=True)
+        fast = m.predict_proba(x)
+    dp = (got - ref).abs().max().item()
+    dl = (got_logits - ref_logits).abs().max().item()
+    agree = (got.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"fp32 validation mode: max|dp|={dp:.2e} max|dlogit|={dl:.2e} argmax agreement {agree:.6f}; bf16 path vs fp32 mode max|dp|={(fast - got).abs().max().item():.4f}")
+    assert dp <= 1e-4
+    assert dl <= 1e-3
+    assert agree >= 0.999
+    assert (fast - got).abs().max().item() <= PROB_TOL      # the production path against the validation mode
+
+
 def test_inference_is_per_patch_and_deterministic(M):
     torch.manual_seed(1)
     m = M.UNet_Baseline(3, 4).to(dev).eval()
