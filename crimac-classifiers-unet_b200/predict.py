@@ -45,6 +45,63 @@ def preload_window(grid, n_pings_total, pw):
     return max(0, int(grid[0, 1]) - pw // 2), min(n_pings_total, int(grid[-1, 1]) + pw // 2)
 
 
+@torch.no_grad()
+def predict_host_batches(model, batches, classes=(1, 2)):
+    """Class probabilities for a stream of HOST batches (pin them for full speed): yields, per batch, a pinned fp16 host
+    tensor (N, len(classes), H, W) - the two classes save_predict.py keeps (:43-65).  Host->device copy of batch i+1,
+    the forward of batch i and the device->host copy of batch i-1 overlap (copy stream + two buffers each way); the
+    reference does the three steps one after the other (pipeline.py:208-218, save_predict.py:196)."""
+    dev = next(model.parameters()).device
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    xin, ready, freed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+    dout, hout, done, drained = [None, None], [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+    cls = list(classes)
+
+    def upload(slot, xh):
+        if xin[slot] is None or xin[slot].shape != xh.shape:
+            xin[slot] = torch.empty(xh.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(copy_in):
+            if freed[slot] is not None:
+                copy_in.wait_event(freed[slot])
+            xin[slot].copy_(xh, non_blocking=True)
+            ready[slot].record(copy_in)
+
+    it = iter(batches)
+    nxt = next(it, None)
+    if nxt is None:
+        return
+    upload(0, nxt)
+    i, pending = 0, None
+    while nxt is not None:
+        slot = i & 1
+        nxt = next(it, None)
+        if nxt is not None:
+            upload(slot ^ 1, nxt)
+        main.wait_event(ready[slot])
+        if drained[slot] is not None:
+            main.wait_event(drained[slot])            # the D2H copy that last read dout[slot] has finished
+        probs = model.predict_proba(xin[slot])
+        dout[slot] = probs[:, cls].half()
+        freed[slot] = torch.cuda.Event()
+        freed[slot].record(main)
+        done[slot].record(main)
+        if hout[slot] is None or hout[slot].shape != dout[slot].shape:
+            hout[slot] = torch.empty(dout[slot].shape, dtype=torch.float16).pin_memory()
+        with torch.cuda.stream(copy_out):
+            copy_out.wait_event(done[slot])
+            hout[slot].copy_(dout[slot], non_blocking=True)
+            drained[slot] = torch.cuda.Event()
+            drained[slot].record(copy_out)
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+        pending = (hout[slot], drained[slot])
+        i += 1
+    pending[1].synchronize()
+    yield pending[0]
+
+
 class SurveyPredictor:
     def __init__(self, model, patch_hw=(256, 256), overlap=20, preload_n_pings=20000, batch_size=32, classes=(1, 2),
                  seabed_pad=10):

@@ -48,6 +48,45 @@ class Trainer:
             for b in self.model.buffers():
                 dist.broadcast(b, src)
 
+    def fit_host(self, batches):
+        """Runs one optimisation step per (x, labels) pair of HOST tensors (pin them for full speed) and yields each
+        step's loss as a 0-dim device tensor.  The host->device copy of batch i+1 runs on a copy stream while batch i
+        is computed (two device buffers), which is what a DataLoader-fed loop (pipeline.py:161-178) needs to keep the
+        GPU busy: the reference copies synchronously (`.to(device)`, pipeline.py:163-164)."""
+        dev = self.flat_params.device
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        bufs, ready, freed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+
+        def upload(slot, xh, yh):
+            if bufs[slot] is None or bufs[slot][0].shape != xh.shape:
+                bufs[slot] = (torch.empty(xh.shape, dtype=torch.float32, device=dev),
+                              torch.empty(yh.shape, dtype=torch.int64, device=dev))
+            with torch.cuda.stream(copy_stream):
+                if freed[slot] is not None:
+                    copy_stream.wait_event(freed[slot])   # the step that last read this buffer has finished
+                bufs[slot][0].copy_(xh, non_blocking=True)
+                bufs[slot][1].copy_(yh, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        upload(0, *nxt)
+        i = 0
+        while nxt is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(slot ^ 1, *nxt)
+            main.wait_event(ready[slot])
+            loss = self.step(bufs[slot][0], bufs[slot][1])
+            freed[slot] = torch.cuda.Event()
+            freed[slot].record(main)
+            yield loss
+            i += 1
+
     def step(self, x, labels):
         """One optimisation step on device tensors; returns the replica's loss as a 0-dim device tensor."""
         loss = self.model.train_step_fused(x, labels, self.class_weight)
