@@ -57,7 +57,7 @@ struct ConvCfg {
                                                        2 * TILE_M * CRIMAC_MAX_CLASSES * 4 /*partial-logit exchange*/)
                                                     : 0;
   static constexpr int AUX_BYTES = 512 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
-                                   2 * MAX_STAT_CH * 4 + HEAD_BYTES;
+                                   2 * MAX_STAT_CH * 4 + HEAD_BYTES + 4 * BLOCK_N * 4 /*EPI_BNRED mask scale/shift x2*/;
   static constexpr int SMEM_BYTES = OPERAND_BYTES + AUX_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
   static_assert(9 % TPS == 0, "taps per weight stage must divide 9");
@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   float* s_acc = s_red + 8 * BLOCK_N;                     // [2][n_total] CTA-lifetime channel sums
   float* s_head = s_acc + 2 * Cfg::MAX_STAT_CH;           // [ncls][64] + [ncls]           (BLOCK_N == 64 only)
   float* s_hx = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2 acc stages][TILE_M][classes]
+  float* s_bnr = reinterpret_cast<float*>(aux + Cfg::AUX_BYTES - 4 * BLOCK_N * 4);  // [2][mask scale | mask shift]
+  constexpr bool HAS_STATS = (EPI == EPI_STATS || EPI == EPI_BNRED);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
     ptx::tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (EPI == EPI_STATS && warp >= 4) {
+  if (HAS_STATS && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 2 * p.n_tiles * BLOCK_N; i += EPI_THREADS) s_acc[i] = 0.f;
   }
   if (EPI == EPI_HEAD && warp >= 4) {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
 
   // Only the variant that keeps 128 BatchNorm accumulators per epilogue thread re-allocates registers between the
   // warpgroups (128 x 72 + 256 x 216 = 64512 <= 65536); measured: the others run faster with the static 168.
-  constexpr bool REALLOC = (EPI == EPI_STATS) && (BLOCK_N == 128);
+  constexpr bool REALLOC = HAS_STATS && (BLOCK_N == 128);
   if (warp < 4) {
   if constexpr (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
     // chunks per warp; with at most two the statistics of all of them fit in registers (the epilogue warps raise their
     // register allowance with setmaxnreg for this)
     constexpr int CPW = NCHUNK / EPI_COLGROUPS;
-    constexpr int RUN_CPW = (EPI == EPI_STATS && CPW <= 2) ? CPW : 0;
+    constexpr int RUN_CPW = (HAS_STATS && CPW <= 2) ? CPW : 0;
     const bool run_stats = (RUN_CPW > 0) && fixed_n;
     float r1[RUN_CPW > 0 ? RUN_CPW : 1][32], r2[RUN_CPW > 0 ? RUN_CPW : 1][32];
     if (RUN_CPW > 0) {
@@ -399,6 +401,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         sc[i] = p.scale ? p.scale[n0 + i] : 1.0f;
         // ConvTranspose scatter: N index = (ky,kx,co) and the bias is per co
         sh[i] = p.shift ? p.shift[p.convt_cout > 0 ? (n0 + i) % p.convt_cout : n0 + i] : 0.0f;
+        if (EPI == EPI_BNRED) {
+          s_bnr[as * 2 * BLOCK_N + i] = p.bnr_scale[n0 + i];
+          s_bnr[as * 2 * BLOCK_N + BLOCK_N + i] = p.bnr_shift[n0 + i];
+        }
       }
     };
     if (fixed_n) {
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       if (!fixed_n) {
         load_affine(as, n0);
         epi_bar();
-      } else if (EPI == EPI_STATS && !run_stats) {
+      } else if (HAS_STATS && !run_stats) {
         epi_bar();  // the previous tile's s_red rows have been consumed
       }
       const float* sc = s_affine + (fixed_n ? 0 : as) * 2 * BLOCK_N;
@@ -439,6 +445,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       }
 
       auto chunk_body = [&](const int chunk, float (&ra)[32], float (&rb)[32]) {
+        uint4 rw[4] = {};
+        if (EPI == EPI_BNRED && valid) {
+          // raw output of the layer whose activation gradient this tile is: issued before the TMEM load so that the
+          // global-memory latency overlaps it
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              p.bnr_raw + ((static_cast<long>(img) * p.H + y) * p.W + x) * p.bnr_pitch + n0 + chunk * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rw[i] = __ldg(rp + i);
+        }
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + chunk * 32, v);
         ptx::tmem_ld_wait();
@@ -457,6 +472,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         if (EPI != EPI_STATS && p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (EPI == EPI_BNRED) {
+          // ReLU backward of the producing layer: keep the gradient where its BatchNorm output was positive
+          const uint32_t* rwu = reinterpret_cast<const uint32_t*>(rw);
+          const float* bs = s_bnr + (fixed_n ? 0 : as) * 2 * BLOCK_N + chunk * 32;
+          const float* bh = bs + BLOCK_N;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 r = unpack_bf16x2(rwu[j]);
+            f[2 * j] = fmaf(r.x, bs[2 * j], bh[2 * j]) > 0.f ? f[2 * j] : 0.f;
+            f[2 * j + 1] = fmaf(r.y, bs[2 * j + 1], bh[2 * j + 1]) > 0.f ? f[2 * j + 1] : 0.f;
+          }
         }
         uint32_t pk[16];
 #pragma unroll
@@ -507,26 +534,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
           }
         }
 
-        if (EPI == EPI_STATS) {
-          // statistics of the bf16-rounded values the BN-apply pass will read back
+        if (HAS_STATS) {
+          // EPI_STATS: sum, sum of squares of the bf16-rounded values the BN-apply pass will read back.
+          // EPI_BNRED: sum g, sum g*raw of the rounded masked gradient the BN-backward apply pass will read back.
+          const uint32_t* rwu = reinterpret_cast<const uint32_t*>(rw);
           if (RUN_CPW > 0 && run_stats) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
+              const float2 o = (EPI == EPI_BNRED) ? unpack_bf16x2(rwu[j]) : t;
               ra[2 * j] += t.x;
               ra[2 * j + 1] += t.y;
-              rb[2 * j] = fmaf(t.x, t.x, rb[2 * j]);
-              rb[2 * j + 1] = fmaf(t.y, t.y, rb[2 * j + 1]);
+              rb[2 * j] = fmaf(t.x, o.x, rb[2 * j]);
+              rb[2 * j + 1] = fmaf(t.y, o.y, rb[2 * j + 1]);
             }
           } else {
             float s1[32], s2[32];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
+              const float2 o = (EPI == EPI_BNRED) ? unpack_bf16x2(rwu[j]) : t;
               s1[2 * j] = t.x;
               s1[2 * j + 1] = t.y;
-              s2[2 * j] = t.x * t.x;
-              s2[2 * j + 1] = t.y * t.y;
+              s2[2 * j] = t.x * o.x;
+              s2[2 * j + 1] = t.y * o.y;
             }
             xpose_reduce(s1, lane);
             xpose_reduce(s2, lane);
@@ -547,7 +578,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[as]);
 
-      if (EPI == EPI_STATS && !run_stats) {
+      if (HAS_STATS && !run_stats) {
         epi_bar();
         const int n_total = p.n_tiles * BLOCK_N;
         for (int c = e; c < BLOCK_N; c += EPI_THREADS) {
@@ -600,7 +631,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       }
     }
 
-    if (EPI == EPI_STATS) {
+    if (HAS_STATS) {
       // one partial row per CTA: stats[blockIdx.x][2][n_total]; bn_finalize sums gridDim.x rows
       const int n_total = p.n_tiles * BLOCK_N;
       const int n2 = 2 * n_total;
@@ -648,7 +679,7 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (EPI == EPI_STATS && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
+  if ((EPI == EPI_STATS || EPI == EPI_BNRED) && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (HALO && BLOCK_N != 256) {
     // resident weights when the whole matrix fits beside two or three halo tiles
@@ -669,7 +700,8 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
 // BLOCK_N in {64,128,256}; p.n_tiles*BLOCK_N == N_total must hold.
 cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num_sms, cudaStream_t stream) {
   if (p.halo && p.taps != 9) return cudaErrorInvalidValue;
-  if (p.b_mn && (epi != EPI_STORE || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
+  if (p.b_mn && ((epi != EPI_STORE && epi != EPI_BNRED) || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
+  if (epi == EPI_BNRED && (!p.b_mn || !p.bnr_raw || !p.bnr_scale || !p.bnr_shift || !p.stats)) return cudaErrorInvalidValue;
 #define CASE(BN, EP)                                                               \
   if (block_n == BN && epi == EP && !p.b_mn)                                       \
     return p.halo ? launch_one<BN, EP, true, false>(p, num_sms, stream) : launch_one<BN, EP, false, false>(p, num_sms, stream);
@@ -677,11 +709,12 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num
   CASE(64, EPI_STATS) CASE(128, EPI_STATS) CASE(256, EPI_STATS)
   CASE(64, EPI_HEAD)
 #undef CASE
-#define CASE_MN(BN)                                                                \
-  if (block_n == BN && p.b_mn)                                                     \
-    return p.halo ? launch_one<BN, EPI_STORE, true, true>(p, num_sms, stream)      \
-                  : launch_one<BN, EPI_STORE, false, true>(p, num_sms, stream);
-  CASE_MN(64) CASE_MN(128) CASE_MN(256)
+#define CASE_MN(BN, EP)                                                            \
+  if (block_n == BN && p.b_mn && epi == EP)                                        \
+    return p.halo ? launch_one<BN, EP, true, true>(p, num_sms, stream)             \
+                  : launch_one<BN, EP, false, true>(p, num_sms, stream);
+  CASE_MN(64, EPI_STORE) CASE_MN(128, EPI_STORE) CASE_MN(256, EPI_STORE)
+  CASE_MN(64, EPI_BNRED) CASE_MN(128, EPI_BNRED) CASE_MN(256, EPI_BNRED)
 #undef CASE_MN
   return cudaErrorInvalidValue;
 }

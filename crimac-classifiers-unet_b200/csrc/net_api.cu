@@ -774,7 +774,14 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   c->wg_dirty = true;  // cleared by the unpack launch at the end
 
   // BN/ReLU backward of layer idx (dA in GA) -> dRaw in GR; then wgrad (+ dgrad into L.gin)
-  auto conv_bwd = [&](int idx) -> int {
+  // pre_rows: BN-backward sums already produced (conv_igemm EPI_BNRED) by the kernel that wrote this layer's dA;
+  // target: the layer whose activation gradient THIS layer's backward-data produces (or -1); returns its rows in *out_rows
+  // Measured on B200 (batch 32): fusing saves 0.59 ms of bn_bwd_reduce but costs 0.51 ms in the dgrad kernels, whose
+  // epilogues have no slack on the narrow layers (the extra raw loads + mask + sums make them the bottleneck) - a wash,
+  // so it is opt-in (CRIMAC_BNRED=1) and the stand-alone HBM-bound reduce kernel stays the default.
+  static const bool fuse_bnred = getenv("CRIMAC_BNRED") != nullptr;
+  auto conv_bwd = [&](int idx, int pre_rows, int target, int* out_rows) -> int {
+    if (out_rows) *out_rows = 0;
     Conv3& L = c->conv[idx];
     const int H = level_h(c, L.level), W = level_w(c, L.level);
     View da{c->GA, nb, H, W, L.cout, L.cout};
@@ -786,15 +793,27 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 4);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
                                       grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2,
-                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, st));
+                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, pre_rows, st));
     }
     if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_draw[L.gr_idx], st));
     // backward-data first (critical path, issued first so that it is scheduled first) ...
     if (!L.first && L.gin.ptr != nullptr) {
       ConvParams p = L.dgrad;
       set_batch(p, nb);
+      int epi = EPI_STORE;
+      if (fuse_bnred && target >= 0) {
+        // the output is the activation gradient of `target`: mask it and emit that layer's BN-backward sums here
+        const Conv3& T = c->conv[target];
+        p.bnr_raw = T.raw.ptr;
+        p.bnr_pitch = T.raw.pitch;
+        p.bnr_scale = T.scale;
+        p.bnr_shift = T.shift;
+        p.stats = c->red_partials;
+        epi = EPI_BNRED;
+        if (out_rows) *out_rows = conv_grid(p.total_tiles, sms);
+      }
       ProfScope ps("conv3x3_dgrad", igemm_flops_n(p, L.cin), px * 2.0 * (L.cin + L.cout), st);
-      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_bwd, EPI_STORE, sms, st));
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_bwd, epi, sms, st));
     }
     // ... then the weight gradient: tensor-bound and off the critical path -> side stream, where it overlaps the
     // HBM-bound BatchNorm / pooling backward kernels of the following layers (dRaw is double-buffered for this)
@@ -825,9 +844,11 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
                                       grads[c->g_head_b], 0, st));
   }
   // decoder, last block first
+  int rows = 0;  // BN-backward partial rows the previous kernel left for the layer processed next
   for (int j = D - 2; j >= 0; --j) {
-    if ((rc = conv_bwd(c->dec2[j]))) return rc;
-    if ((rc = conv_bwd(c->dec1[j]))) return rc;  // dgrad wrote dCat_j
+    int r1 = 0;
+    if ((rc = conv_bwd(c->dec2[j], rows, c->dec1[j], &r1))) return rc;   // dgrad -> dA of dec1[j]
+    if ((rc = conv_bwd(c->dec1[j], r1, -1, nullptr))) return rc;         // dgrad wrote dCat_j
     ConvT& U = c->up[j];
     {
       ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, st, 2);
@@ -837,8 +858,21 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     {
       ConvParams p = U.dgrad;
       set_batch(p, nb);
+      int epi = EPI_STORE;
+      rows = 0;
+      if (fuse_bnred) {
+        // -> GA = activation gradient of the block below (dec2[j-1], or the deepest encoder conv)
+        const Conv3& T = c->conv[j > 0 ? c->dec2[j - 1] : c->enc2[D - 1]];
+        p.bnr_raw = T.raw.ptr;
+        p.bnr_pitch = T.raw.pitch;
+        p.bnr_scale = T.scale;
+        p.bnr_shift = T.shift;
+        p.stats = c->red_partials;
+        epi = EPI_BNRED;
+        rows = conv_grid(p.total_tiles, sms);
+      }
       ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
-      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));  // -> GA (grad of the convT input)
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, epi, sms, st));
     }
     if (c->overlap) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->side, c->ev_cat, 0));
     if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, c->overlap ? c->side : st))) return rc;
@@ -853,9 +887,12 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       View dact{c->GA, nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
       ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 3.25, st);
       CRIMAC_CHECK_CUDA(launch_pool_bwd_add(with_batch(L2.act, nb), dpool, dskip, dact, st));
+      rows = 0;
     }
-    if ((rc = conv_bwd(c->enc2[l]))) return rc;
-    if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
+    int r1 = 0;
+    if ((rc = conv_bwd(c->enc2[l], rows, c->enc1[l], &r1))) return rc;  // dgrad -> dA of enc1[l]
+    if ((rc = conv_bwd(c->enc1[l], r1, -1, nullptr))) return rc;        // dgrad wrote GP (grad of the pooled input), none for l == 0
+    rows = 0;
   }
   if (c->overlap) {
     CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_join, c->side));
