@@ -90,6 +90,7 @@ struct WgradHaloParams {
   int k_tiles_total;
   int splits;
   int s_tiles, f_tiles;  // Cs/64, Cf/64
+  int nf;                // 64: nine taps per CTA; 128: eight taps with 128-wide X tiles (centre tap done separately)
   float* dw;             // scratch [9][Cs][Cf] fp32
 };
 

@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
                                                                    double count, float* out0, float* out1,
                                                                    int accumulate, float* c1, float* c2,
                                                                    const float* gscale, const float* mean,
-                                                                   const float* invstd) {
+                                                                   const float* invstd, float* zero_out) {
   // block = 8 channels x 32 part-lanes (short dependent load chains)
   __shared__ double sh[NQ][32][8];
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
     if (NQ == 2 && mean != nullptr)
       a[NQ - 1] = static_cast<double>(invstd[c]) * (a[NQ - 1] - static_cast<double>(mean[c]) * a[0]);
     out0[c] = accumulate ? out0[c] + static_cast<float>(a[0]) : static_cast<float>(a[0]);
+    if (zero_out != nullptr && !accumulate) zero_out[c] = 0.f;
     if (NQ == 2) {
       out1[c] = accumulate ? out1[c] + static_cast<float>(a[NQ - 1]) : static_cast<float>(a[NQ - 1]);
       c1[c] = static_cast<float>(a[0] / count);
@@ -774,14 +775,15 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
   }
 }
 
-// phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) = A*g + B*raw + K per channel -> bf16; partial = sum dRaw (= the
-// conv-bias gradient)
+// phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) = A*g + B*raw + K per channel -> bf16.
+// (The conv-bias gradient sum(dRaw) is EXACTLY zero in exact arithmetic - train-mode BatchNorm removes any bias - and the
+// reference's value is pure cancellation noise ~1e-9; it is written as 0 by the finalize kernel instead of being summed.)
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View raw, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd,
                                                               const float* __restrict__ c1, const float* __restrict__ c2,
-                                                              const float* gscale, View draw, float* partials) {
+                                                              const float* gscale, View draw) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
@@ -802,9 +804,6 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View ra
       ck[j] = -sc[j] * k1[j] - cb[j] * mu[j];
     }
   }
-  float acc[1][8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   const long stride = static_cast<long>(gridDim.x) * ppb;
   constexpr int U = 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
@@ -831,14 +830,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View ra
           o[2 * h + 1] = fmaf(ca[2 * h + 1], g1, fmaf(cb[2 * h + 1], r.y, ck[2 * h + 1]));
         }
         store8(draw.ptr + p * draw.pitch + g * 8, o);
-        // conv-bias gradient = sum of dRaw: exactly zero in exact arithmetic (BN removes the bias); summed from the
-        // fp32 values so that, like the reference, only cancellation noise is left
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] += o[j];
       }
     }
   }
-  block_channel_sums<1>(acc, C, g, pl, ppb, partials);
 }
 
 // plain per-channel sum of a view (ConvTranspose bias gradient)
@@ -1080,7 +1074,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* p
 #define FW(C)                                                                                       \
   if (cin == C) {                                                                                   \
     first_conv_wgrad_kernel<C><<<grid, 256, 0, st>>>(x, draw, draw.N, draw.H, draw.W, partials);    \
-    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr, nullptr, nullptr, nullptr); \
+    partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
   FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
@@ -1184,11 +1178,9 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   if (pre_rows <= 0)
     bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
   partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, pre_rows > 0 ? pre_rows : grid, C, count, dbeta,
-                                                                dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd);
-  bn_bwd_apply_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C,
-                                                                  gscale, draw, partials);
-  partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, dbias, nullptr, accumulate, nullptr,
-                                                                nullptr, nullptr, nullptr, nullptr);
+                                                                dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd,
+                                                                dbias);
+  bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
   return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
@@ -1198,7 +1190,7 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
   const int ppb = 256 / (C / 8);
   view_colsum_kernel<<<grid, 256, ppb * C * sizeof(float), st>>>(v, partials);
   partial_sum_finalize_kernel<1><<<(C + 7) / 8, 256, 0, st>>>(partials, grid, C, 1.0, out, nullptr, accumulate, nullptr,
-                                                                nullptr, nullptr, nullptr, nullptr);
+                                                                nullptr, nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st) {

@@ -45,6 +45,7 @@ struct Conv3 {
   ConvParams fwd{}, dgrad{};
   WgradHaloParams wg{};   // all-taps halo kernel (wide, shallow layers)
   WgradParams wg_tap{};   // one-tap-per-CTA kernel (deep layers: few pixels, many channels)
+  WgradParams wg_center{};  // centre tap only (taps = 1): completes the eight-tap 128-wide halo variant
   bool wg_use_halo = true;
   float* wg_scratch = nullptr;  // [9][cout][cin] fp32, zero between steps
   int gr_idx = 0;               // which of the two dRaw buffers this layer's BatchNorm backward writes
@@ -410,6 +411,20 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         // measured on B200 (profiles/): the 64x64-channel halo tiles win up to Cout*Cin = 256*128, beyond that the
         // 128 x 256 one-tap tiles re-read fewer operand bytes per FLOP
         L.wg_use_halo = static_cast<long>(L.cout) * L.cin <= 256L * 128L;
+        // Cin a multiple of 128: the eight-tap variant with 128-wide X tiles (2/3 of the shared-memory traffic per FLOP)
+        // plus the centre tap as a plain GEMM into the same scratch.  Measured on B200: the eight-tap kernel runs at
+        // 1235 TFLOP/s instead of 967, but the centre-tap GEMM re-streams both operands for 1/9 of the FLOPs and is
+        // L2-bound (255 TFLOP/s): 0.357 ms instead of 0.320 ms for the 128->64 layer.  Opt-in (CRIMAC_WG128=1) until the
+        // centre tap shares the operand loads (cluster multicast).
+        static const bool nf128 = getenv("CRIMAC_WG128") != nullptr;
+        w.nf = (L.wg_use_halo && L.cin % 128 == 0 && nf128) ? 128 : 64;
+        if (w.nf == 128) {
+          WgradParams& wc = L.wg_center;
+          wgeom(wc, H, W, L.cout, L.cin, L.bn_wg, 1, 0);
+          wc.dw = L.wg_scratch ? L.wg_scratch + static_cast<size_t>(4) * L.cout * L.cin : nullptr;
+          if ((rc = make_act_map(&wc.a_map, gr, 4))) return rc;
+          if ((rc = make_act_map(&wc.b_map[0], L.in, 4))) return rc;
+        }
         WgradParams& wt = L.wg_tap;
         wgeom(wt, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
         wt.dw = L.wg_scratch;
@@ -471,7 +486,7 @@ void set_batch(WgradParams& p, int nb) {
 void set_batch(WgradHaloParams& p, int nb) {
   p.NB = nb;
   p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
-  const int tiles = p.s_tiles * p.f_tiles;
+  const int tiles = p.s_tiles * (p.nf == 128 ? p.Cf / 128 : p.f_tiles);
   int splits = (2 * device_num_sms() + tiles - 1) / tiles;
   if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
   if (splits < 1) splits = 1;
@@ -514,7 +529,7 @@ int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, cudaStream_t st) {
 
 int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, cudaStream_t st) {
   set_batch(w, nb);
-  ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * 9, 0, st);
+  ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * (w.nf == 128 ? 8 : 9), 0, st);
   CRIMAC_CHECK_CUDA(launch_wgrad_halo(w, st));
   return 0;
 }
@@ -790,7 +805,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     // the weight gradient that last read this dRaw buffer (two layers ago) must have finished
     if (c->overlap) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_wg[L.gr_idx], 0));
     {
-      ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 4);
+      ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 3);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
                                       grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2,
                                       (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, pre_rows, st));
@@ -828,6 +843,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     } else {
       int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, ws) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, ws);
       if (r) return r;
+      if (L.wg_use_halo && L.wg.nf == 128 && (r = wgrad_run(c, L.wg_center, L.bn_wg, nb, ws))) return r;
     }
     if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_wg[L.gr_idx], c->side));
     return 0;

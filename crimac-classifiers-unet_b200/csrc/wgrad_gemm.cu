@@ -212,25 +212,40 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ scratch, float* __
 constexpr int WH_HALO_W = 18, WH_HALO_H = 6;
 constexpr int WH_HALO_BYTES = WH_HALO_W * WH_HALO_H * 128;  // 13824
 constexpr int WH_HALO_SLOT = 14336;                          // padded to a multiple of 1024
-constexpr int WH_FIXED_BYTES = 64 * 128;                     // 8192
-constexpr int WH_STAGE = WH_HALO_SLOT + WH_FIXED_BYTES;
-constexpr int WH_STAGES = 8;
-constexpr int WH_SMEM = WH_STAGES * WH_STAGE + 256 + 1024;
+constexpr int WH_FIXED_BYTES = 64 * 128;                     // 8192 per 64-channel box of the fixed operand
 constexpr int WH_TMEM_COLS = 512;
 
+// NF = channels of the fixed operand (X) per CTA = MMA N.
+//   NF = 64 : five accumulators (tap pairs (8,7) (6,5) (4,3) (2,1) (1,0); the lower half of the last repeats tap 1 and is
+//             discarded) - 20 MMAs of 128x64x16 per k-step; bound by shared-memory bandwidth (6 KB per 32-cycle MMA).
+//   NF = 128: four accumulators x 128 columns = all of TMEM (tap pairs (8,7) (6,5) (3,2) (1,0)); the centre tap 4 is a
+//             plain GEMM done by wgrad_gemm_kernel (taps = 1).  16 MMAs of 128x128x16 per k-step: 8 KB per 64-cycle MMA,
+//             i.e. the operand traffic per FLOP is 2/3 of the NF = 64 variant and no MMA row is wasted.
+template <int NF>
+struct WhCfg {
+  static constexpr int GROUPS = (NF == 64) ? 5 : 4;
+  static constexpr int STAGE = WH_HALO_SLOT + (NF / 64) * WH_FIXED_BYTES;
+  static constexpr int STAGES = (NF == 64) ? 8 : 6;
+  static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
+};
+
+template <int NF>
 __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+  using Cfg = WhCfg<NF>;
+  constexpr int G = Cfg::GROUPS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* aux = smem + WH_STAGES * WH_STAGE;
+  uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
-  uint64_t* empty_bar = full_bar + WH_STAGES;
-  uint64_t* acc_bar = empty_bar + WH_STAGES;
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* acc_bar = empty_bar + Cfg::STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int f_tile = blockIdx.x % p.f_tiles;
-  const int s_tile = blockIdx.x / p.f_tiles;
+  const int f_tiles = p.Cf / NF;
+  const int f_tile = blockIdx.x % f_tiles;
+  const int s_tile = blockIdx.x / f_tiles;
   const int split = blockIdx.y;
   const int kt_per = (p.k_tiles_total + p.splits - 1) / p.splits;
   const int kt_begin = split * kt_per;
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
     ptx::prefetch_tmap(&p.f_map);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < WH_STAGES; ++s) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
@@ -259,8 +274,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   // tap pairs (first -> MMA rows 0..63, second -> rows 64..127); halo row offsets grow from first to second
-  constexpr int PA[5] = {8, 6, 4, 2, 1};
-  constexpr int PB[5] = {7, 5, 3, 1, 0};
+  constexpr int PA5[5] = {8, 6, 4, 2, 1}, PB5[5] = {7, 5, 3, 1, 0};
+  constexpr int PA4[4] = {8, 6, 3, 1}, PB4[4] = {7, 5, 2, 0};
 
   if (ksteps > 0) {
     if (warp == 0) {
@@ -275,11 +290,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
         const int img = u / p.tiles_y;
         const int x0 = tx * 16, y0 = ty * 4;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sh = smem + stage * WH_STAGE;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], WH_HALO_BYTES + WH_FIXED_BYTES);
+        uint8_t* sh = smem + stage * Cfg::STAGE;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], WH_HALO_BYTES + (NF / 64) * WH_FIXED_BYTES);
         ptx::tma_load_4d(sh, &p.s_map, &full_bar[stage], s_tile * 64, x0 - 1, y0 - 1, img);
-        ptx::tma_load_4d(sh + WH_HALO_SLOT, &p.f_map, &full_bar[stage], f_tile * 64, x0, y0, img);
-        if (++stage == WH_STAGES) {
+#pragma unroll
+        for (int b = 0; b < NF / 64; ++b)
+          ptx::tma_load_4d(sh + WH_HALO_SLOT + b * WH_FIXED_BYTES, &p.f_map, &full_bar[stage], f_tile * NF + b * 64, x0,
+                           y0, img);
+        if (++stage == Cfg::STAGES) {
           stage = 0;
           phase ^= 1u;
         }
@@ -287,14 +305,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
       }
     } else if (warp == 1) {
       if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc = ptx::make_idesc_bf16(128, NF, 1, 1);
       // per pair: descriptor (without start address) and the byte offset of the first tap's view
-      uint64_t dtmpl[5];
-      uint32_t off16[5];
+      uint64_t dtmpl[G];
+      uint32_t off16[G];
 #pragma unroll
-      for (int g = 0; g < 5; ++g) {
-        const int oa = ((2 - PA[g] / 3) * WH_HALO_W + (2 - PA[g] % 3)) * 128;
-        const int ob = ((2 - PB[g] / 3) * WH_HALO_W + (2 - PB[g] % 3)) * 128;
+      for (int g = 0; g < G; ++g) {
+        const int ta = (NF == 64) ? PA5[g] : PA4[g], tb = (NF == 64) ? PB5[g] : PB4[g];
+        const int oa = ((2 - ta / 3) * WH_HALO_W + (2 - ta % 3)) * 128;
+        const int ob = ((2 - tb / 3) * WH_HALO_W + (2 - tb % 3)) * 128;
         dtmpl[g] = ptx::make_smem_desc(0, ob - oa, 1024);
         off16[g] = oa >> 4;
       }
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
       for (int ks = 0; ks < ksteps; ++ks) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t sh = ptx::smem_u32(smem + stage * WH_STAGE);
+        const uint32_t sh = ptx::smem_u32(smem + stage * Cfg::STAGE);
         const uint32_t sh16 = sh >> 4;
         const uint64_t bdesc0 = ptx::make_smem_desc(sh + WH_HALO_SLOT, WH_FIXED_BYTES, 1024);
 #pragma unroll
@@ -311,11 +330,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(r * 128);          // 16 pixels * 128 B = 2048 B
           const uint32_t row16 = sh16 + static_cast<uint32_t>(r * WH_HALO_W * 8);  // halo row pitch 18 * 128 B
 #pragma unroll
-          for (int g = 0; g < 5; ++g)
-            ptx::umma_bf16(tmem_base + g * 64, dtmpl[g] + row16 + off16[g], bdesc, idesc, (ks | r) != 0);
+          for (int g = 0; g < G; ++g)
+            ptx::umma_bf16(tmem_base + g * NF, dtmpl[g] + row16 + off16[g], bdesc, idesc, (ks | r) != 0);
         }
         ptx::umma_commit(&empty_bar[stage]);
-        if (++stage == WH_STAGES) {
+        if (++stage == Cfg::STAGES) {
           stage = 0;
           phase ^= 1u;
         }
@@ -330,14 +349,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
       ptx::mbar_wait(acc_bar, 0);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < 5; ++g) {
-        const int tap = half ? PB[g] : PA[g];
-        const bool live = !(g == 4 && half == 0);  // lower half of the last group repeats tap 1
-        float* row = p.dw + (static_cast<long>(tap) * p.Cs + co) * p.Cf + f_tile * 64;
+      for (int g = 0; g < G; ++g) {
+        const int tap = (NF == 64) ? (half ? PB5[g] : PA5[g]) : (half ? PB4[g] : PA4[g]);
+        const bool live = !(NF == 64 && g == 4 && half == 0);  // lower half of the fifth group repeats tap 1
+        float* row = p.dw + (static_cast<long>(tap) * p.Cs + co) * p.Cf + f_tile * NF;
 #pragma unroll 1
-        for (int chunk = 0; chunk < 2; ++chunk) {
+        for (int chunk = 0; chunk < NF / 32; ++chunk) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 64 + chunk * 32, v);
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * NF + chunk * 32, v);
           ptx::tmem_ld_wait();
           if (live) {
             if (p.splits == 1) {
@@ -424,16 +443,26 @@ cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t st
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) {
+namespace {
+template <int NF>
+cudaError_t launch_wh(const WgradHaloParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, WhCfg<NF>::SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid(p.s_tiles * p.f_tiles, p.splits);
-  wgrad_halo_kernel<<<grid, 256, WH_SMEM, stream>>>(p);
+  dim3 grid(p.s_tiles * (p.Cf / NF), p.splits);
+  wgrad_halo_kernel<NF><<<grid, 256, WhCfg<NF>::SMEM, stream>>>(p);
   return cudaGetLastError();
+}
+}  // namespace
+
+// p.nf = 64: all nine taps.  p.nf = 128 (Cf % 128 == 0): eight taps; the caller adds the centre tap with a taps = 1
+// wgrad_gemm launch into scratch + 4*Cs*Cf.
+cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) {
+  if (p.nf == 128) return (p.Cf % 128 == 0) ? launch_wh<128>(p, stream) : cudaErrorInvalidValue;
+  return launch_wh<64>(p, stream);
 }
 
 cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,
