@@ -1036,7 +1036,7 @@ inline int grid_for(long work_items, int threads) {
 // remain for 8 frequencies and as the A/B reference (CRIMAC_FC_CUDACORE=1).
 static bool first_conv_use_tc(int cin) {
   static const bool off = getenv("CRIMAC_FC_CUDACORE") != nullptr;
-  return !off && cin <= 7;
+  return !off && cin <= 8;
 }
 static int first_conv_cc_grid(int NB, int H, int W) {
   const int tiles = NB * ((H + TILE_H - 1) / TILE_H) * ((W + TILE_W - 1) / TILE_W);
@@ -1047,13 +1047,13 @@ int first_conv_grid(int NB, int cin, int H, int W) {
 }
 size_t first_conv_wgrad_partial_floats(int cin) {
   const size_t cc = static_cast<size_t>(first_conv_wgrad_blocks()) * 4 * 64 * cin * 9;
-  const size_t tc = static_cast<size_t>(256) * 128 * 64;  // >= number of SMs partial tiles
+  const size_t tc = static_cast<size_t>(256) * 2 * 128 * 64;  // >= number of SMs x 2 accumulator groups of [128][64]
   return cc > tc ? cc : tc;
 }
-cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
-                              int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st) {
+cudaError_t launch_first_conv(const float* x, bf16* xs, const float* w, const float* scale, const float* shift, int relu,
+                              int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st) {
   if (first_conv_use_tc(cin))
-    return launch_first_conv_tc(x, w, scale, shift, relu, NB, cin, H, W, out, out_pitch, stats, st);
+    return launch_first_conv_tc(x, xs, w, scale, shift, relu, NB, cin, H, W, out, out_pitch, stats, st);
   const int grid = first_conv_cc_grid(NB, H, W);
 #define FC(C)                                                                                                   \
   if (cin == C) {                                                                                               \
@@ -1066,9 +1066,9 @@ cudaError_t launch_first_conv(const float* x, const float* w, const float* scale
 }
 
 int first_conv_wgrad_blocks() { return 148 * 2; }
-cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
-                                    cudaStream_t st) {
-  if (first_conv_use_tc(cin)) return launch_first_conv_wgrad_tc(x, draw, cin, partials, dw, accumulate, st);
+cudaError_t launch_first_conv_wgrad(const float* x, const bf16* xs, View draw, int cin, float* partials, float* dw,
+                                    int accumulate, cudaStream_t st) {
+  if (first_conv_use_tc(cin)) return launch_first_conv_wgrad_tc(xs, draw, cin, partials, dw, accumulate, st);
   const int tiles = draw.N * ((draw.H + TILE_H - 1) / TILE_H) * ((draw.W + TILE_W - 1) / TILE_W);
   const int grid = tiles < first_conv_wgrad_blocks() ? tiles : first_conv_wgrad_blocks();
 #define FW(C)                                                                                       \

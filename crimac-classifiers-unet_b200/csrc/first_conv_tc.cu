@@ -1,200 +1,216 @@
 // First conv of the echogram U-Net (down_convs.0.main.0, reference models/unet.py:76: nn.Conv2d(#frequencies, 64, 3,
-// padding=1)) and its weight gradient on the tensor cores.
+// padding=1)) and its weight gradient on the tensor cores, with the im2col done by TMA.
 //
-// The input is the fp32 NCHW dB echogram (values in [-75, 0]: bf16 alone would lose 0.25-0.5 dB), K = 9*Cin <= 63 is one
-// 64-wide k-block.  Both kernels build the im2col tile [128 pixels][64 k] in shared memory themselves (no TMA: the
-// source is fp32 NCHW) in the 128B-swizzled layout tcgen05.mma reads, as TWO bf16 tiles: hi = bf16(x), lo = bf16(x - hi),
-// i.e. 16 mantissa bits of x.  Forward also splits the weights, D = x_hi*W_hi + x_lo*W_hi + x_hi*W_lo (the dropped
-// x_lo*W_lo term is 2^-16 relative), so the result matches the fp32 CUDA-core kernel it replaces to ~1e-5 relative
-// while running ~4x faster (that kernel was FFMA/LSU bound at 0.5 ms per batch of 32).
+// The input is the fp32 NCHW dB echogram (values in [-75, 0]: bf16 alone would lose 0.25-0.5 dB).  A tiny pre-pass
+// (split_input_kernel) rewrites it ONCE per step as NHWC bf16 pairs  hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits
+// of x) in 16-byte chunks per pixel: one plane [pixel][hi c0..3 | lo c0..3] for <= 4 frequencies (P = 4), else two planes
+// [pixel][hi c0..7], [pixel][lo c0..7] (P = 8).
 //
-//   forward : M = 128 pixels (8 rows x 16 pings), N = 64 channels, K = 3 x 16*ceil(9*Cin/16); epilogue as conv_igemm:
-//             +bias | scale/shift+ReLU -> bf16 NHWC, train-mode BatchNorm statistics kept in registers per CTA.
-//   wgrad   : dW[co][k] = sum_p dRaw[p][co] * im2col(x)[p][k]: M = 128 = (k of x_hi | k of x_lo), N = 64 channels,
-//             K = pixels; A = the same two im2col tiles read MN-major, B = the dRaw tile (TMA box, MN-major); the fp32
-//             accumulator stays in TMEM for the CTA's lifetime, one partial [128][64] per CTA, folded by a finalize.
+// One TMA box {16 pings x 8 elements (256 contiguous bytes), 8 rows} of a plane at a tap-shifted coordinate is then exactly 16 UN-swizzled
+// UMMA core matrices (8 pixels x 16 B, 128 B apart): the nine taps are nine (P = 8: eighteen) boxes, 2 KB apart, and a
+// 16-wide k-slice of the GEMM is two consecutive boxes (descriptor LBO = 2048, SBO = 128; probed on B200 with
+// tools/gpu_probe_noswizzle.py).  Out-of-image taps are zero-filled by TMA = the conv's zero padding.  No thread touches
+// the operand: the builder warps of the previous version (bound by load latency + conversion ALU) are gone.
+//
+//   forward : M = 128 pixels, N = 64, k' = (tap, hi|lo, c).  D = A*B1 + A*B2 with B1 = W_hi at the hi AND lo positions
+//             (x_hi*W_hi + x_lo*W_hi) and B2 = W_lo at the hi positions only (x_hi*W_lo); the dropped x_lo*W_lo term is
+//             2^-16 relative.  Epilogue as conv_igemm: +bias | scale/shift+ReLU -> bf16 NHWC, BatchNorm statistics in
+//             registers per CTA.
+//   wgrad   : D[k'][co] = sum_p A[p][k'] * dRaw[p][co]: the same boxes read MN-major (LBO = 128, SBO = 2048), B = the dRaw
+//             tile (SW128 TMA box); the fp32 accumulator stays in TMEM for the CTA's lifetime; a fold kernel adds the hi
+//             and lo rows and the per-CTA partials.
 #include "host_util.h"
 #include "ptx.cuh"
 #include "devfn.cuh"
 
 namespace {
 
-constexpr int FC_A_TILE = 128 * 128;  // 128 pixels x 64 k bf16
-constexpr int FC_B_TILE = 64 * 128;   // 64 channels x 64 k bf16
+constexpr int BOX_BYTES = 128 * 16;  // one tap box: 128 pixels x 8 bf16
+constexpr int FC_THREADS = 384;      // w0 TMA, w1 MMA, w2 TMEM alloc, w4-11 epilogue
 
-// byte offset of 16-byte chunk c (8 bf16) of 128-byte row r in a SWIZZLE_128B tile whose base is 1024-byte aligned
-__device__ __forceinline__ uint32_t sw128(int r, int c) { return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4)); }
-
-__device__ __forceinline__ void split_store8(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float (&v)[8]) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    const float2 hf = __bfloat1622float2(hh);
-    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[j] = pack_bf16x2(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-  }
-  *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// im2col of one pixel row of an 8x16-pixel tile: row r = pixel (r>>4, r&15), k = ci*9 + ky*3 + kx.  One thread builds
-// the whole 128-byte row (all its loads are independent and in flight together).  Out-of-image taps are zero (= the
-// conv's zero padding).
 template <int CIN>
-__device__ __forceinline__ void build_im2col_row(const float* __restrict__ x, int img, int y0, int x0, int H, int W,
-                                                 int r, uint8_t* a_hi, uint8_t* a_lo) {
-  constexpr int K = CIN * 9;
-  constexpr int NCHUNK = 2 * ((K + 15) / 16);
-  const int y = y0 + (r >> 4), xx = x0 + (r & 15);
-  const float* xi = x + static_cast<long>(img) * CIN * H * W;
-  float v[NCHUNK][8];
-#pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = c * 8 + j;
-      v[c][j] = 0.f;
-      if (k < K) {
-        const int ci = k / 9, tap = k % 9;
-        const int yy = y + tap / 3 - 1, xq = xx + tap % 3 - 1;
-        const bool ok = yy >= 0 && yy < H && xq >= 0 && xq < W;
-        const float* src = xi + (static_cast<long>(ci) * H + (ok ? yy : 0)) * W + (ok ? xq : 0);
-        const float t = __ldg(src);  // unconditional load of a clamped address: no branch, loads stay independent
-        v[c][j] = ok ? t : 0.f;
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NCHUNK; ++c) split_store8(a_hi, a_lo, sw128(r, c), v[c]);
-}
-
-__device__ __forceinline__ void named_bar(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-constexpr int FC_A_BUF = 2 * FC_A_TILE;  // hi | lo
-// shared memory: [A buf 0 | A buf 1 | B region 32 KB | barriers | floats]
-//   forward: B region = W_hi (8 KB) | W_lo (8 KB);  wgrad: B region = dRaw tile 0 (16 KB) | dRaw tile 1 (16 KB)
-constexpr int FC_SMEM_BYTES = 1024 + 2 * FC_A_BUF + 2 * FC_A_TILE + 128 + (2 * 64 + 8 * 64) * 4;
-struct FcSmem {
-  uint8_t* a[2];
-  uint8_t* b;
-  uint64_t* bars;
-  uint32_t* tmem_ptr;
-  float* fl;
+struct FcCfg {
+  static constexpr int P = (CIN <= 4) ? 4 : 8;       // padded channels per half
+  static constexpr int CT = P / 4;                    // 16-byte chunks per tap (hi|lo in one chunk, or hi chunk + lo chunk)
+  static constexpr int NCH = 9 * CT;                  // chunks (= TMA boxes) per tile
+  static constexpr int KS = (NCH + 1) / 2;            // 16-wide k-slices
+  static constexpr int A_STAGE = 2 * KS * BOX_BYTES;  // forward: NCH boxes + a zero pad box when NCH is odd
+  static constexpr int WG_GROUPS = (NCH + 15) / 16;   // wgrad accumulators (128 k' rows = 16 boxes each)
+  static constexpr int A_STAGE_WG = WG_GROUPS * 16 * BOX_BYTES;
+  static constexpr int B_BYTES = (2 * KS) * 1024;     // weights: 2*KS chunks x [64 co][16 B]
 };
-__device__ __forceinline__ FcSmem carve(uint8_t* raw) {
-  uint8_t* base = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);
-  FcSmem s;
-  s.a[0] = base;
-  s.a[1] = base + FC_A_BUF;
-  s.b = base + 2 * FC_A_BUF;
-  s.bars = reinterpret_cast<uint64_t*>(s.b + 2 * FC_A_TILE);
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.bars + 8);
-  s.fl = reinterpret_cast<float*>(s.bars + 16);
-  return s;
+
+__device__ __forceinline__ void epi_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// fp32 NCHW -> [pixel][hi c0..P-1 | lo c0..P-1] bf16 (channels >= CIN are zero)
+template <int CIN>
+__global__ void __launch_bounds__(256) split_input_kernel(const float* __restrict__ x, long npix_per_img, int NB,
+                                                          bf16* __restrict__ xs) {
+  constexpr int P = FcCfg<CIN>::P;
+  const long total = static_cast<long>(NB) * npix_per_img;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = i / npix_per_img, r = i - n * npix_per_img;
+    float hi[P], lo[P];
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+      const float v = c < CIN ? __ldg(x + (n * CIN + c) * npix_per_img + r) : 0.f;
+      const float h = __bfloat162float(__float2bfloat16(v));
+      hi[c] = h;
+      lo[c] = v - h;
+    }
+    uint32_t w[P];  // P/2 words of hi then P/2 words of lo
+#pragma unroll
+    for (int c = 0; c < P / 2; ++c) {
+      w[c] = pack_bf16x2(hi[2 * c], hi[2 * c + 1]);
+      w[P / 2 + c] = pack_bf16x2(lo[2 * c], lo[2 * c + 1]);
+    }
+    // planes [part][pixel][8]: P = 4: one plane (hi4 | lo4); P = 8: plane 0 = hi8, plane 1 = lo8
+    *reinterpret_cast<uint4*>(xs + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (P == 8) *reinterpret_cast<uint4*>(xs + (total + i) * 8) = make_uint4(w[P - 4], w[P - 3], w[P - 2], w[P - 1]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------- forward
-// 12 warps: w0-3 build the im2col tiles (one pixel row per thread, double-buffered) and w0's elected lane issues the
-// MMAs; w4-11 are the epilogue (TMEM lane quarter w%4, 32-column half (w-4)/4) on two TMEM accumulator stages.
-constexpr int FC_FWD_THREADS = 384;
 template <int CIN>
-__global__ void __launch_bounds__(FC_FWD_THREADS, 1)
-first_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
-                     const float* __restrict__ shift, int relu, int NB, int H, int W, bf16* __restrict__ out,
-                     int out_pitch, float* stats) {
-  constexpr int K = CIN * 9;
-  constexpr int KS = (K + 15) / 16;  // 16-wide k-slices
+__global__ void __launch_bounds__(FC_THREADS, 1)
+first_conv_tc_kernel(const __grid_constant__ CUtensorMap x_map, const float* __restrict__ w,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int relu, int NB, int H, int W,
+                     bf16* __restrict__ out, int out_pitch, float* stats) {
+  using Cfg = FcCfg<CIN>;
+  constexpr int P = Cfg::P, CT = Cfg::CT, NCH = Cfg::NCH, KS = Cfg::KS;
+  constexpr int STAGES = 4;
   extern __shared__ uint8_t smem_raw[];
-  const FcSmem s = carve(smem_raw);
-  uint64_t* tmem_full = s.bars;       // [2] MMAs of the tile done: accumulator ready, operand buffer free
-  uint64_t* tmem_empty = s.bars + 2;  // [2] accumulator drained by the 256 epilogue threads
-  float* s_sc = s.fl;                 // [64]
-  float* s_sh = s.fl + 64;            // [64]
-  float* s_red = s.fl + 128;          // [4 quarters][2][64]
-  uint8_t* w_hi = s.b;
-  uint8_t* w_lo = s.b + FC_B_TILE;
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_ring = smem;                                   // [STAGES][2*KS boxes]
+  uint8_t* b1 = a_ring + STAGES * Cfg::A_STAGE;             // W_hi at hi and lo positions
+  uint8_t* b2 = b1 + Cfg::B_BYTES;                          // W_lo at hi positions
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(b2 + Cfg::B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_sc = reinterpret_cast<float*>(tmem_ptr + 4);     // [64]
+  float* s_sh = s_sc + 64;                                  // [64]
+  float* s_red = s_sh + 64;                                 // [4 quarters][2][64]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&x_map);
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 256);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
-    ptx::tmem_alloc(s.tmem_ptr, 128);
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, 128);
     ptx::tmem_relinquish();
   }
-  // k columns >= 16*KS of the operand tiles are never written and never read; zero everything once for hygiene
-  for (int i = threadIdx.x; i < (2 * FC_A_BUF + 2 * FC_A_TILE) / 16; i += FC_FWD_THREADS)
-    reinterpret_cast<uint4*>(s.a[0])[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
+  // operand ring zeroed once: the pad box behind an odd number of chunks must read as zeros
+  for (int i = threadIdx.x; i < (STAGES * Cfg::A_STAGE + 2 * Cfg::B_BYTES) / 16; i += FC_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 64) {
     s_sc[threadIdx.x] = scale ? scale[threadIdx.x] : 1.f;
     s_sh[threadIdx.x] = shift ? shift[threadIdx.x] : 0.f;
   }
-  if (threadIdx.x < 256) {  // weights [co][k] fp32 -> W_hi / W_lo tiles (row = co)
-    const int co = threadIdx.x & 63, c0 = threadIdx.x >> 6;
-    for (int c = c0; c < 2 * KS; c += 4) {
-      float v[8];
+  __syncthreads();
+  // weights (co, c, tap) fp32 -> un-swizzled K-major core matrices: chunk j at j*1024, co group g at g*128, row co%8
+  for (int i = threadIdx.x; i < 64 * NCH; i += FC_THREADS) {
+    const int co = i & 63, j = i >> 6;
+    const int tap = j / CT, part = j % CT;  // P = 8: part 0 = hi chunk, part 1 = lo chunk
+    uint32_t h1[4], h2[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = c * 8 + j;
-        v[j] = k < K ? w[co * K + k] : 0.f;
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float wv[2], lv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = 2 * e2 + u;
+        const int c = (P == 4) ? (e & 3) : e;
+        const bool is_lo_pos = (P == 4) ? (e >= 4) : (part == 1);
+        const float v = c < CIN ? w[(co * CIN + c) * 9 + tap] : 0.f;
+        const float hv = __bfloat162float(__float2bfloat16(v));
+        wv[u] = hv;                           // W_hi multiplies x_hi and x_lo
+        lv[u] = is_lo_pos ? 0.f : (v - hv);   // W_lo multiplies x_hi only
       }
-      split_store8(w_hi, w_lo, sw128(co, c), v);
+      h1[e2] = pack_bf16x2(wv[0], wv[1]);
+      h2[e2] = pack_bf16x2(lv[0], lv[1]);
     }
+    const int off = j * 1024 + (co >> 3) * 128 + (co & 7) * 16;
+    *reinterpret_cast<uint4*>(b1 + off) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(b2 + off) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
   }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *s.tmem_ptr;
+  const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
   const int total = NB * tiles_x * tiles_y;
 
-  if (warp < 4) {
-    // ===================== builders + MMA issue =====================
-    const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 0, 0);
-    const uint64_t b_hi_d = ptx::make_smem_desc(ptx::smem_u32(w_hi), 16, 1024);
-    const uint64_t b_lo_d = ptx::make_smem_desc(ptx::smem_u32(w_lo), 16, 1024);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      int t = tile;
-      const int tx = t % tiles_x;
-      t /= tiles_x;
-      const int ty = t % tiles_y;
-      const int img = t / tiles_y;
-      // the MMAs that read this operand buffer two tiles ago have completed
-      if (it >= 2) ptx::mbar_wait(&tmem_full[buf], ((it >> 1) & 1) ^ 1u);
-      build_im2col_row<CIN>(x, img, ty * TILE_H, tx * TILE_W, H, W, threadIdx.x, s.a[buf], s.a[buf] + FC_A_TILE);
-      ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      named_bar(2, 128);
-      if (warp == 0) {
-        if (ptx::elect_one()) {
-          ptx::mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1u);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * 64;
-          const uint64_t a_hi_d = ptx::make_smem_desc(ptx::smem_u32(s.a[buf]), 16, 1024);
-          const uint64_t a_lo_d = ptx::make_smem_desc(ptx::smem_u32(s.a[buf] + FC_A_TILE), 16, 1024);
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      // ===================== TMA producer: NCH tap boxes per tile =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % tiles_x;
+        t /= tiles_x;
+        const int ty = t % tiles_y;
+        const int img = t / tiles_y;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], NCH * BOX_BYTES);
+        uint8_t* sa = a_ring + stage * Cfg::A_STAGE;
 #pragma unroll
-          for (int k = 0; k < KS; ++k) ptx::umma_bf16(d_tmem, a_hi_d + 2 * k, b_hi_d + 2 * k, idesc, k != 0);
-#pragma unroll
-          for (int k = 0; k < KS; ++k) ptx::umma_bf16(d_tmem, a_lo_d + 2 * k, b_hi_d + 2 * k, idesc, 1);
-#pragma unroll
-          for (int k = 0; k < KS; ++k) ptx::umma_bf16(d_tmem, a_hi_d + 2 * k, b_lo_d + 2 * k, idesc, 1);
-          ptx::umma_commit(&tmem_full[buf]);
+        for (int j = 0; j < NCH; ++j) {
+          const int tap = j / CT, part = j % CT;
+          ptx::tma_load_4d(sa + j * BOX_BYTES, &x_map, &full_bar[stage], (tx * TILE_W + tap % 3 - 1) * 8,
+                           ty * TILE_H + tap / 3 - 1, img, part);
         }
-        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
-  } else {
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 0, 0);
+      // un-swizzled K-major: LBO = K-direction stride between 16-byte chunks, SBO = stride between 8-row groups
+      const uint64_t adesc0 = ptx::make_smem_desc(0, BOX_BYTES, 128, 0, 0);
+      const uint64_t b1d = ptx::make_smem_desc(ptx::smem_u32(b1), 1024, 128, 0, 0);
+      const uint64_t b2d = ptx::make_smem_desc(ptx::smem_u32(b2), 1024, 128, 0, 0);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        ptx::mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1u);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 64;
+        const uint64_t adesc = adesc0 + (ptx::smem_u32(a_ring + stage * Cfg::A_STAGE) >> 4);
+#pragma unroll
+        for (int k = 0; k < KS; ++k)  // one k-slice = two chunks: +4096 B in A, +2048 B in B
+          ptx::umma_bf16(d_tmem, adesc + k * (2 * BOX_BYTES >> 4), b1d + k * (2048 >> 4), idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+          ptx::umma_bf16(d_tmem, adesc + k * (2 * BOX_BYTES >> 4), b2d + k * (2048 >> 4), idesc, 1);
+        ptx::umma_commit(&empty_bar[stage]);
+        ptx::umma_commit(&tmem_full[as]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3, hc = (warp - 4) >> 2;  // TMEM lane quarter / 32-column half of this warp
     const int r = q * 32 + lane;
@@ -204,7 +220,7 @@ first_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     for (int j = 0; j < 32; ++j) r1[j] = r2[j] = 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+      const int as = it & 1;
       int t = tile;
       const int tx = t % tiles_x;
       t /= tiles_x;
@@ -212,13 +228,13 @@ first_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       const int img = t / tiles_y;
       const int y = ty * TILE_H + (r >> 4), xx = tx * TILE_W + (r & 15);
       const bool valid = y < H && xx < W;
-      ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      ptx::mbar_wait(&tmem_full[as], (it >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t v[32];
-      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 64 + hc * 32, v);
+      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 64 + hc * 32, v);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty[buf]);  // accumulator is in registers: the stage may be overwritten
+      ptx::mbar_arrive(&tmem_empty[as]);  // accumulator is in registers: the stage may be overwritten
       const float4* sc4 = reinterpret_cast<const float4*>(s_sc + hc * 32);
       const float4* sh4 = reinterpret_cast<const float4*>(s_sh + hc * 32);
       uint32_t pk[16];
@@ -260,7 +276,7 @@ first_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       xpose_reduce(r2, lane);
       s_red[(q * 2 + 0) * 64 + hc * 32 + lane] = r1[0];
       s_red[(q * 2 + 1) * 64 + hc * 32 + lane] = r2[0];
-      named_bar(1, 256);
+      epi_bar256();
       if (e < 128) {
         const int which = e >> 6, c = e & 63;
         float a = 0.f;
@@ -272,138 +288,177 @@ first_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, c
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 128);
   }
 }
+template <int CIN>
+constexpr int fc_fwd_smem() {
+  return 1024 + 4 * FcCfg<CIN>::A_STAGE + 2 * FcCfg<CIN>::B_BYTES + 256 + (2 * 64 + 8 * 64) * 4;
+}
 
 // ---------------------------------------------------------------------------------------------------------------- wgrad
-// 8 warps = two builder groups (w0-3 even tiles, w4-7 odd tiles); the elected lane of each group's first warp fetches the
-// tile's dRaw box by TMA and issues its 8 MMAs.  The accumulator never leaves TMEM until the CTA has done all tiles.
+// w0 TMA, w1 MMA, w2 TMEM alloc, w4-7 read the accumulator out once at the end.
 constexpr int FC_WG_THREADS = 256;
 template <int CIN>
 __global__ void __launch_bounds__(FC_WG_THREADS, 1)
-first_conv_wgrad_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap d_map, int NB, int H, int W,
-                           float* partials) {
+first_conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap d_map, int NB,
+                           int H, int W, float* partials) {
+  using Cfg = FcCfg<CIN>;
+  constexpr int CT = Cfg::CT, NCH = Cfg::NCH, G = Cfg::WG_GROUPS;
+  constexpr int STAGES = (G == 1) ? 3 : 2;
+  constexpr int D_TILE = 128 * 128;  // dRaw tile: 128 pixels x 64 channels bf16, SW128
+  constexpr int STAGE = Cfg::A_STAGE_WG + D_TILE;
+  constexpr int TMEM_COLS = (G == 1) ? 64 : 128;
   extern __shared__ uint8_t smem_raw[];
-  const FcSmem s = carve(smem_raw);
-  uint64_t* d_full = s.bars;      // [2] dRaw tile landed
-  uint64_t* mma_done = s.bars + 2;  // [2] MMAs of the tile done: its operand buffers are free
-  uint64_t* first_done = s.bars + 4;  // one-shot: group 0's first tile has started the accumulator
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&x_map);
     ptx::prefetch_tmap(&d_map);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&d_full[i], 1);
-      ptx::mbar_init(&mma_done[i], 1);
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
     }
-    ptx::mbar_init(first_done, 1);
+    ptx::mbar_init(acc_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
-    ptx::tmem_alloc(s.tmem_ptr, 64);
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * FC_A_BUF / 16; i += FC_WG_THREADS)  // k columns >= 16*KS are never written
-    reinterpret_cast<uint4*>(s.a[0])[i] = make_uint4(0, 0, 0, 0);
+  // the MMA reads 16 boxes per accumulator group, TMA only writes NCH of them: the rest must be finite (zeros)
+  for (int i = threadIdx.x; i < STAGES * STAGE / 16; i += FC_WG_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *s.tmem_ptr;
+  const uint32_t tmem_base = *tmem_ptr;
   const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
   const int total = NB * tiles_x * tiles_y;
-  // both operands MN-major: A = (x_hi | x_lo) im2col tiles, two 64-wide boxes 16 KB apart; B = dRaw [128 px][64 co]
-  const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);
-  const int grp = warp >> 2;                 // builder group = operand buffer
-  const int r = threadIdx.x & 127;
-  uint8_t* a_buf = s.a[grp];
-  uint8_t* d_buf = s.b + grp * FC_A_TILE;
-  const uint64_t adesc = ptx::make_smem_desc(ptx::smem_u32(a_buf), FC_A_TILE, 1024);
-  const uint64_t bdesc = ptx::make_smem_desc(ptx::smem_u32(d_buf), FC_A_TILE, 1024);
-  const bool leader = (warp & 3) == 0;
 
-  // group g handles the CTA's tiles number g, g+2, ...; the MMAs of the two groups interleave on one accumulator, which
-  // is fine: accumulation order inside a CTA is free (fp32 sums), only the very first MMA must not accumulate.
-  int n = 0;  // tiles this group has done
-  for (int tile = blockIdx.x + grp * gridDim.x; tile < total; tile += 2 * gridDim.x, ++n) {
-    int t = tile;
-    const int tx = t % tiles_x;
-    t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int img = t / tiles_y;
-    const int y0 = ty * TILE_H, x0 = tx * TILE_W;
-    if (n >= 1) ptx::mbar_wait(&mma_done[grp], (n - 1) & 1);  // this group's previous MMAs have consumed the buffers
-    if (leader) {
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&d_full[grp], FC_A_TILE);
-        ptx::tma_load_4d(d_buf, &d_map, &d_full[grp], 0, x0, y0, img);  // out-of-image pixels arrive as zeros
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % tiles_x;
+        t /= tiles_x;
+        const int ty = t % tiles_y;
+        const int img = t / tiles_y;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], NCH * BOX_BYTES + D_TILE);
+        uint8_t* sa = smem + stage * STAGE;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int tap = j / CT, part = j % CT;
+          ptx::tma_load_4d(sa + j * BOX_BYTES, &x_map, &full_bar[stage], (tx * TILE_W + tap % 3 - 1) * 8,
+                           ty * TILE_H + tap / 3 - 1, img, part);
+        }
+        ptx::tma_load_4d(sa + Cfg::A_STAGE_WG, &d_map, &full_bar[stage], 0, tx * TILE_W, ty * TILE_H, img);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
-      __syncwarp();
     }
-    build_im2col_row<CIN>(x, img, y0, x0, H, W, r, a_buf, a_buf + FC_A_TILE);
-    ptx::fence_proxy_async_smem();
-    named_bar(2 + grp, 128);
-    if (leader) {
-      if (ptx::elect_one()) {
-        ptx::mbar_wait(&d_full[grp], n & 1);
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      // A: un-swizzled MN-major (M = k' rows: 8 per box, boxes 2048 B apart = SBO; K = pixels: 8-pixel groups 128 B apart
+      // = LBO; 16 pixels per MMA = +256 B).  B: dRaw tile, SW128 MN-major as in wgrad_gemm (+2048 B per 16 pixels).
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);
+      const uint64_t adesc0 = ptx::make_smem_desc(0, 128, BOX_BYTES, 0, 0);
+      const uint64_t bdesc0 = ptx::make_smem_desc(0, 8192, 1024);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        // group 1 must not start the accumulator: its first MMA accumulates onto group 0's first tile, so it waits for it
-        if (grp == 1 && n == 0) ptx::mbar_wait(first_done, 0);
+        const uint32_t sa16 = ptx::smem_u32(smem + stage * STAGE) >> 4;
+        const uint64_t bdesc = bdesc0 + (sa16 + (Cfg::A_STAGE_WG >> 4));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // 16 pixels per MMA: +2048 B in both tiles
-          ptx::umma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (grp | n | k) != 0);
-        ptx::umma_commit(&mma_done[grp]);
-        if (grp == 0 && n == 0) ptx::umma_commit(first_done);
+        for (int g = 0; g < G; ++g) {
+          const uint64_t adesc = adesc0 + (sa16 + g * (16 * BOX_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            ptx::umma_bf16(tmem_base + g * 64, adesc + k * (256 >> 4), bdesc + k * (2048 >> 4), idesc, (it | k) != 0);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
-      __syncwarp();
+      ptx::umma_commit(acc_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    ptx::mbar_wait(acc_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2 * G; ++c) {  // 32-column chunks: group c/2, half c%2
+      uint32_t v[32];
+      ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      ptx::tmem_ld_wait();
+      float* dst = partials + ((static_cast<long>(blockIdx.x) * G + c / 2) * 128 + q * 32 + lane) * 64 + (c & 1) * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
     }
   }
-  // all MMAs of both groups complete -> read the accumulator
-  if (n >= 1) ptx::mbar_wait(&mma_done[grp], (n - 1) & 1);
   ptx::tc_fence_before();
   __syncthreads();
-  ptx::tc_fence_after();
-  {
-    const int q = warp & 3, hc = warp >> 2;
-    uint32_t v[32];
-    ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + hc * 32, v);
-    ptx::tmem_ld_wait();
-    float* dst = partials + (static_cast<long>(blockIdx.x) * 128 + q * 32 + lane) * 64 + hc * 32;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 64);
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+template <int CIN>
+constexpr int fc_wg_smem() {
+  return 1024 + (FcCfg<CIN>::WG_GROUPS == 1 ? 3 : 2) * (FcCfg<CIN>::A_STAGE_WG + 128 * 128) + 256;
+}
 
-// partials [ncta][128 = (k_hi | k_lo)][64 co] -> dw[co][k], k < K.  Block = one k: 64 channels x 4 CTA-lanes.
-__global__ void __launch_bounds__(256) first_conv_wgrad_fold_kernel(const float* __restrict__ partials, int ncta, int K,
+// partials [ncta][G*128 k' rows][64 co] -> dw[co][c][tap] = hi row + lo row.  Block = one (c, tap): 64 co x 4 CTA-lanes.
+template <int CIN>
+__global__ void __launch_bounds__(256) first_conv_wgrad_fold_kernel(const float* __restrict__ partials, int ncta,
                                                                     float* dw, int accumulate) {
+  using Cfg = FcCfg<CIN>;
+  constexpr int P = Cfg::P, G = Cfg::WG_GROUPS;
   __shared__ float s[4][64];
-  const int k = blockIdx.x, co = threadIdx.x & 63, ln = threadIdx.x >> 6;
+  const int c = blockIdx.x / 9, tap = blockIdx.x % 9;
+  const int co = threadIdx.x & 63, ln = threadIdx.x >> 6;
+  // k' row of (tap, hi|lo, c): P = 4: tap*8 + {0,4} + c ; P = 8: (tap*2 + {0,1})*8 + c
+  const int row_hi = (P == 4) ? tap * 8 + c : (tap * 2) * 8 + c;
+  const int row_lo = (P == 4) ? tap * 8 + 4 + c : (tap * 2 + 1) * 8 + c;
   float a = 0.f;
-  for (int c = ln; c < ncta; c += 4)
-    a += partials[(static_cast<long>(c) * 128 + k) * 64 + co] + partials[(static_cast<long>(c) * 128 + 64 + k) * 64 + co];
+  for (int b = ln; b < ncta; b += 4) {
+    const float* base = partials + static_cast<long>(b) * G * 128 * 64;
+    a += base[row_hi * 64 + co] + base[row_lo * 64 + co];
+  }
   s[ln][co] = a;
   __syncthreads();
   if (ln == 0) {
     const float g = (s[0][co] + s[1][co]) + (s[2][co] + s[3][co]);
-    float* d = dw + co * K + k;
+    float* d = dw + (co * CIN + c) * 9 + tap;
     *d = accumulate ? *d + g : g;
   }
 }
 
 template <typename Kern>
-cudaError_t set_smem(Kern kern) {
-  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES);
+cudaError_t set_smem(Kern kern, int bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+int x_map_for(CUtensorMap* map, bf16* xs, int NB, int H, int W, int P) {
+  return make_split_input_map(map, xs, P / 4, NB, H, W);
 }
 
 }  // namespace
@@ -413,50 +468,63 @@ int first_conv_tc_grid(int NB, int H, int W) {
   const int sms = device_num_sms();
   return tiles < sms ? tiles : sms;
 }
+size_t first_conv_split_elems(int NB, int cin, int H, int W) {
+  return static_cast<size_t>(NB) * H * W * 2 * (cin <= 4 ? 4 : 8);
+}
 
-// cin <= 7 (K = 9*cin <= 63 fits one 64-wide k-block); stats: [grid][2][64] partial rows
-cudaError_t launch_first_conv_tc(const float* x, const float* w, const float* scale, const float* shift, int relu,
-                                 int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats,
+// cin <= 8.  xs: scratch of first_conv_split_elems() bf16 (written here, reused by the weight gradient of the same
+// input); stats: [grid][2][64] partial rows
+cudaError_t launch_first_conv_tc(const float* x, bf16* xs, const float* w, const float* scale, const float* shift,
+                                 int relu, int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats,
                                  cudaStream_t st) {
   const int grid = first_conv_tc_grid(NB, H, W);
-#define FC(C)                                                                                                     \
-  if (cin == C) {                                                                                                 \
-    static bool done = false;                                                                                     \
-    if (!done) {                                                                                                  \
-      cudaError_t e = set_smem(first_conv_tc_kernel<C>);                                                          \
-      if (e != cudaSuccess) return e;                                                                             \
-      done = true;                                                                                                \
-    }                                                                                                             \
-    first_conv_tc_kernel<C><<<grid, FC_FWD_THREADS, FC_SMEM_BYTES, st>>>(x, w, scale, shift, relu, NB, H, W, out,     \
-                                                                     out_pitch, stats);                           \
-    return cudaGetLastError();                                                                                    \
+  const long npix = static_cast<long>(H) * W;
+#define FC(C)                                                                                                      \
+  if (cin == C) {                                                                                                  \
+    static bool done = false;                                                                                      \
+    if (!done) {                                                                                                   \
+      cudaError_t e = set_smem(first_conv_tc_kernel<C>, fc_fwd_smem<C>());                                         \
+      if (e != cudaSuccess) return e;                                                                              \
+      done = true;                                                                                                 \
+    }                                                                                                              \
+    long blocks = (NB * npix + 255) / 256;                                                                         \
+    if (blocks > 148 * 8) blocks = 148 * 8;                                                                        \
+    split_input_kernel<C><<<static_cast<int>(blocks), 256, 0, st>>>(x, npix, NB, xs);                              \
+    CUtensorMap map;                                                                                               \
+    if (x_map_for(&map, xs, NB, H, W, FcCfg<C>::P) != 0) return cudaErrorInvalidValue;                             \
+    first_conv_tc_kernel<C><<<grid, FC_THREADS, fc_fwd_smem<C>(), st>>>(map, w, scale, shift, relu, NB, H, W, out,  \
+                                                                        out_pitch, stats);                         \
+    return cudaGetLastError();                                                                                     \
   }
-  FC(1) FC(2) FC(3) FC(4) FC(5) FC(6) FC(7)
+  FC(1) FC(2) FC(3) FC(4) FC(5) FC(6) FC(7) FC(8)
 #undef FC
   return cudaErrorInvalidValue;
 }
 
-// partials: at least first_conv_tc_grid() * 128 * 64 floats
-cudaError_t launch_first_conv_wgrad_tc(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
+// partials: at least first_conv_tc_grid() * 2 * 128 * 64 floats.  xs: the split input written by the matching forward.
+cudaError_t launch_first_conv_wgrad_tc(const bf16* xs, View draw, int cin, float* partials, float* dw, int accumulate,
                                        cudaStream_t st) {
   if (draw.C != 64) return cudaErrorInvalidValue;
-  CUtensorMap map;
-  if (make_act_map(&map, draw, TILE_H) != 0) return cudaErrorInvalidValue;
+  CUtensorMap dmap;
+  if (make_act_map(&dmap, draw, TILE_H) != 0) return cudaErrorInvalidValue;
   const int grid = first_conv_tc_grid(draw.N, draw.H, draw.W);
-#define FW(C)                                                                                                     \
-  if (cin == C) {                                                                                                 \
-    static bool done = false;                                                                                     \
-    if (!done) {                                                                                                  \
-      cudaError_t e = set_smem(first_conv_wgrad_tc_kernel<C>);                                                    \
-      if (e != cudaSuccess) return e;                                                                             \
-      done = true;                                                                                                \
-    }                                                                                                             \
-    first_conv_wgrad_tc_kernel<C><<<grid, FC_WG_THREADS, FC_SMEM_BYTES, st>>>(x, map, draw.N, draw.H, draw.W,        \
-                                                                           partials);                             \
-    first_conv_wgrad_fold_kernel<<<C * 9, 256, 0, st>>>(partials, grid, C * 9, dw, accumulate);                   \
-    return cudaGetLastError();                                                                                    \
+#define FW(C)                                                                                                      \
+  if (cin == C) {                                                                                                  \
+    static bool done = false;                                                                                      \
+    if (!done) {                                                                                                   \
+      cudaError_t e = set_smem(first_conv_wgrad_tc_kernel<C>, fc_wg_smem<C>());                                    \
+      if (e != cudaSuccess) return e;                                                                              \
+      done = true;                                                                                                 \
+    }                                                                                                              \
+    CUtensorMap xmap;                                                                                              \
+    if (x_map_for(&xmap, const_cast<bf16*>(xs), draw.N, draw.H, draw.W, FcCfg<C>::P) != 0)                         \
+      return cudaErrorInvalidValue;                                                                                \
+    first_conv_wgrad_tc_kernel<C><<<grid, FC_WG_THREADS, fc_wg_smem<C>(), st>>>(xmap, dmap, draw.N, draw.H, draw.W, \
+                                                                                partials);                         \
+    first_conv_wgrad_fold_kernel<C><<<C * 9, 256, 0, st>>>(partials, grid, dw, accumulate);                        \
+    return cudaGetLastError();                                                                                     \
   }
-  FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7)
+  FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
 #undef FW
   return cudaErrorInvalidValue;
 }

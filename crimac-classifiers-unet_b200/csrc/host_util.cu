@@ -21,7 +21,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, int kx, int box_w) {
+int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, int kx, int box_w, int box_c, int swizzle) {
   auto enc = get_encode();
   CRIMAC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   CRIMAC_REQUIRE(v.C % 8 == 0 && v.pitch % 8 == 0, "channel count / pitch must be multiples of 8");
@@ -41,13 +41,35 @@ int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, in
   }
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(v.C), W, H, static_cast<cuuint64_t>(v.N)};
   cuuint64_t strides[3] = {sx, sy, sn};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     crimac_set_error("cuTensorMapEncodeTiled(activation) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 2;
+  }
+  return 0;
+}
+
+// Un-swizzled map over the first conv's split input planes xs[part][n][y][x*8 + e] (first_conv_tc.cu): the ping and the
+// 8-element chunk are ONE flattened inner dimension, so a box {16 pings x 8, 8 rows} is fetched as 8 rows of 256 B
+// instead of 128 rows of 16 B while landing in shared memory in the same order (16 core matrices of 8 pixels x 16 B).
+int make_split_input_map(CUtensorMap* out, const bf16* xs, int parts, int NB, int H, int W) {
+  auto enc = get_encode();
+  CRIMAC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(W) * 8, static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(NB),
+                        static_cast<cuuint64_t>(parts)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 16, static_cast<cuuint64_t>(H) * W * 16,
+                           static_cast<cuuint64_t>(NB) * H * W * 16};
+  cuuint32_t box[4] = {128, 8, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(xs), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    crimac_set_error("cuTensorMapEncodeTiled(split input) failed with CUresult " + std::to_string(static_cast<int>(r)));
     return 2;
   }
   return 0;

@@ -26,7 +26,9 @@ void crimac_set_error(const std::string& msg);
 // 4-D map {C, W, H, N} over an NHWC bf16 view, box {64, 16, box_h, 1}, SWIZZLE_128B, zero OOB fill.
 // sub = 0: plain view.  sub = 1: the (ky,kx) 2x2 sub-sampled view of a (2H x 2W) tensor, i.e. pixel (y,x) of the map
 // is pixel (2y+ky, 2x+kx) of v (used for ConvTranspose2d backward).
-int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub = 0, int ky = 0, int kx = 0, int box_w = 16);
+int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub = 0, int ky = 0, int kx = 0, int box_w = 16,
+                 int box_c = 64, int swizzle = 1);  // box_c = 8, swizzle = 0: un-swizzled 16-byte-per-pixel boxes (first conv)
+int make_split_input_map(CUtensorMap* out, const bf16* xs, int parts, int NB, int H, int W);
 // 2-D map over packed weights [rows][cols] bf16 (cols contiguous), box {64, box_rows}.
 int make_weight_map(CUtensorMap* out, const bf16* w, int rows, int cols, int box_rows);
 
@@ -64,20 +66,23 @@ struct ProfScope {
 };
 
 // ---- CUDA-core kernels (elementwise.cu)
-cudaError_t launch_first_conv(const float* x, const float* w, const float* scale, const float* shift, int relu, int NB,
-                              int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st);
+// xs: scratch of first_conv_split_elems() bf16 - the tensor-core path rewrites x there as bf16 hi/lo pairs (forward) and
+// reads it back (weight gradient of the same input)
+cudaError_t launch_first_conv(const float* x, bf16* xs, const float* w, const float* scale, const float* shift, int relu,
+                              int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats, cudaStream_t st);
 int first_conv_grid(int NB, int cin, int H, int W);  // = rows of the statistics partials the kernel writes
 int first_conv_wgrad_blocks();
 size_t first_conv_wgrad_partial_floats(int cin);  // scratch the weight-gradient launcher needs
-// tensor-core variants (first_conv_tc.cu), cin <= 7; the launchers above dispatch to them
+size_t first_conv_split_elems(int NB, int cin, int H, int W);
+// tensor-core variants (first_conv_tc.cu); the launchers above dispatch to them
 int first_conv_tc_grid(int NB, int H, int W);
-cudaError_t launch_first_conv_tc(const float* x, const float* w, const float* scale, const float* shift, int relu,
-                                 int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats,
+cudaError_t launch_first_conv_tc(const float* x, bf16* xs, const float* w, const float* scale, const float* shift,
+                                 int relu, int NB, int cin, int H, int W, bf16* out, int out_pitch, float* stats,
                                  cudaStream_t st);
-cudaError_t launch_first_conv_wgrad_tc(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
+cudaError_t launch_first_conv_wgrad_tc(const bf16* xs, View draw, int cin, float* partials, float* dw, int accumulate,
                                        cudaStream_t st);
-cudaError_t launch_first_conv_wgrad(const float* x, View draw, int cin, float* partials, float* dw, int accumulate,
-                                    cudaStream_t st);
+cudaError_t launch_first_conv_wgrad(const float* x, const bf16* xs, View draw, int cin, float* partials, float* dw,
+                                    int accumulate, cudaStream_t st);
 cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double count, const float* gamma,
                                const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
                                float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);

@@ -88,6 +88,7 @@ struct crimac_ctx {
   bool wg_dirty = true;        // scratch may hold partial sums (first use, or a failed backward)
   float* head_partials = nullptr;
   float* fc_partials = nullptr;
+  bf16* xs = nullptr;          // first conv: the input echogram as bf16 hi/lo pairs, NHWC (first_conv_tc.cu)
   double* ce_partials = nullptr;
   float* logits = nullptr;   // internal logits / dlogits for the fused train step
   float* dlogits = nullptr;
@@ -268,6 +269,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     U.bn_bwd = pick_bn(U.cin);
     U.bn_wg = pick_bn(U.cout);
   }
+  c->xs = bump.arr<bf16>(first_conv_split_elems(B, cfg.in_channels, cfg.height, cfg.width));
   // ---- training scratch
   c->dcat.assign(D - 1, nullptr);
   if (train) {
@@ -647,7 +649,7 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
       if (L.first) {
         ProfScope ps("first_conv", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st);
         stat_rows = first_conv_grid(nb, L.cin, H, W);
-        CRIMAC_CHECK_CUDA(launch_first_conv(x, S<float>(state, L.s_w), nullptr, S<float>(state, L.s_b), 0, nb, L.cin, H,
+        CRIMAC_CHECK_CUDA(launch_first_conv(x, c->xs, S<float>(state, L.s_w), nullptr, S<float>(state, L.s_b), 0, nb, L.cin, H,
                                             W, raw.ptr, raw.pitch, c->stats, st));
       } else {
         ConvParams p = L.fwd;
@@ -677,7 +679,7 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
       const double px = static_cast<double>(nb) * H * W;
       if (L.first) {
         ProfScope ps("first_conv", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), st);
-        CRIMAC_CHECK_CUDA(launch_first_conv(x, S<float>(state, L.s_w), L.scale, L.shift, 1, nb, L.cin, H, W, L.act.ptr,
+        CRIMAC_CHECK_CUDA(launch_first_conv(x, c->xs, S<float>(state, L.s_w), L.scale, L.shift, 1, nb, L.cin, H, W, L.act.ptr,
                                             L.act.pitch, nullptr, st));
       } else {
         ConvParams p = L.fwd;
@@ -839,7 +841,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     }
     if (L.first) {
       ProfScope ps("first_conv_wgrad", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), ws, 2);
-      CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, dr, L.cin, c->fc_partials, grads[L.g_w], 0, ws));
+      CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, c->xs, dr, L.cin, c->fc_partials, grads[L.g_w], 0, ws));
     } else {
       int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, ws) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, ws);
       if (r) return r;
