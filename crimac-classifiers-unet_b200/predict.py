@@ -103,7 +103,7 @@ def predict_host_batches(model, batches, classes=(1, 2)):
 
 
 class SurveyPredictor:
-    def __init__(self, model, patch_hw=(256, 256), overlap=20, preload_n_pings=20000, batch_size=32, classes=(1, 2),
+    def __init__(self, model, patch_hw=(256, 256), overlap=20, preload_n_pings=20000, batch_size=93, classes=(1, 2),
                  seabed_pad=10):
         self.model, self.patch_hw, self.overlap = model, tuple(patch_hw), int(overlap)
         self.preload_n_pings, self.batch_size = int(preload_n_pings), int(batch_size)

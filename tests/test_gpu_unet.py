@@ -313,3 +313,53 @@ def test_training_converges_and_trained_net_meets_argmax_tolerance(M, pkg):
     # host-batch inference pipeline == direct call
     outs = [o.clone() for o in P.predict_host_batches(m, [x.cpu().pin_memory()] * 3)]
     assert len(outs) == 3 and all(torch.equal(o, got[:, 1:3].half().cpu()) for o in outs)
+
+
+def test_full_size_config2_batch32_parity_and_invariances(M):
+    """BASELINE.json configs[1] at its FULL size (batch 32 of 4x256x256): loss, head gradient, BatchNorm running
+    statistics and class probabilities against the fp32 oracle (run with torch on the GPU), plus the size-independent
+    properties the path offers: eval results are per-patch (any sub-batch reproduces its slice bit for bit) and the
+    train-mode forward is deterministic."""
+    torch.manual_seed(0)
+    m = M.UNet_Baseline(3, 4).to(dev).train()
+    st0 = _state(m)
+    x = O.synthetic_echogram(32, 4, 256, 256, seed=0, device=dev)
+    y = O.synthetic_labels(32, 256, 256, seed=1, device=dev)
+    ref_logits, ref_loss, ref_g, ref_stats = O.train_step(st0, x, y)
+    cw = torch.tensor(O.CLASS_WEIGHTS, device=dev)
+    loss = m.train_step_fused(x, y, cw)
+    assert abs(loss.item() - ref_loss.item()) < 2e-3 * abs(ref_loss.item())
+    named = dict(m.named_parameters())
+    for k in ("conv_final.weight", "conv_final.bias", "up_convs.3.bn2.weight", "up_convs.3.bn2.bias"):
+        assert _rel(named[k].grad, ref_g[k]) < 5e-3, k
+    for name, p in m.named_parameters():
+        if not _pre_bn_bias(name):
+            assert _cos(p.grad, ref_g[name]) >= 0.8, (name, _cos(p.grad, ref_g[name]))
+    sd = m.state_dict()
+    for k, v in ref_stats.items():
+        if "num_batches" not in k:
+            assert _rel(sd[k], v) < 1e-2, k
+    del ref_logits, ref_g
+    # train-mode forward is deterministic (no atomics on the forward path)
+    torch.manual_seed(0)
+    m2 = M.UNet_Baseline(3, 4).to(dev).train()
+    with torch.no_grad():
+        a = m2(x)
+    torch.manual_seed(0)
+    m3 = M.UNet_Baseline(3, 4).to(dev).train()
+    with torch.no_grad():
+        b = m3(x)
+    assert torch.equal(a, b)
+    # eval: probabilities vs oracle on the full batch; sub-batches reproduce their slice exactly
+    m.eval()
+    with torch.no_grad():
+        ref = O.softmax_probs(O.unet_forward(_state(m), x))
+        got = m.predict_proba(x)
+        parts = torch.cat([m.predict_proba(x[i:i + 8]) for i in range(0, 32, 8)])
+    dp = (got - ref).abs().max().item()
+    top2 = ref.topk(2, 1).values
+    conf = (top2[:, 0] - top2[:, 1]) > 2 * PROB_TOL
+    agree_conf = (got.argmax(1) == ref.argmax(1))[conf].float().mean().item()
+    print(f"full size: loss {loss.item():.5f} (oracle {ref_loss.item():.5f}); max|dp|={dp:.4f}; argmax agreement on confident pixels {agree_conf:.5f}")
+    assert dp <= PROB_TOL and agree_conf >= 0.999
+    assert torch.equal(got, parts)

@@ -29,7 +29,7 @@ if [ "$1" == "ncu" ]; then
   echo "ncu elem exit $?"
 fi
 if [ "$1" == "extra" ]; then
-  timeout 600 python bench.py --mode survey --steps 10 --warmup 3 --batch 62 > gpurun_out/bench_survey.json 2> gpurun_out/bench_survey.err
+  timeout 600 python bench.py --mode survey --steps 10 --warmup 3 --batch 93 > gpurun_out/bench_survey.json 2> gpurun_out/bench_survey.err
   echo "bench survey exit $?"; cat gpurun_out/bench_survey.json; tail -5 gpurun_out/bench_survey.err
   timeout 600 python bench.py --mode train --in-ch 6 --size 512 --batch 64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stress_train.json 2> gpurun_out/bench_stress_train.err
   echo "bench stress train exit $?"; cat gpurun_out/bench_stress_train.json; tail -5 gpurun_out/bench_stress_train.err
