@@ -511,10 +511,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
             const long opix = (static_cast<long>(img) * p.H + y) * p.W + x;
             dst = p.out + opix * p.out_pitch + ng;
           }
-          store16(dst, pk);
-          store16(dst + 8, pk + 4);
-          store16(dst + 16, pk + 8);
-          store16(dst + 24, pk + 12);
+          store32(dst, pk);
+          store32(dst + 16, pk + 8);
         }
 
         if (EPI == EPI_STORE && p.pool_out != nullptr) {
@@ -527,10 +525,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
           if (valid && !(px & 1) && !(py & 1)) {
             const long ppix = (static_cast<long>(img) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
             bf16* dst = p.pool_out + ppix * p.pool_pitch + ng;
-            store16(dst, pm);
-            store16(dst + 8, pm + 4);
-            store16(dst + 16, pm + 8);
-            store16(dst + 24, pm + 12);
+            store32(dst, pm);
+            store32(dst + 16, pm + 8);
           }
         }
 
@@ -700,6 +696,9 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
 // BLOCK_N in {64,128,256}; p.n_tiles*BLOCK_N == N_total must hold.
 cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num_sms, cudaStream_t stream) {
   if (p.halo && p.taps != 9) return cudaErrorInvalidValue;
+  // the epilogue writes 32-byte (256-bit) vectors
+  if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 31) || p.out_pitch % 16)) return cudaErrorInvalidValue;
+  if (p.pool_out && ((reinterpret_cast<uintptr_t>(p.pool_out) & 31) || p.pool_pitch % 16)) return cudaErrorInvalidValue;
   if (p.b_mn && ((epi != EPI_STORE && epi != EPI_BNRED) || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
   if (epi == EPI_BNRED && (!p.b_mn || !p.bnr_raw || !p.bnr_scale || !p.bnr_shift || !p.stats)) return cudaErrorInvalidValue;
 #define CASE(BN, EP)                                                               \

@@ -36,6 +36,12 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 __device__ __forceinline__ void store16(bf16* dst, const uint32_t* pk) {
   *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
+// 32 bytes (16 bf16) in one 256-bit store (STG.E.256 on sm_100); dst must be 32-byte aligned
+__device__ __forceinline__ void store32(bf16* dst, const uint32_t* pk) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+               "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+               : "memory");
+}
 // 8 consecutive bf16 channels <-> 8 floats
 __device__ __forceinline__ void load8(const bf16* src, float (&f)[8]) {
   const uint4 u = *reinterpret_cast<const uint4*>(src);

@@ -254,10 +254,8 @@ first_conv_tc_kernel(const __grid_constant__ CUtensorMap x_map, const float* __r
       }
       if (valid) {
         bf16* dst = out + ((static_cast<long>(img) * H + y) * W + xx) * out_pitch + hc * 32;
-        store16(dst, pk);
-        store16(dst + 8, pk + 4);
-        store16(dst + 16, pk + 8);
-        store16(dst + 24, pk + 12);
+        store32(dst, pk);
+        store32(dst + 16, pk + 8);
       }
       if (stats != nullptr) {
         // statistics of the bf16-rounded values the BN-apply pass reads back; per-thread until the CTA is done
