@@ -230,9 +230,7 @@ def run_b200(args):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        l0 = E.launch_count()
         ms_total = timed(lambda: step(x, y), args.steps)
-        launches = E.launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
         ms_step = ms_total / args.steps
         value = world * B / (ms_step * 1e-3)
@@ -271,11 +269,19 @@ def run_b200(args):
         e2e_value = world * B / (ms_e2e * 1e-3)
 
         # ---- per-kernel breakdown of one more step (CUDA events around every launch, on the launching stream)
+        # (an EAGER step: the timed steps replay a CUDA graph of exactly these launches, which the library's launch
+        # counter and per-launch events cannot see)
         torch.cuda.synchronize()
         E.profile_enable(True)
-        step(x, y)
+        l0 = E.launch_count()
+        if args.mode == "train":
+            trainer._launch_step(x, y)
+        else:
+            step(x, y)
+        launches_per_step = E.launch_count() - l0
         recs = E.profile_read()
         E.profile_enable(False)
+        launches = launches_per_step * args.steps
 
     fam = {}
     for name, ms, fl, by, ln in recs:
@@ -320,6 +326,7 @@ def run_b200(args):
             "dtype": "bf16 (fp32 accumulate; first conv, BN statistics, head, loss in fp32)", "data": "synthetic",
             "config": {"workload": (WORKLOAD if standard and B == 32 else "UNet training fwd+bwd, batch %d of %dx%dx%d per GPU" % (B, C, S, S)) if args.mode == "train" else "UNet inference, batch %d of %dx%dx%d" % (B, C, S, S),
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single GPU",
+                       "launch": ("CUDA graph replay of one captured step" if getattr(trainer, "_graph", None) is not None else "eager stream launches") if args.mode == "train" else "eager stream launches",
                        "step": "weight re-pack + forward + weighted CE + backward" + (" + NCCL all-reduce of the 124 MB gradient arena" if world > 1 else "") + " + fused SGD-momentum update" if args.mode == "train" else "forward + softmax",
                        "l2": "per-step working set (activations + gradients) is ~6 GB >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
     // one n-tile for the whole kernel: scale/shift are loaded once, and with one chunk per warp the BN statistics
     // stay in per-thread registers until the CTA has finished all of its tiles (no shuffles in the tile loop)
     const bool fixed_n = (p.n_tiles == 1);
+    const bool unit_scale = (p.scale == nullptr), identity = (p.scale == nullptr && p.shift == nullptr);
     // chunks per warp; with at most two the statistics of all of them fit in registers (the epilogue warps raise their
     // register allowance with setmaxnreg for this)
     constexpr int CPW = NCHUNK / EPI_COLGROUPS;
@@ -459,15 +460,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         ptx::tmem_ld_wait();
         const int ng = n0 + chunk * 32;
         float f[32];
-        const float4* sc4 = reinterpret_cast<const float4*>(sc + chunk * 32);
-        const float4* sh4 = reinterpret_cast<const float4*>(sh + chunk * 32);
+        if ((EPI == EPI_STORE || EPI == EPI_BNRED) && identity) {
+          // backward-data: no scale, no shift - the accumulator goes out as it is
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 s = sc4[j4], t = sh4[j4];
-          f[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), s.x, t.x);
-          f[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), s.y, t.y);
-          f[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), s.z, t.z);
-          f[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), s.w, t.w);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        } else if (EPI != EPI_HEAD && unit_scale) {
+          // train-mode forward: conv bias only
+          const float4* sh4 = reinterpret_cast<const float4*>(sh + chunk * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = sh4[j4];
+            f[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + t.x;
+            f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + t.y;
+            f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + t.z;
+            f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + t.w;
+          }
+        } else {
+          const float4* sc4 = reinterpret_cast<const float4*>(sc + chunk * 32);
+          const float4* sh4 = reinterpret_cast<const float4*>(sh + chunk * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s = sc4[j4], t = sh4[j4];
+            f[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), s.x, t.x);
+            f[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), s.y, t.y);
+            f[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), s.z, t.z);
+            f[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), s.w, t.w);
+          }
         }
         if (EPI != EPI_STATS && p.relu) {
 #pragma unroll

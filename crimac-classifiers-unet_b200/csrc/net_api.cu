@@ -797,6 +797,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   // epilogues have no slack on the narrow layers (the extra raw loads + mask + sums make them the bottleneck) - a wash,
   // so it is opt-in (CRIMAC_BNRED=1) and the stand-alone HBM-bound reduce kernel stays the default.
   static const bool fuse_bnred = getenv("CRIMAC_BNRED") != nullptr;
+  bool wg_recorded[2] = {false, false};
   auto conv_bwd = [&](int idx, int pre_rows, int target, int* out_rows) -> int {
     if (out_rows) *out_rows = 0;
     Conv3& L = c->conv[idx];
@@ -804,8 +805,9 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     View da{c->GA, nb, H, W, L.cout, L.cout};
     View dr{c->GR[L.gr_idx], nb, H, W, L.cout, L.cout};
     const double px = static_cast<double>(nb) * H * W;
-    // the weight gradient that last read this dRaw buffer (two layers ago) must have finished
-    if (c->overlap) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_wg[L.gr_idx], 0));
+    // the weight gradient that last read this dRaw buffer (two layers ago, in THIS call) must have finished.  Events of
+    // an earlier call are never waited on: the call ends with a join, and a stream capture must not depend on them.
+    if (c->overlap && wg_recorded[L.gr_idx]) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_wg[L.gr_idx], 0));
     {
       ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 3);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
@@ -847,7 +849,10 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       if (r) return r;
       if (L.wg_use_halo && L.wg.nf == 128 && (r = wgrad_run(c, L.wg_center, L.bn_wg, nb, ws))) return r;
     }
-    if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_wg[L.gr_idx], c->side));
+    if (c->overlap) {
+      CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_wg[L.gr_idx], c->side));
+      wg_recorded[L.gr_idx] = true;
+    }
     return 0;
   };
 
