@@ -338,7 +338,27 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(dist, locals().get("trainer"))
+
+
+def _teardown(dist, trainer=None):
+    """Leave the process group without ever hanging the job: drop captured graphs first, then destroy the group under a
+    watchdog that force-exits (status 0: the JSON line is already out) if NCCL teardown blocks."""
+    import gc
+    import torch
+
+    def _bail():
+        sys.stdout.flush()
+        os._exit(0)
+    threading.Timer(30.0, _bail).start()
+    if trainer is not None:
+        trainer._graph = None
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def run_survey(args, model, dev, rank, world, E):
@@ -425,7 +445,7 @@ def run_survey(args, model, dev, rank, world, E):
                          "traffic": None, "note": "whole-chunk figure (all kernels incl. preprocess and stitch) against the sustained bf16 peak"},
             "cpu_baseline": None}), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(dist)
 
 
 if __name__ == "__main__":

@@ -99,11 +99,20 @@ class Trainer:
             yield loss
             i += 1
 
-    def _launch_step(self, x, labels):
-        loss = self.model.train_step_fused(x, labels, self.class_weight)
+    def _launch_fwd_bwd(self, x, labels):
+        """Forward + loss + backward: library kernels only (this is what a CUDA graph captures)."""
+        return self.model.train_step_fused(x, labels, self.class_weight)
+
+    def _launch_update(self):
+        """Gradient exchange + optimizer.  The NCCL all-reduce is never captured in a graph (a captured collective
+        keeps communicator resources alive and made process-group teardown hang in our runs): eager on `world` > 1."""
         grads = self.model._grad_arena
         gscale = reduce_gradients(grads, self.world)  # NCCL over NVLink / NVSwitch
         _engine.sgd_step(self.flat_params, self.flat_momentum, grads, self.lr, self.momentum, gscale)
+
+    def _launch_step(self, x, labels):
+        loss = self._launch_fwd_bwd(x, labels)
+        self._launch_update()
         return loss
 
     def _advance(self):
@@ -127,7 +136,9 @@ class Trainer:
                 torch.cuda.synchronize(x.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):                 # recorded, not executed
-                    self._sloss = self._launch_step(self._sx, self._sy)
+                    self._sloss = self._launch_fwd_bwd(self._sx, self._sy)
+                    if self.world == 1:
+                        self._launch_update()             # single GPU: the SGD kernel rides in the same graph
                 self._graph, self._graph_key = g, key
             except Exception as exc:                      # e.g. a collective that cannot be captured: stay eager
                 import warnings
@@ -140,5 +151,7 @@ class Trainer:
         self._sx.copy_(x)
         self._sy.copy_(labels)
         self._graph.replay()
+        if self.world > 1:
+            self._launch_update()
         self._advance()
         return self._sloss.clone()
