@@ -122,7 +122,9 @@ class Trainer:
 
     def step(self, x, labels):
         """One optimisation step on device tensors; returns the replica's loss as a 0-dim device tensor."""
-        key = (tuple(x.shape), tuple(labels.shape), x.device, self.lr)
+        # the captured graph bakes in device addresses: re-capture if any parameter / buffer storage was replaced
+        ptrs = hash(tuple(t.data_ptr() for t in self.model._state_tensors()))
+        key = (tuple(x.shape), tuple(labels.shape), x.device, self.lr, ptrs)
         shape_key = key[:3]
         if not self.use_cuda_graph or shape_key not in self._eager_done:
             loss = self._launch_step(x, labels)           # first step of a shape: eager (lazy initialisation inside)
