@@ -18,7 +18,7 @@
 // 32-column chunk of the accumulator, so two warps per SM sub-partition hide each other's TMEM / shuffle latency.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.  With one chunk per
 // warp (Cout = 64 layers) the train-mode BatchNorm statistics stay in registers for the CTA's lifetime.
-#include "common.cuh"
+#include "host_util.h"
 #include "ptx.cuh"
 #include "devfn.cuh"
 #include <cstdlib>
@@ -687,12 +687,7 @@ template <int BLOCK_N, int EPI, bool HALO, bool BMN>
 cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, HALO>;
   auto kern = conv_igemm_kernel<BLOCK_N, EPI, HALO, BMN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES); e != cudaSuccess) return e;
   if ((EPI == EPI_STATS || EPI == EPI_BNRED) && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (HALO && BLOCK_N != 256) {

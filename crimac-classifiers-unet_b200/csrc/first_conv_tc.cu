@@ -450,11 +450,6 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_fold_kernel(const float*
   }
 }
 
-template <typename Kern>
-cudaError_t set_smem(Kern kern, int bytes) {
-  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-
 int x_map_for(CUtensorMap* map, bf16* xs, int NB, int H, int W, int P) {
   return make_split_input_map(map, xs, P / 4, NB, H, W);
 }
@@ -479,12 +474,7 @@ cudaError_t launch_first_conv_tc(const float* x, bf16* xs, const float* w, const
   const long npix = static_cast<long>(H) * W;
 #define FC(C)                                                                                                      \
   if (cin == C) {                                                                                                  \
-    static bool done = false;                                                                                      \
-    if (!done) {                                                                                                   \
-      cudaError_t e = set_smem(first_conv_tc_kernel<C>, fc_fwd_smem<C>());                                         \
-      if (e != cudaSuccess) return e;                                                                              \
-      done = true;                                                                                                 \
-    }                                                                                                              \
+    if (cudaError_t e = ensure_dynamic_smem(first_conv_tc_kernel<C>, fc_fwd_smem<C>()); e != cudaSuccess) return e; \
     long blocks = (NB * npix + 255) / 256;                                                                         \
     if (blocks > 148 * 8) blocks = 148 * 8;                                                                        \
     split_input_kernel<C><<<static_cast<int>(blocks), 256, 0, st>>>(x, npix, NB, xs);                              \
@@ -508,12 +498,8 @@ cudaError_t launch_first_conv_wgrad_tc(const bf16* xs, View draw, int cin, float
   const int grid = first_conv_tc_grid(draw.N, draw.H, draw.W);
 #define FW(C)                                                                                                      \
   if (cin == C) {                                                                                                  \
-    static bool done = false;                                                                                      \
-    if (!done) {                                                                                                   \
-      cudaError_t e = set_smem(first_conv_wgrad_tc_kernel<C>, fc_wg_smem<C>());                                    \
-      if (e != cudaSuccess) return e;                                                                              \
-      done = true;                                                                                                 \
-    }                                                                                                              \
+    if (cudaError_t e = ensure_dynamic_smem(first_conv_wgrad_tc_kernel<C>, fc_wg_smem<C>()); e != cudaSuccess)     \
+      return e;                                                                                                    \
     CUtensorMap xmap;                                                                                              \
     if (x_map_for(&xmap, const_cast<bf16*>(xs), draw.N, draw.H, draw.W, FcCfg<C>::P) != 0)                         \
       return cudaErrorInvalidValue;                                                                                \

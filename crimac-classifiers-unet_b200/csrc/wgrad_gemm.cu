@@ -423,12 +423,7 @@ template <int BLOCK_N>
 cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   using Cfg = WgCfg<BLOCK_N>;
   auto kern = wgrad_gemm_kernel<BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES); e != cudaSuccess) return e;
   dim3 grid(p.taps * p.m_tiles * p.n_tiles, p.splits);
   kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
@@ -446,12 +441,7 @@ cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t st
 namespace {
 template <int NF>
 cudaError_t launch_wh(const WgradHaloParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, WhCfg<NF>::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(wgrad_halo_kernel<NF>, WhCfg<NF>::SMEM); e != cudaSuccess) return e;
   dim3 grid(p.s_tiles * (p.Cf / NF), p.splits);
   wgrad_halo_kernel<NF><<<grid, 256, WhCfg<NF>::SMEM, stream>>>(p);
   return cudaGetLastError();
