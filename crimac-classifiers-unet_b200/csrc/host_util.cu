@@ -1,4 +1,6 @@
 #include "host_util.h"
+#include <mutex>
+#include <unordered_map>
 #include <cudaTypedefs.h>
 #include <mutex>
 
@@ -91,6 +93,26 @@ int make_weight_map(CUtensorMap* out, const bf16* w, int rows, int cols, int box
     return 2;
   }
   return 0;
+}
+
+cudaError_t ensure_dynamic_smem_impl(const void* kern, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, uint64_t> done;  // kernel -> bit mask of devices already configured
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(kern);
+    if (bit && it != done.end() && (it->second & bit)) return cudaSuccess;
+  }
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && bit) {
+    std::lock_guard<std::mutex> lk(mu);
+    done[kern] |= bit;
+  }
+  return e;
 }
 
 int device_num_sms() {

@@ -54,17 +54,11 @@ cudaError_t launch_wgrad_unpack_all(UnpackTable& t, cudaStream_t stream);
 
 int device_num_sms();
 // Opt a kernel in to `bytes` of dynamic shared memory once per (kernel, device): the attribute is per device, and one
-// process may drive several devices.
+// process may drive several devices.  (Keyed by the function ADDRESS: kernels with the same signature share one type.)
+cudaError_t ensure_dynamic_smem_impl(const void* kern, int bytes);
 template <typename Kern>
 inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
-  static bool done[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
-  return e;
+  return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), bytes);
 }
 bool crimac_profiling();  // per-launch event timing is on: kernels are then kept on ONE stream so that times are isolated
 
