@@ -1173,11 +1173,13 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int C = raw.C;
   if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
   const int grid = reduce_grid(raw);
+  // the reduce kernel fits three blocks per SM: one full wave (a 592-block grid would leave a 1/3-occupancy tail wave)
+  const int grid_r = grid < 148 * 3 ? grid : 148 * 3;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
   if (pre_rows <= 0)
-    bn_bwd_reduce_kernel<<<grid, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
-  partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, pre_rows > 0 ? pre_rows : grid, C, count, dbeta,
+    bn_bwd_reduce_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
+  partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, pre_rows > 0 ? pre_rows : grid_r, C, count, dbeta,
                                                                 dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd,
                                                                 dbias);
   bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);

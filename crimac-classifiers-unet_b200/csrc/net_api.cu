@@ -479,7 +479,9 @@ void set_batch(WgradParams& p, int nb) {
   p.NB = nb;
   p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
   const int tiles = p.taps * p.m_tiles * p.n_tiles;
-  int splits = (2 * device_num_sms() + tiles - 1) / tiles;
+  // one CTA per SM is resident: aim for (at most) two FULL waves - rounding the split factor UP would leave a third,
+  // almost empty wave (e.g. 18 tiles x 17 splits = 306 CTAs on 148 SMs)
+  int splits = (2 * device_num_sms()) / tiles;
   if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -489,7 +491,7 @@ void set_batch(WgradHaloParams& p, int nb) {
   p.NB = nb;
   p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
   const int tiles = p.s_tiles * (p.nf == 128 ? p.Cf / 128 : p.f_tiles);
-  int splits = (2 * device_num_sms() + tiles - 1) / tiles;
+  int splits = (2 * device_num_sms()) / tiles;
   if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
   if (splits < 1) splits = 1;
   p.splits = splits;
