@@ -215,7 +215,8 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 // division, several independent 16-byte loads in flight.
 template <bool POOL>
 __global__ void __launch_bounds__(256) bn_apply_kernel(View raw, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, View act, View pool) {
+                                                       const float* __restrict__ shift, View act, View pool,
+                                                       uint16_t* __restrict__ pool_arg) {
   const int groups = raw.C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   float sc[8], sh[8];
@@ -259,6 +260,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(View raw, const float* __
       for (int w = 0; w < 4; ++w)
         rv[w] = __ldcs(reinterpret_cast<const uint4*>(raw.ptr + (p00 + (w >> 1) * raw.W + (w & 1)) * raw.pitch + g * 8));
       uint32_t mx[4] = {0, 0, 0, 0};
+      float best[8];
+      uint32_t arg = 0;  // 2 bits per channel: index (row*2 + col) of the FIRST maximal window element (PyTorch's tie-break)
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t rw[4] = {rv[w].x, rv[w].y, rv[w].z, rv[w].w};
@@ -268,9 +271,24 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(View raw, const float* __
           const float2 r = unpack_bf16x2(rw[h]);
           pk[h] = pack_bf16x2(fmaxf(fmaf(r.x, sc[2 * h], sh[2 * h]), 0.f), fmaxf(fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]), 0.f));
           mx[h] = w == 0 ? pk[h] : bf16x2_max(mx[h], pk[h]);
+          const float2 v = unpack_bf16x2(pk[h]);  // compare the stored (rounded) activations, as the backward used to
+          if (w == 0) {
+            best[2 * h] = v.x;
+            best[2 * h + 1] = v.y;
+          } else {
+            if (v.x > best[2 * h]) {
+              best[2 * h] = v.x;
+              arg = (arg & ~(3u << (4 * h))) | (static_cast<uint32_t>(w) << (4 * h));
+            }
+            if (v.y > best[2 * h + 1]) {
+              best[2 * h + 1] = v.y;
+              arg = (arg & ~(3u << (4 * h + 2))) | (static_cast<uint32_t>(w) << (4 * h + 2));
+            }
+          }
         }
         store16(act.ptr + (p00 + (w >> 1) * raw.W + (w & 1)) * act.pitch + g * 8, pk);
       }
+      if (pool_arg != nullptr) pool_arg[static_cast<size_t>(pp) * groups + g] = static_cast<uint16_t>(arg);
       store16(pool.ptr + static_cast<size_t>(pp) * pool.pitch + g * 8, mx);
     }
   }
@@ -854,51 +872,38 @@ __global__ void __launch_bounds__(256) view_colsum_kernel(View v, float* partial
 
 // ============================================================================ max-pool backward + skip gradient
 // dA[2x2 window] = dSkip[window] + (first maximal element of the window ? dP : 0)     (autograd of unet.py:86,92,132)
-__global__ void __launch_bounds__(256) pool_bwd_add_kernel(View act, View dpool, View dskip, View dact) {
-  const int groups = act.C >> 3;
-  const int Ho = act.H >> 1, Wo = act.W >> 1;
-  const long total = static_cast<long>(act.N) * Ho * Wo * groups;
+// The arg-max comes from the 2-bit-per-channel map the forward BN-apply pass wrote (16 bits per 8 channels), so the
+// full-resolution activation is not read again.
+__global__ void __launch_bounds__(256) pool_bwd_add_kernel(const uint16_t* __restrict__ pool_arg, View dpool, View dskip,
+                                                           View dact) {
+  const int groups = dact.C >> 3;
+  const int Ho = dact.H >> 1, Wo = dact.W >> 1;
+  const long total = static_cast<long>(dact.N) * Ho * Wo * groups;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(i % groups);
     long pix = i / groups;
+    const long pp = pix;
     const int xo = static_cast<int>(pix % Wo);
     pix /= Wo;
     const int yo = static_cast<int>(pix % Ho);
     const int n = static_cast<int>(pix / Ho);
-    float a[4][8], dp[8];
-    long pidx[4];
+    float dp[8];
+    load8(dpool.ptr + pp * dpool.pitch + g * 8, dp);
+    const uint32_t arg = pool_arg[pp * groups + g];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      pidx[q] = (static_cast<long>(n) * act.H + 2 * yo + (q >> 1)) * act.W + 2 * xo + (q & 1);
-      load8(act.ptr + pidx[q] * act.pitch + g * 8, a[q]);
-    }
-    load8(dpool.ptr + ((static_cast<long>(n) * Ho + yo) * Wo + xo) * dpool.pitch + g * 8, dp);
-    int arg[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int best = 0;
-      float bv = a[0][j];
-#pragma unroll
-      for (int q = 1; q < 4; ++q)
-        if (a[q][j] > bv) {
-          bv = a[q][j];
-          best = q;
-        }
-      arg[j] = best;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+      const long p = (static_cast<long>(n) * dact.H + 2 * yo + (q >> 1)) * dact.W + 2 * xo + (q & 1);
       float o[8];
       if (dskip.ptr != nullptr)
-        load8(dskip.ptr + pidx[q] * dskip.pitch + g * 8, o);
+        load8(dskip.ptr + p * dskip.pitch + g * 8, o);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += (arg[j] == q) ? dp[j] : 0.f;
-      store8(dact.ptr + pidx[q] * dact.pitch + g * 8, o);
+      for (int j = 0; j < 8; ++j) o[j] += (((arg >> (2 * j)) & 3u) == static_cast<uint32_t>(q)) ? dp[j] : 0.f;
+      store8(dact.ptr + p * dact.pitch + g * 8, o);
     }
   }
 }
@@ -1095,16 +1100,17 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
   bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, conv_bias, eps, C, scale, shift);
   return cudaGetLastError();
 }
-cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, cudaStream_t st) {
+cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, uint16_t* pool_arg,
+                            cudaStream_t st) {
   if (raw.C % 8 != 0 || raw.C / 8 > 256) return cudaErrorInvalidValue;
   if (static_cast<long>(raw.N) * raw.H * raw.W > 0x7fffffffL) return cudaErrorInvalidValue;  // 32-bit pixel index
   const int ppb = 256 / (raw.C / 8);
   if (pool.ptr != nullptr) {
     const long items = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2);
-    bn_apply_kernel<true><<<grid_for(items, ppb), 256, 0, st>>>(raw, scale, shift, act, pool);
+    bn_apply_kernel<true><<<grid_for(items, ppb), 256, 0, st>>>(raw, scale, shift, act, pool, pool_arg);
   } else {
     const long items = static_cast<long>(raw.N) * raw.H * raw.W;
-    bn_apply_kernel<false><<<grid_for((items + 3) / 4, ppb), 256, 0, st>>>(raw, scale, shift, act, pool);
+    bn_apply_kernel<false><<<grid_for((items + 3) / 4, ppb), 256, 0, st>>>(raw, scale, shift, act, pool, nullptr);
   }
   return cudaGetLastError();
 }
@@ -1195,9 +1201,9 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
                                                                 nullptr, nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
-cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st) {
-  const long items = static_cast<long>(act.N) * (act.H / 2) * (act.W / 2) * (act.C / 8);
-  pool_bwd_add_kernel<<<grid_for(items, 256), 256, 0, st>>>(act, dpool, dskip, dact);
+cudaError_t launch_pool_bwd_add(const uint16_t* pool_arg, View dpool, View dskip, View dact, cudaStream_t st) {
+  const long items = static_cast<long>(dact.N) * (dact.H / 2) * (dact.W / 2) * (dact.C / 8);
+  pool_bwd_add_kernel<<<grid_for(items, 256), 256, 0, st>>>(pool_arg, dpool, dskip, dact);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_conv3x3_all(PackTable& t, cudaStream_t st) {

@@ -95,7 +95,9 @@ cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double
                                float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st);
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                                 const float* conv_bias, float eps, int C, float* scale, float* shift, cudaStream_t st);
-cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, cudaStream_t st);
+// pool_arg (optional, with pool): uint16 per (pooled pixel, 8-channel group): 2-bit arg-max per channel for the backward
+cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, View act, View pool, uint16_t* pool_arg,
+                            cudaStream_t st);
 cudaError_t launch_head_fwd(View act, const float* hw, const float* hb, int ncls, float* logits, cudaStream_t st);
 int ce_blocks();
 cudaError_t launch_ce(const float* logits, const long long* labels, const float* cw, int ncls, int NB, long HW,
@@ -113,7 +115,7 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
                           float* partials, float* c1c2, const float* gscale, int pre_rows, cudaStream_t st);
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st);
-cudaError_t launch_pool_bwd_add(View act, View dpool, View dskip, View dact, cudaStream_t st);
+cudaError_t launch_pool_bwd_add(const uint16_t* pool_arg, View dpool, View dskip, View dact, cudaStream_t st);
 // fp32 parameters -> bf16 GEMM operands for every layer of one kind in ONE launch (item0 is filled by the launcher)
 struct PackEntry {
   const float* w;

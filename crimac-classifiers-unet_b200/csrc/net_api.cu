@@ -39,6 +39,7 @@ struct Conv3 {
   int s_w = 0, s_b = 0, s_g = 0, s_beta = 0, s_rm = 0, s_rv = 0, s_nbt = 0;
   int g_w = 0, g_b = 0, g_g = 0, g_beta = 0;
   View in{}, raw{}, act{}, pool{}, gin{};
+  uint16_t* pool_arg = nullptr;  // train: 2-bit arg-max map of the fused max-pool (one uint16 per 8 channels)
   bf16* w_fwd = nullptr;  // backward-data reads the same matrix as an MN-major operand
   float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
   int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
@@ -257,6 +258,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     L.mean = bump.arr<float>(L.cout);
     L.invstd = bump.arr<float>(L.cout);
     if (train) L.raw = dense(L.level, L.cout);
+    if (train && L.pool.C > 0)  // encoder second convs below the deepest level (same test in the sizing pass)
+      L.pool_arg = bump.arr<uint16_t>(static_cast<size_t>(B) * (level_h(c, L.level) / 2) * (level_w(c, L.level) / 2) * (L.cout / 8));
     const size_t rows = L.first ? 148 * 8 : 256;  // >= first_conv_grid() / >= number of SMs (one partial row per CTA)
     if (rows * 2 * L.cout > max_stats) max_stats = rows * 2 * L.cout;
     L.bn_fwd = pick_bn(L.cout);
@@ -676,7 +679,7 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
       View pool = L.pool;
       if (pool.ptr) pool.N = nb;
       ProfScope ps("bn_apply", 0, px * L.cout * (pool.ptr ? 4.5 : 4.0), st);
-      CRIMAC_CHECK_CUDA(launch_bn_apply(raw, L.scale, L.shift, with_batch(L.act, nb), pool, st));
+      CRIMAC_CHECK_CUDA(launch_bn_apply(raw, L.scale, L.shift, with_batch(L.act, nb), pool, L.pool_arg, st));
     } else {
       const double px = static_cast<double>(nb) * H * W;
       if (L.first) {
@@ -910,8 +913,8 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       View dpool{c->GP, nb, level_h(c, l + 1), level_w(c, l + 1), L2.cout, L2.cout};
       View dskip{c->dcat[j] + L2.cout, nb, level_h(c, l), level_w(c, l), L2.cout, 2 * L2.cout};
       View dact{c->GA, nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
-      ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 3.25, st);
-      CRIMAC_CHECK_CUDA(launch_pool_bwd_add(with_batch(L2.act, nb), dpool, dskip, dact, st));
+      ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 2.28, st);
+      CRIMAC_CHECK_CUDA(launch_pool_bwd_add(L2.pool_arg, dpool, dskip, dact, st));
       rows = 0;
     }
     int r1 = 0;
