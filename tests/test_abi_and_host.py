@@ -155,3 +155,15 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_flop_accounting_matches_the_survey_numbers():
+    """bench.py's generic FLOP counter reproduces SURVEY.md section 8(d) / BASELINE.md exactly (4x256x256 and 6x512x512)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("crimac_bench", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert abs(b.unet_gflop(4, 256, False) - 96.42704896) < 1e-6 and abs(b.GFLOP_INFER - 96.42704896) < 1e-9
+    assert abs(b.unet_gflop(4, 256, True) - 288.979156992) < 1e-6 and abs(b.GFLOP_TRAIN - 288.979156992) < 1e-9
+    assert abs(b.unet_gflop(6, 512, False) - 386.312175616) < 1e-6
+    assert abs(b.unet_gflop(6, 512, True) - 1157.12458752) < 1e-6
