@@ -168,7 +168,6 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
-    from oracle import unet_oracle as O   # synthetic workload generators only (and the cpu_baseline leg below)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -181,6 +180,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     load_package()
     import crimac_unet_b200.engine as E
+    import crimac_unet_b200.synthetic as O   # workload generators; nothing under oracle/ is imported by this arm
     import crimac_unet_b200.models.unet as M
     from crimac_unet_b200.trainer import Trainer
 
