@@ -83,6 +83,7 @@ struct crimac_ctx {
   std::vector<bf16*> dcat;
   float* stats = nullptr;
   float* red_partials = nullptr;
+  float* colsum_partials = nullptr;  // ConvTranspose bias-gradient partials (side stream: must not share red_partials)
   float* c1c2 = nullptr;
   float* wg_arena = nullptr;   // all layers' weight-gradient scratch, contiguous
   size_t wg_arena_bytes = 0;
@@ -300,6 +301,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     const int cmax = chan(D - 1);
     c->stats = bump.arr<float>(max_stats);
     c->red_partials = bump.arr<float>(static_cast<size_t>(reduce_blocks()) * 2 * cmax);
+    c->colsum_partials = bump.arr<float>(static_cast<size_t>(reduce_blocks()) * cmax);
     c->c1c2 = bump.arr<float>(2 * cmax);
     {
       // one contiguous arena, one region per layer: the unpack kernel re-zeroes behind itself, so no per-layer memset
@@ -878,11 +880,18 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     if ((rc = conv_bwd(c->dec2[j], rows, c->dec1[j], &r1))) return rc;   // dgrad -> dA of dec1[j]
     if ((rc = conv_bwd(c->dec1[j], r1, -1, nullptr))) return rc;         // dgrad wrote dCat_j
     ConvT& U = c->up[j];
-    {
-      ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, st, 2);
-      CRIMAC_CHECK_CUDA(launch_view_colsum(with_batch(U.gout, nb), c->red_partials, grads[U.g_b], 0, st));
+    // everything that only READS dCat_j and is off the critical path goes to the side stream: the ConvTranspose bias
+    // gradient (HBM-bound column sum, own partial buffer) and its weight gradient; the main stream continues with the
+    // backward-data GEMM
+    cudaStream_t ss = c->overlap ? c->side : st;
+    if (c->overlap) {
+      CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_cat, st));
+      CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->side, c->ev_cat, 0));
     }
-    if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_cat, st));
+    {
+      ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, ss, 2);
+      CRIMAC_CHECK_CUDA(launch_view_colsum(with_batch(U.gout, nb), c->colsum_partials, grads[U.g_b], 0, ss));
+    }
     {
       ConvParams p = U.dgrad;
       set_batch(p, nb);
@@ -902,8 +911,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
       CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, epi, sms, st));
     }
-    if (c->overlap) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->side, c->ev_cat, 0));
-    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, c->overlap ? c->side : st))) return rc;
+    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, ss))) return rc;
   }
   // encoder, deepest level first
   for (int l = D - 1; l >= 0; --l) {
