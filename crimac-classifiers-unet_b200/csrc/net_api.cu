@@ -9,6 +9,11 @@
 //          channels [0,C_l), the encoder's second conv of level l writes its activation into [C_l,2*C_l) — torch.cat
 //          (unet.py:132) never happens as a copy.
 //   train mode additionally keeps every conv's raw (pre-BN) output for the BN/ReLU backward.
+//
+// Streams: everything runs on the caller's stream except the weight-gradient GEMMs and the ConvTranspose bias sums of
+// crimac_backward, which go to a context-owned side stream (fork/join with events recorded inside the same call, so a
+// whole train step can be captured in a CUDA graph: trainer.py does).  While crimac_profile_enable(1) is on, the side
+// stream is not used and every launch is bracketed by events on the caller's stream.
 #include "host_util.h"
 #include "../../include/crimac_b200.h"
 #include <vector>
