@@ -6,6 +6,7 @@ by putting this directory on ``sys.path`` and doing ``import models.unet as mode
 (reference pipeline_train_predict/pipeline.py:32).
 
 Contents: ``csrc/`` hand-written sm_100a kernels + the C-ABI (``include/crimac_b200.h``), ``lib.py``/``engine.py`` the
-ctypes host side, ``models/unet.py`` the drop-in nn.Module surface, ``predict.py`` the sliding-window driver.
+ctypes host side, ``models/unet.py`` the drop-in nn.Module surface, ``predict.py`` the sliding-window driver,
+``train_patches.py`` the on-device training-sample feeder.
 """
-__all__ = ["lib", "engine", "models", "predict"]
+__all__ = ["lib", "engine", "models", "predict", "train_patches"]

@@ -178,6 +178,39 @@ def stitch(probs, centres, nan_mask, out, ping_start, overlap, labels=None, seab
     return out
 
 
+def train_patches(sv, labels, centres, flags, patch_hw, noise_mult=None, seed=0, thr_freq=None, thr=(1e-7, 1e-4),
+                  scaled=False, border_zero=False, out=None, labels_out=None):
+    """One batch of training samples from a survey resident in HBM (crimac_train_patches).
+    sv: fp32 (F,P,R) device tensor in the zarr store's [frequency][ping][range] order; labels: fp32 (P,R) raw
+    annotation categories; centres: int32 (n,2) (range, ping); flags: uint8 (n), bit0 = noise, bit1 = flip."""
+    L = _lib.load()
+    F, P, R = sv.shape
+    n = centres.shape[0]
+    ph, pw = patch_hw
+    for t, dt, name in ((sv, torch.float32, "sv"), (labels, torch.float32, "labels"), (centres, torch.int32, "centres"),
+                        (flags, torch.uint8, "flags")):
+        if t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {dt} CUDA tensor")
+    if tuple(labels.shape) != (P, R) or tuple(centres.shape) != (n, 2) or tuple(flags.shape) != (n,):
+        raise ValueError("labels must be (P,R), centres (n,2), flags (n)")
+    if noise_mult is not None and (tuple(noise_mult.shape) != (n, F, ph, pw) or noise_mult.dtype != torch.float32
+                                   or not noise_mult.is_cuda or not noise_mult.is_contiguous()):
+        raise ValueError("noise_mult must be a contiguous fp32 CUDA tensor of shape (n,F,ph,pw)")
+    if out is None:
+        out = torch.empty((n, F, ph, pw), dtype=torch.float32, device=sv.device)
+    if labels_out is None:
+        labels_out = torch.empty((n, ph, pw), dtype=torch.int64, device=sv.device)
+    thr_freq = F - 1 if thr_freq is None else int(thr_freq)
+    _lib.check(
+        L.crimac_train_patches(_lib.ptr(sv), _lib.ptr(labels), F, P, R, _lib.ptr(centres), _lib.ptr(flags),
+                               _lib.ptr(noise_mult), ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), n, ph, pw,
+                               thr_freq, ctypes.c_double(thr[0]), ctypes.c_double(thr[1]), int(bool(scaled)),
+                               int(bool(border_zero)), _lib.ptr(out), _lib.ptr(labels_out), _lib.stream_ptr()),
+        "crimac_train_patches",
+    )
+    return out, labels_out
+
+
 def launch_count():
     L = _lib.load()
     L.crimac_launch_count.restype = ctypes.c_ulonglong

@@ -99,6 +99,14 @@ class Trainer:
             yield loss
             i += 1
 
+    def fit_survey(self, feeder, steps):
+        """Runs `steps` optimisation steps on batches drawn on the device by a train_patches.SurveyPatchFeeder (the
+        device-side replacement of the reference's DataLoader + Dataset.__getitem__, pipeline.py:161-178) and yields
+        each step's loss as a 0-dim device tensor.  Everything is stream-ordered: no host synchronisation per step."""
+        for _ in range(int(steps)):
+            x, labels = feeder.next_batch()
+            yield self.step(x, labels)
+
     def _launch_fwd_bwd(self, x, labels):
         """Forward + loss + backward: library kernels only (this is what a CUDA graph captures)."""
         return self.model.train_step_fused(x, labels, self.class_weight)

@@ -12,6 +12,8 @@
  *   crimac_train_step      pipeline.py:171-177 in one call
  *   crimac_sgd_step        pipeline.py:156,178 (optim.SGD(momentum) step)
  *   crimac_preprocess      batch/dataset.py:192-205 + utils/np.py:362-375 + batch/data_transforms/{remove_nan_inf,db_with_limits}.py
+ *   crimac_train_patches   batch/dataset.py:75-108,358-407 (Dataset.__getitem__ / get_crop_zarr) + batch/data_augmentation/*.py +
+ *                          batch/label_transforms/{refine_label_boundary,convert_label_indexing}.py + data transforms
  *   crimac_stitch          pipeline_train_predict/save_predict.py:41-65 (fill_out_array) + label masks of
  *                          batch/label_transforms/mask_label_{overlap,seabed}.py
  *   crimac_forward_infer_fp32   the same forward in plain fp32 (validation mode, 1e-4 parity)
@@ -102,6 +104,25 @@ int crimac_preprocess(const float* sv_dev, int F, int R, int P, int data_ping0, 
 int crimac_stitch(const float* probs_dev, int n, int n_classes, int ph, int pw, const int32_t* centres_dev,
                   const uint8_t* nan_dev, const int16_t* labels_dev, const int32_t* seabed_dev, int seabed_pad,
                   int overlap, int ping_start, int Pc, int R, const int32_t* cls, int K, void* out_dev, void* stream);
+
+/* Training-sample path: one batch of random crops with augmentation, label refinement
+ * and the dB transform, from a survey resident in HBM in the zarr store's own order.
+ *   sv_dev      fp32 (F, P, R) [frequency][ping][range];  labels_dev fp32 (P, R) raw annotation category per sample
+ *               (0 background, 27 sandeel, 1 other, other species > 0, NaN / -100 = no data)
+ *   centres_dev int32 (n,2) crop centres (range, ping): sample (py,px) of crop b is survey sample
+ *               (cy - ph/2 + 1 + py, cx - pw/2 + 1 + px) (utils/np.py:378-380); outside the survey -> sv 0, label -100
+ *   flags_dev   uint8 (n): bit0 = add_noise fires for this crop, bit1 = flip_x_axis fires (the two coin flips of
+ *               add_noise.py:25 / flip_x_axis.py:22 are the caller's)
+ *   noise_mult_dev  optional fp32 (n,F,ph,pw): explicit multipliers in un-flipped crop coordinates (replay / tests);
+ *               NULL = draw add_noise.py:28-38's distribution from Philox4x32-10 keyed by (noise_seed, sample index)
+ *   thr_freq, thr_lo, thr_hi  refine_label_boundary's threshold channel index and (1e-7, 1e-4) window on linear sv
+ *   scaled      0: db_with_limits, 1: db_with_limits_scaled;  border_zero: set_data_border_value on the final labels
+ *   x_out       fp32 (n,F,ph,pw) network input;  labels_out int64 (n,ph,pw) in {0,1,2,-100}
+ * ph == pw, multiples of 32.  Two launches on `stream`, no allocation, no synchronisation. */
+int crimac_train_patches(const float* sv_dev, const float* labels_dev, int F, int P, int R, const int32_t* centres_dev,
+                         const uint8_t* flags_dev, const float* noise_mult_dev, uint64_t noise_seed, int n, int ph,
+                         int pw, int thr_freq, double thr_lo, double thr_hi, int scaled, int border_zero,
+                         float* x_out, int64_t* labels_out, void* stream);
 
 /* ---- fp32 VALIDATION mode of the eval forward (models/unet.py:327-343 + pipeline.py:218): an independent plain-fp32
  * CUDA-core implementation reading the fp32 parameters directly (no packing, no tensor cores, no bf16).  ~50x slower

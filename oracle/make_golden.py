@@ -6,6 +6,8 @@ Vectors:
                      all gradients / updated BN buffers (models/unet.py + pipeline.py:135-138,176-177)
   unet_d5.npz        reference UNet_Baseline(3, 4) (the production depth): weights regenerated from seed 0 (checksums
                      stored), eval + train logits, loss, a subset of gradients
+  pipeline_train.npz reference get_crop_zarr + add_noise + flip_x_axis + refine_label_boundary + convert_label_indexing +
+                     remove_nan_inf + db_with_limits(_scaled) + set_data_border_value on scripted random decisions
   pipeline_small.npz reference DatasetGriddedReader (preload branch) + remove_nan_inf + db_with_limits +
                      mask_label_seabed + mask_label_overlap + fill_out_array, driven by a fake in-memory zarr reader
 """
@@ -125,11 +127,16 @@ class FakeZarrReader:
         self.time_vector = np.arange(sv.shape[1])
         self.range_vector = np.arange(sv.shape[2])
 
-    def get_data_slice(self, idx_ping, n_pings, frequencies=None, drop_na=False, return_numpy=True):
-        return self.sv[:, idx_ping:idx_ping + n_pings, :].copy()
+    def get_data_slice(self, idx_ping, n_pings, idx_range=None, n_range=None, frequencies=None, drop_na=False,
+                       return_numpy=True):
+        r0 = 0 if idx_range is None else idx_range
+        r1 = self.shape[1] if n_range is None else r0 + n_range
+        return self.sv[:, idx_ping:idx_ping + n_pings, r0:r1].copy()
 
-    def get_label_slice(self, idx_ping, n_pings, return_numpy=True, **kw):
-        return self.labels[idx_ping:idx_ping + n_pings, :].copy()
+    def get_label_slice(self, idx_ping, n_pings, idx_range=None, n_range=None, return_numpy=True, **kw):
+        r0 = 0 if idx_range is None else idx_range
+        r1 = self.shape[1] if n_range is None else r0 + n_range
+        return self.labels[idx_ping:idx_ping + n_pings, r0:r1].copy()
 
     def get_seabed(self, idx_ping, n_pings=1, idx_range=None, n_range=None, return_numpy=True):
         s = self.seabed_idx[idx_ping:idx_ping + n_pings]
@@ -225,6 +232,124 @@ def golden_pipeline():
     np.savez_compressed(os.path.join(OUT, "pipeline_small.npz"), **out)
 
 
+class _ScriptedRandom:
+    """Stands in for numpy's global generator while the reference's add_noise / flip_x_axis run, so that their random
+    decisions are known: randint -> the scripted coin, binomial / uniform -> the scripted fields."""
+
+    def __init__(self):
+        self.coins, self.binomials, self.uniforms = [], [], []
+
+    def __enter__(self):
+        self.saved = (np.random.randint, np.random.binomial, np.random.uniform)
+        np.random.randint = lambda *a, **k: self.coins.pop(0)
+        np.random.binomial = lambda *a, **k: self.binomials.pop(0)
+        np.random.uniform = lambda *a, **k: self.uniforms.pop(0)
+        return self
+
+    def __exit__(self, *exc):
+        np.random.randint, np.random.binomial, np.random.uniform = self.saved
+
+
+def train_survey(seed=11, F=3, NP=150, R=110):
+    """Small synthetic survey for the training-sample path: schools of sandeel (27), other (1) and an unused species
+    (12) whose threshold-frequency response straddles refine_label_boundary's (1e-7, 1e-4) window, NaN / inf holes."""
+    rng = np.random.default_rng(seed)
+    sv = (10.0 ** rng.uniform(-9, -2, size=(F, NP, R))).astype(np.float32)
+    labels = np.zeros((NP, R), dtype=np.float32)
+    yy, xx = np.meshgrid(np.arange(NP), np.arange(R), indexing="ij")
+    for (cy, cx, ry, rx, val) in [(30, 40, 14, 20, 27), (70, 75, 18, 12, 1), (110, 30, 10, 16, 12), (5, 100, 9, 9, 27),
+                                  (140, 8, 12, 10, 1)]:
+        blob = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
+        labels[blob] = val
+        # inside a school the last frequency is mostly inside the window, with speckle outside it
+        inside = 10.0 ** rng.uniform(-6.8, -4.2, size=blob.sum())
+        speckle = rng.random(blob.sum())
+        inside = np.where(speckle < 0.25, 10.0 ** rng.uniform(-9, -7.2, size=blob.sum()), inside)
+        inside = np.where(speckle > 0.9, 10.0 ** rng.uniform(-3.9, -2, size=blob.sum()), inside)
+        sv[F - 1][blob] = inside.astype(np.float32)
+    sv[0, 60:63, 20:50] = np.nan
+    sv[F - 1, 28:31, 35:45] = np.nan
+    sv[1, 100, 60:64] = np.inf
+    labels[90:94, 90:100] = np.nan
+    labels[20:24, 100:104] = -1
+    return sv, labels
+
+
+def golden_train_pipeline():
+    """tests/golden/pipeline_train.npz: the reference's Dataset.__getitem__ composition (dataset.py:75-108 with
+    train.py:56-60's functions) on scripted random decisions."""
+    from oracle import pipeline_oracle as P
+    _stub_missing_modules()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from batch.dataset import get_crop_zarr
+    from batch.data_augmentation.add_noise import add_noise
+    from batch.data_augmentation.flip_x_axis import flip_x_axis
+    from batch.label_transforms.refine_label_boundary import refine_label_boundary
+    from batch.label_transforms.convert_label_indexing import convert_label_indexing
+    from batch.data_transforms.remove_nan_inf import remove_nan_inf
+    from batch.data_transforms.db_with_limits import db_with_limits, db_with_limits_scaled
+    from batch.data_transforms.set_data_border_value import set_data_border_value
+
+    sv, labels = train_survey()
+    F, NP, R = sv.shape
+    freqs = [18, 38, 200]
+    reader = FakeZarrReader(sv, labels, np.zeros(NP, dtype=int))
+    patch = [64, 64]
+    centres = np.array([[40, 30], [75, 70], [30, 110], [100, 5], [8, 140], [55, 75], [105, 149], [400, 400],
+                        [31, 31], [78, 118]])
+    rng = np.random.default_rng(3)
+    noise_on = np.array([1, 0, 1, 1, 0, 1, 0, 1, 0, 1])
+    flip = np.array([0, 1, 1, 0, 0, 1, 1, 0, 0, 1])
+    refine = refine_label_boundary(frequencies=freqs, threshold_freq=freqs[-1])
+    out = {"sv": sv, "labels": labels, "centres": centres.astype(np.int32), "noise_on": noise_on.astype(np.uint8),
+           "flip": flip.astype(np.uint8), "patch": np.array(patch)}
+    mults, datas, labs, datas_scaled, datas_border = [], [], [], [], []
+    for i, c in enumerate(centres):
+        shape = (F, patch[0], patch[1])
+        change = rng.binomial(1, 0.05, shape)
+        inc = rng.binomial(1, 0.5, shape)
+        u_hi = rng.uniform(1, 10, shape).astype(np.float32).astype(np.float64)
+        u_lo = rng.uniform(0, 1, shape).astype(np.float32).astype(np.float64)
+        mult = np.where(change == 1, np.where(inc == 1, u_hi, u_lo), 1.0).astype(np.float32)
+        data, lab = get_crop_zarr(reader, list(c), patch, freqs)
+        with _ScriptedRandom() as sr:
+            sr.coins = [int(noise_on[i])]
+            sr.binomials = [change, inc]
+            sr.uniforms = [u_hi, u_lo]
+            data, lab, _ = add_noise(data, lab, reader)
+            sr.coins = [int(flip[i])]
+            data, lab, _ = flip_x_axis(data, lab, reader)
+        data, lab, _, _ = refine(data, lab, list(c), reader)
+        data, lab, _, _ = convert_label_indexing(data, lab, list(c), reader)
+        data, lab, _, _ = remove_nan_inf(data, lab, reader, freqs)
+        with np.errstate(invalid="ignore"):
+            d_plain, _, _, _ = db_with_limits(data.copy(), lab, reader, freqs)
+            d_scaled, _, _, _ = db_with_limits_scaled(data.copy(), lab, reader, freqs)
+        d_border, _, _, _ = set_data_border_value(d_plain.copy(), lab, reader, freqs)
+        mults.append(mult)
+        datas.append(d_plain.astype(np.float32))
+        datas_scaled.append(d_scaled.astype(np.float32))
+        datas_border.append(d_border.astype(np.float32))
+        labs.append(lab.astype(np.int64))
+        # the oracle restatement must agree with the reference on the same decisions
+        od, ol = P.train_patch_item(sv, labels, c, noise_on[i], flip[i], mult, tuple(patch))
+        assert np.array_equal(ol, labs[-1]), (i, (ol != labs[-1]).sum())
+        assert np.array_equal(np.isnan(od), np.isnan(datas[-1])) and np.allclose(od, datas[-1], atol=1e-5, equal_nan=True), i
+        od, _ = P.train_patch_item(sv, labels, c, noise_on[i], flip[i], mult, tuple(patch), scaled=True)
+        assert np.allclose(od, datas_scaled[-1], atol=1e-6, equal_nan=True), i
+        od, _ = P.train_patch_item(sv, labels, c, noise_on[i], flip[i], mult, tuple(patch), border_zero=True)
+        assert np.allclose(od, datas_border[-1], atol=1e-5, equal_nan=True), i
+        vals, cnt = np.unique(labs[-1], return_counts=True)
+        print(f"train crop {i} centre {c.tolist()} noise {noise_on[i]} flip {flip[i]} labels {dict(zip(vals.tolist(), cnt.tolist()))}")
+    out["mult"] = np.stack(mults)
+    out["data"] = np.stack(datas)
+    out["data_scaled"] = np.stack(datas_scaled)
+    out["data_border"] = np.stack(datas_border)
+    out["out_labels"] = np.stack(labs).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "pipeline_train.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -233,5 +358,6 @@ if __name__ == "__main__":
     golden_unet(ref, depth=5, hw=64, batch=2, fname="unet_d5.npz", store_state=False,
                 grad_subset=("conv_final", "main.1.", "main.4.", "bn1", "bn2", "down_convs.0.main.0", "upconv.bias"))
     golden_pipeline()
+    golden_train_pipeline()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

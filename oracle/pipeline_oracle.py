@@ -140,3 +140,118 @@ def patch_item(sv_preload, data_ping0, labels_chunk, ping_start, centre, seabed_
     labels = mask_overlap(labels, overlap)
     data, labels = data_transform(data, labels)
     return data.astype(np.float32), labels.astype(np.int16)
+
+
+# ---- training-sample path: Dataset.__getitem__, batch/dataset.py:75-108 ---------------------
+LABEL_REFINE_BOUNDARY_VAL = -30   # constants.py:29
+
+DISC7 = np.array([[0, 0, 1, 1, 1, 0, 0],
+                  [0, 1, 1, 1, 1, 1, 0],
+                  [1, 1, 1, 1, 1, 1, 1],
+                  [1, 1, 1, 1, 1, 1, 1],
+                  [1, 1, 1, 1, 1, 1, 1],
+                  [0, 1, 1, 1, 1, 1, 0],
+                  [0, 0, 1, 1, 1, 0, 0]], dtype=bool)   # refine_label_boundary.py:53-61
+
+
+def _morph(mask, structure, erode):
+    """scipy.ndimage.binary_dilation / binary_erosion with border_value=0, origin 0 (symmetric structure)."""
+    h, w = mask.shape
+    r = structure.shape[0] // 2
+    padded = np.zeros((h + 2 * r, w + 2 * r), dtype=bool)
+    padded[r:r + h, r:r + w] = mask
+    out = np.ones((h, w), dtype=bool) if erode else np.zeros((h, w), dtype=bool)
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            if not structure[dy + r, dx + r]:
+                continue
+            win = padded[r + dy:r + dy + h, r + dx:r + dx + w]
+            out = (out & win) if erode else (out | win)
+    return out
+
+
+def binary_closing(mask, structure=DISC7):
+    """scipy.ndimage.binary_closing(mask, structure): dilation then erosion, both with border_value 0."""
+    return _morph(_morph(mask, structure, erode=False), structure, erode=True)
+
+
+def get_crop_zarr(sv_fpr, labels_pr, centre, patch_hw):
+    """dataset.py:358-407. sv_fpr (F, pings, range) and labels_pr (pings, range) in the zarr store's order; returns
+    float64 data (F, ph, pw) [freq, range, ping] and float64 labels (ph, pw); outside the data -> 0 / -100;
+    np.nan_to_num on the slices (NaN -> 0 / -100, +-inf -> +-max of the slice dtype).  Square patches (the reference
+    mixes window_size[0] / [1], :397-398)."""
+    ph, pw = patch_hw
+    F, P, R = sv_fpr.shape
+    y0, x0 = centre[0] - ph // 2 + 1, centre[1] - pw // 2 + 1    # utils/np.py:378-380
+    out_data = np.zeros((F, ph, pw), dtype=np.float64)
+    out_labels = np.full((ph, pw), float(LABEL_BOUNDARY_VAL))
+    xa, xb = max(x0, 0), min(P, x0 + pw)
+    ya, yb = max(y0, 0), min(R, y0 + ph)
+    if xb > xa and yb > ya:
+        ch = np.nan_to_num(sv_fpr[:, xa:xb, ya:yb].swapaxes(1, 2), nan=0)
+        lb = np.nan_to_num(labels_pr[xa:xb, ya:yb].T, nan=LABEL_BOUNDARY_VAL)
+        out_data[:, ya - y0:yb - y0, xa - x0:xb - x0] = ch
+        out_labels[ya - y0:yb - y0, xa - x0:xb - x0] = lb
+    return out_data, out_labels
+
+
+def refine_label_boundary(data, labels, thr_idx, thr=(1e-7, 1e-4)):
+    """refine_label_boundary.py:38-104 with ignore_zero_inside_bbox=True."""
+    new = labels.copy()
+    idx = np.argwhere(new != LABEL_BOUNDARY_VAL)
+    if len(idx) == 0:
+        return new
+    y0, y1 = idx[:, 0].min(), idx[:, 0].max() + 1
+    x0, x1 = idx[:, 1].min(), idx[:, 1].max() + 1
+    m = (labels > 0) & (data[thr_idx] > thr[0]) & (data[thr_idx] < thr[1])
+    closed = binary_closing(m[y0:y1, x0:x1])
+    mask = np.zeros(new.shape, dtype=bool)
+    mask[y0:y1, x0:x1] = (~closed) & (new[y0:y1, x0:x1] > 0)
+    new[mask] = LABEL_REFINE_BOUNDARY_VAL
+    new[labels == LABEL_IGNORE_VAL] = LABEL_IGNORE_VAL
+    return new
+
+
+def convert_label_indexing(labels):
+    """convert_label_indexing.py:24-35."""
+    new = np.full(labels.shape, float(LABEL_IGNORE_VAL))
+    new[labels == 0] = BACKGROUND
+    new[labels == 27] = SANDEEL
+    new[labels == 1] = OTHER
+    return new
+
+
+def train_patch_item(sv_fpr, labels_pr, centre, noise_on, flip, mult=None, patch_hw=(256, 256), thr_idx=None,
+                     thr=(1e-7, 1e-4), scaled=False, border_zero=False):
+    """Dataset.__getitem__ (dataset.py:75-108) with train.py's composition (batch/transforms.py:40-75): get_crop_zarr
+    -> add_noise (multiplier field `mult` (F, ph, pw) in place of numpy's global RNG, add_noise.py:28-38) ->
+    flip_x_axis -> refine_label_boundary -> convert_label_indexing -> remove_nan_inf -> db_with_limits[_scaled]
+    [-> set_data_border_value].  Returns (data float32 (F, ph, pw), labels int64 (ph, pw))."""
+    data, labels = get_crop_zarr(sv_fpr, labels_pr, centre, patch_hw)
+    if noise_on:
+        data = data * np.asarray(mult, dtype=np.float64)
+    if flip:
+        data = np.flip(data, 2).copy()
+        labels = np.flip(labels, 1).copy()
+    thr_idx = data.shape[0] - 1 if thr_idx is None else thr_idx
+    labels = refine_label_boundary(data, labels, thr_idx, thr)
+    labels = convert_label_indexing(labels)
+    labels[~np.isfinite(data[0])] = LABEL_IGNORE_VAL           # remove_nan_inf.py:32 (a no-op after nan_to_num)
+    data[~np.isfinite(data)] = 0.0
+    with np.errstate(invalid="ignore"):
+        db = 10 * np.log10(data + 1e-10)
+        db[db > 0] = 0
+        db[db < -75] = -75
+    if scaled:
+        db = 1 + db / 75.0                                     # db_with_limits.py:27-33
+    if border_zero:
+        db[:, labels == LABEL_BOUNDARY_VAL] = 0.0              # set_data_border_value.py:21-24
+    return db.astype(np.float32), labels.astype(np.int64)
+
+
+def noise_multiplier_field(shape, rng):
+    """add_noise.py:28-38's multiplier as a field (float32-rounded so that a device replay sees the same numbers)."""
+    change = rng.binomial(1, 0.05, shape)
+    inc = rng.binomial(1, 0.5, shape)
+    m = (1 - change) + change * (inc * rng.uniform(1, 10, shape) + (1 - inc) * rng.uniform(0, 1, shape))
+    return m.astype(np.float32)
