@@ -65,6 +65,17 @@ TP_HD float sv_to_db(double v, int scaled) {
   return static_cast<float>(d);
 }
 
+// The data channels use fp32 arithmetic (the network input is fp32 and log10f is within 2 ulp: |error| < 2e-5 dB, the
+// same bound as crimac_preprocess); double is kept for the label threshold decision only, where a rounding difference
+// could flip a label.
+TP_HD float sv_to_db_f32(float v, int scaled) {
+  float d = 10.f * log10f(v + 1e-10f);
+  if (d > 0.f) d = 0.f;
+  if (d < -75.f) d = -75.f;
+  if (scaled) d = 1.f + d / 75.f;
+  return d;
+}
+
 // ---- counter-based noise (Philox4x32-10) --------------------------------------------------------------------
 // The reference draws from numpy's global generator (add_noise.py:25-38); a device kernel cannot replay that stream,
 // so the product draws the same distribution from a counter-based generator keyed by (seed, sample index): every
@@ -84,17 +95,31 @@ TP_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-TP_HD double u01(uint32_t r) { return (static_cast<double>(r) + 0.5) * (1.0 / 4294967296.0); }
-
 // add_noise.py:28-38: (1 - change) + change * (increase * U(1,10) + (1 - increase) * U(0,1)), P(change) = 0.05,
-// P(increase) = 0.5, the three draws independent.
-TP_HD double noise_multiplier(uint64_t seed, uint64_t index) {
+// P(increase) = 0.5, the three draws independent.  One sample consumes 64 random bits: word `lo` decides change
+// (31 bits against 0.05) and increase (1 bit), word `hi` is the uniform magnitude (24 bits, fp32 like the network input).
+TP_HD float noise_from_bits(uint32_t lo, uint32_t hi) {
+  if ((lo >> 1) >= 107374182u) return 1.f;  // 0.05 * 2^31
+  const float u = (static_cast<float>(hi >> 8) + 0.5f) * (1.f / 16777216.f);
+  return (lo & 1u) ? 1.f + 9.f * u : u;
+}
+
+// One Philox call serves the two samples (py, px) and (py + 8, px) with ((py >> 3) & 1) == 0 — the two range rows a
+// thread of the gather kernel handles back to back — so the generator costs half a call per sample.  chan = crop * F +
+// frequency.  The multiplier stays a pure function of (seed, chan, py, px).
+TP_HD void noise_pair(uint64_t seed, int chan, int base_row, int px, float out[2]) {
   uint32_t r[4];
-  philox4x32_10(static_cast<uint32_t>(index), static_cast<uint32_t>(index >> 32), 0x43524d43u, 0u,
+  philox4x32_10(static_cast<uint32_t>(px), static_cast<uint32_t>(base_row), static_cast<uint32_t>(chan), 0x43524d43u,
                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
-  if (u01(r[0]) >= 0.05) return 1.0;
-  const double u = u01(r[2]);
-  return u01(r[1]) < 0.5 ? 1.0 + 9.0 * u : u;
+  out[0] = noise_from_bits(r[0], r[1]);
+  out[1] = noise_from_bits(r[2], r[3]);
+}
+
+TP_HD float noise_multiplier(uint64_t seed, int chan, int py, int px) {
+  float m[2];
+  const int q = (py >> 3) & 1;
+  noise_pair(seed, chan, py - 8 * q, px, m);
+  return m[q];
 }
 
 // ---- 7x7 disc closing on bit rows ----------------------------------------------------------------------------
@@ -178,13 +203,6 @@ struct TileCoord {  // blockIdx of the gather kernel: x = tile of the crop, y = 
   int tile, chan, crop;
 };
 
-TP_HD double sample_multiplier(const GatherParams& p, int b, int f, int py, int px, bool noisy) {
-  if (!noisy) return 1.0;
-  const long idx = ((static_cast<long>(b) * p.F + f) * p.ph + py) * p.pw + px;
-  return p.noise != nullptr ? static_cast<double>(TP_LDG(p.noise + idx))
-                            : noise_multiplier(p.seed, static_cast<uint64_t>(idx));
-}
-
 // Load phase: thread (tx, ty) of the (32, 8) block; tx runs along RANGE, which is contiguous in the store.
 // tile[i][j]: i = ping offset inside the tile, j = range offset.
 TP_HD void gather_load(const GatherParams& p, const TileCoord& blk, int tx, int ty, float (*tile)[33],
@@ -195,65 +213,96 @@ TP_HD void gather_load(const GatherParams& p, const TileCoord& blk, int tx, int 
   const int cy = p.centres[2 * blk.crop], cx = p.centres[2 * blk.crop + 1];
   const int Y = cy - p.ph / 2 + 1 + ty0 + tx;  // utils/np.py:378-380
   const int src_f = is_label ? p.thr_freq : blk.chan;
+  // the loads are issued unconditionally from clamped (always valid) addresses so that all of a thread's loads are in
+  // flight together; a sample outside the survey is replaced afterwards
+  const int Yc = Y < 0 ? 0 : (Y >= p.R ? p.R - 1 : Y);
+  float s[4], l[4];
+  bool in[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    const int X = cx - p.pw / 2 + 1 + tx0 + ty + 8 * k;
+    const int Xc = X < 0 ? 0 : (X >= p.P ? p.P - 1 : X);
+    in[k] = Y >= 0 && Y < p.R && X >= 0 && X < p.P;
+    s[k] = TP_LDG(p.sv + (static_cast<long>(src_f) * p.P + Xc) * p.R + Yc);
+    l[k] = is_label ? TP_LDG(p.labels + static_cast<long>(Xc) * p.R + Yc) : 0.f;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
   for (int k = 0; k < 4; ++k) {
     const int i = ty + 8 * k;
-    const int X = cx - p.pw / 2 + 1 + tx0 + i;
-    const bool in = Y >= 0 && Y < p.R && X >= 0 && X < p.P;
-    float s = 0.f;  // boundary_val_data, dataset.py:360
-    if (in) s = nan_to_num_f32(TP_LDG(p.sv + (static_cast<long>(src_f) * p.P + X) * p.R + Y));
-    tile[i][tx] = s;
-    if (is_label) tile_lab[i][tx] = in ? TP_LDG(p.labels + static_cast<long>(X) * p.R + Y) : -100.f;
+    tile[i][tx] = in[k] ? nan_to_num_f32(s[k]) : 0.f;  // boundary_val_data, dataset.py:360
+    if (is_label) tile_lab[i][tx] = in[k] ? l[k] : -100.f;
   }
 }
 
 // Store phase: tx runs along PING, which is contiguous in the network input.
-TP_HD void gather_store(const GatherParams& p, const TileCoord& blk, int tx, int ty, const float (*tile)[33],
-                        const float (*tile_lab)[33]) {
+// fl = p.flags[crop], read by the caller before the load phase (one less dependent load after the barrier).
+TP_HD void gather_store(const GatherParams& p, const TileCoord& blk, int tx, int ty, uint8_t fl,
+                        const float (*tile)[33], const float (*tile_lab)[33]) {
   const bool is_label = blk.chan == p.F;
   const int tiles_x = p.pw >> 5;
   const int ty0 = (blk.tile / tiles_x) << 5, tx0 = (blk.tile % tiles_x) << 5;
   const int b = blk.crop;
-  const uint8_t fl = p.flags[b];
   const bool noisy = (fl & 1) != 0, flip = (fl & 2) != 0;
   const int src_f = is_label ? p.thr_freq : blk.chan;
   const int px = tx0 + tx;
   const int ox = flip ? p.pw - 1 - px : px;  // flip_x_axis.py:22-25 (after the noise)
-  for (int k = 0; k < 4; ++k) {
-    const int j = ty + 8 * k;
-    const int py = ty0 + j;
-    const double v = static_cast<double>(tile[tx][j]) * sample_multiplier(p, b, src_f, py, px, noisy);
-    if (!is_label) {
-      p.x[((static_cast<long>(b) * p.F + blk.chan) * p.ph + py) * p.pw + ox] = sv_to_db(v, p.scaled);
-    } else {
-      int code = label_code(tile_lab[tx][j]);
-      // refine_label_boundary.py:88-89: (labels > 0) & (data > lo) & (data < hi) on the threshold frequency
-      const bool positive = code == L_OTHER || code == L_SANDEEL || code == L_POSITIVE;
-      if (positive && v > p.thr_lo && v < p.thr_hi) code |= kThresholdBit;
-      p.lab[(static_cast<long>(b) * p.ph + py) * p.pw + ox] = code;
+  for (int kp = 0; kp < 2; ++kp) {  // rows (ty + 16 kp) and (ty + 16 kp + 8) of the tile share one generator call
+    float m[2] = {1.f, 1.f};
+    if (noisy && p.noise == nullptr) noise_pair(p.seed, b * p.F + src_f, ty0 + ty + 16 * kp, px, m);
+    for (int q = 0; q < 2; ++q) {
+      const int j = ty + 16 * kp + 8 * q;
+      const int py = ty0 + j;
+      if (noisy && p.noise != nullptr)
+        m[q] = TP_LDG(p.noise + ((static_cast<long>(b) * p.F + src_f) * p.ph + py) * p.pw + px);
+      if (!is_label) {
+        const float v = tile[tx][j] * m[q];
+        p.x[((static_cast<long>(b) * p.F + blk.chan) * p.ph + py) * p.pw + ox] = sv_to_db_f32(v, p.scaled);
+      } else {
+        // float64 like the reference's out_data (dataset.py:361): the product of two fp32 numbers is exact in double
+        const double v = static_cast<double>(tile[tx][j]) * static_cast<double>(m[q]);
+        int code = label_code(tile_lab[tx][j]);
+        // refine_label_boundary.py:88-89: (labels > 0) & (data > lo) & (data < hi) on the threshold frequency
+        const bool positive = code == L_OTHER || code == L_SANDEEL || code == L_POSITIVE;
+        if (positive && v > p.thr_lo && v < p.thr_hi) code |= kThresholdBit;
+        p.lab[(static_cast<long>(b) * p.ph + py) * p.pw + ox] = code;
+      }
     }
   }
 }
 
-// ---- the label kernel's word / sample phases (one crop per thread block; T, D, E = bit masks of ph*pw/32 words) --
-TP_HD void labels_dilate(const uint32_t* T, uint32_t* D, const BBox& bb, int ph, int wpr, int i) {
-  const int y = i / wpr, w = i - y * wpr;
+// ---- the label kernel's phases.  A crop is split into kBands horizontal bands of ph/kBands range rows, one thread
+// block each (the blocks of a crop form a cluster); a band keeps three bit masks in shared memory:
+//   T  threshold mask,  rows [r0 - 6, r0 + rows + 6)   (rows outside the crop are 0)
+//   D  its dilation cut to the bounding box, rows [r0 - 3, r0 + rows + 3)
+//   E  the closing, rows [r0, r0 + rows)
+constexpr int kBands = 8;
+
+TP_HD void labels_dilate_band(const uint32_t* T, uint32_t* D, const BBox& bb, int wpr, int r0, int rows, int i) {
+  const int ly = i / wpr, w = i - ly * wpr;  // D row ly = crop row r0 - 3 + ly = T row ly + 3
   // binary_closing on the bounding-box crop (refine_label_boundary.py:91) = dilation, cut to the box, erosion with
   // everything outside the box counting as 0 (border_value = 0 in both passes)
-  D[i] = dilate_word(T, wpr, ph, y, w) & bbox_word(bb, y, w);
+  D[i] = dilate_word(T, wpr, rows + 12, ly + 3, w) & bbox_word(bb, r0 - 3 + ly, w);
 }
 
-TP_HD void labels_erode(const uint32_t* D, uint32_t* E, int ph, int wpr, int i) {
-  const int y = i / wpr, w = i - y * wpr;
-  E[i] = erode_word(D, wpr, ph, y, w);
+TP_HD void labels_erode_band(const uint32_t* D, uint32_t* E, int wpr, int rows, int i) {
+  const int ly = i / wpr, w = i - ly * wpr;  // E row ly = crop row r0 + ly = D row ly + 3
+  E[i] = erode_word(D, wpr, rows + 6, ly + 3, w);
 }
 
-TP_HD void labels_finish(long long* L, float* x_crop, const uint32_t* E, int F, int npx, int border_zero, int i) {
-  const int code = static_cast<int>(L[i]) & 7;
+// i = sample index inside the band; L / x_crop point at the crop, npx = ph * pw
+TP_HD void labels_finish_band(long long* L, float* x_crop, const uint32_t* E, int F, int npx, int band_px0,
+                              int border_zero, int i) {
+  const int gi = band_px0 + i;
+  const int code = static_cast<int>(L[gi]) & 7;
   const bool closed = ((E[i >> 5] >> (i & 31)) & 1u) != 0;
   const long out = final_label(code, closed);
-  L[i] = out;
+  L[gi] = out;
   if (border_zero && out == -100) {  // set_data_border_value.py:21-24 on this path's final labels
-    for (int f = 0; f < F; ++f) x_crop[static_cast<long>(f) * npx + i] = 0.f;
+    for (int f = 0; f < F; ++f) x_crop[static_cast<long>(f) * npx + gi] = 0.f;
   }
 }
 

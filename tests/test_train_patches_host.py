@@ -24,10 +24,13 @@ def hostlib(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("tphost") / "libtphost.so")
     subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "host", "train_patch_hostcheck.cc")],
                    check=True)
-    lib = ctypes.CDLL(so)
-    lib.tp_host_noise_multiplier.restype = ctypes.c_double
-    lib.tp_host_noise_multiplier.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
-    return lib
+    return ctypes.CDLL(so)
+
+
+def noise_field(lib, seed, chan, ph, pw):
+    out = np.zeros((ph, pw), np.float32)
+    lib.tp_host_noise_field(ctypes.c_uint64(seed), chan, ph, pw, vp(out.ctypes.data))
+    return out
 
 
 def host_train_patches(lib, sv, labels, centres, flags, mult, patch, seed=0, thr_freq=None, scaled=0, border=0):
@@ -85,7 +88,7 @@ def test_kernel_bodies_on_the_host_match_the_reference_made_fixture(hostlib, gol
         x, y = host_train_patches(hostlib, g["sv"], g["labels"], g["centres"], flags, g["mult"], patch, **kw)
         assert np.array_equal(y, g["out_labels"].astype(np.int64))          # labels: bit-exact
         assert np.array_equal(np.isnan(x), np.isnan(g[key]))
-        assert np.nanmax(np.abs(x - g[key])) <= 1e-5                        # dB values: double log10 both sides
+        assert np.nanmax(np.abs(x - g[key])) <= 1e-4                        # dB values: fp32 log10f vs numpy float64
 
 
 def test_kernel_bodies_on_the_host_match_the_oracle_on_random_crops(hostlib):
@@ -106,7 +109,7 @@ def test_kernel_bodies_on_the_host_match_the_oracle_on_random_crops(hostlib):
     for i in range(n):
         d, l = P.train_patch_item(sv, labels, centres[i], flags[i] & 1, flags[i] & 2, mult[i], (patch, patch))
         assert np.array_equal(y[i], l), i
-        assert np.allclose(x[i], d, rtol=0, atol=1e-5, equal_nan=True), i
+        assert np.allclose(x[i], d, rtol=0, atol=1e-4, equal_nan=True), i
 
 
 def test_bit_row_closing_matches_scipy(hostlib):
@@ -128,18 +131,24 @@ def test_bit_row_closing_matches_scipy(hostlib):
 
 def test_counter_based_noise_has_the_distribution_of_add_noise(hostlib):
     """add_noise.py:28-38: 5 % of the samples change; half of those are multiplied by U(1,10), half by U(0,1)."""
-    n = 400_000
-    m = np.array([hostlib.tp_host_noise_multiplier(12345, i) for i in range(n)])
+    m = noise_field(hostlib, 12345, 3, 640, 640).astype(np.float64).ravel()
     changed = m != 1.0
     assert abs(changed.mean() - 0.05) < 0.002
     up, down = m[changed & (m > 1.0)], m[changed & (m < 1.0)]
+    assert len(up) + len(down) == changed.sum()
     assert abs(len(up) / changed.sum() - 0.5) < 0.02
-    assert 1.0 < up.min() and up.max() < 10.0 and abs(up.mean() - 5.5) < 0.1
-    assert 0.0 < down.min() and abs(down.mean() - 0.5) < 0.02
-    # a different seed gives a different field, the same seed the same field
-    assert hostlib.tp_host_noise_multiplier(1, 77) == hostlib.tp_host_noise_multiplier(1, 77)
-    m2 = np.array([hostlib.tp_host_noise_multiplier(54321, i) for i in range(20000)])
-    assert (m2 != m[:20000]).mean() > 0.05
+    assert 1.0 < up.min() and up.max() < 10.0 and abs(up.mean() - 5.5) < 0.1 and abs(up.std() - 9 / 12 ** 0.5) < 0.1
+    assert 0.0 < down.min() and abs(down.mean() - 0.5) < 0.02 and abs(down.std() - 1 / 12 ** 0.5) < 0.02
+    # the two samples that share one generator call (rows py and py + 8) are independent
+    f = noise_field(hostlib, 12345, 3, 640, 640) != 1.0
+    rows = np.arange(640)
+    base = rows[(rows >> 3) & 1 == 0]
+    both = (f[base] & f[base + 8]).mean()
+    assert abs(both - 0.0025) < 0.0006
+    # a pure function of (seed, channel, row, ping): reproducible, and different for another seed / channel
+    assert np.array_equal(noise_field(hostlib, 1, 0, 64, 64), noise_field(hostlib, 1, 0, 64, 64))
+    assert (noise_field(hostlib, 1, 0, 64, 64) != noise_field(hostlib, 2, 0, 64, 64)).mean() > 0.05
+    assert (noise_field(hostlib, 1, 0, 64, 64) != noise_field(hostlib, 1, 1, 64, 64)).mean() > 0.05
 
 
 def test_feeder_argument_validation_needs_no_gpu(pkg):
