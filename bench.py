@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="train", choices=["train", "infer", "survey"],
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "survey", "feed"],
                     help="train = BASELINE configs[1]/[2] (headline); infer = forward+softmax; survey = configs[3] sliding window")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--in-ch", type=int, default=4, help="frequencies (configs[4] stress: 6)")
@@ -190,6 +190,8 @@ def run_b200(args):
     model = M.UNet_Baseline(3, C).to(dev)
     if args.mode == "survey":
         return run_survey(args, model, dev, rank, world, E)
+    if args.mode == "feed":
+        return run_feed(args, model, dev, rank, world, E)
     x = O.synthetic_echogram(B, C, S, S, seed=100 + rank, device=dev)
     y = O.synthetic_labels(B, S, S, seed=200 + rank, device=dev)
     standard = (C == 4 and S == 256)
@@ -446,6 +448,98 @@ def run_survey(args, model, dev, rank, world, E):
             "cpu_baseline": None}), flush=True)
     if world > 1:
         _teardown(dist)
+
+
+def run_feed(args, model, dev, rank, world, E):
+    """the headline train step fed by training samples drawn ON THE DEVICE from a resident
+    survey (crop + add_noise + flip + refine_label_boundary + convert_label_indexing + dB transform, the work of the
+    reference's CPU DataLoader workers, batch/dataset.py:75-108).  A step = sample generation (2 launches) + weight
+    re-pack + forward + weighted CE + backward (+ all-reduce) + SGD."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from crimac_unet_b200.trainer import Trainer
+    from crimac_unet_b200.train_patches import SurveyPatchFeeder
+    B, C, S = args.batch, args.in_ch, args.size
+    NP, R = 60000, 500
+    g = torch.Generator(device=dev).manual_seed(400 + rank)
+    sv = torch.pow(10.0, torch.rand((C, NP, R), device=dev, generator=g) * 7.0 - 9.0)        # zarr order (F, ping, range)
+    labels = torch.zeros((NP, R), device=dev)
+    rng = np.random.default_rng(500 + rank)
+    for _ in range(400):                                                                      # schools: 27 sandeel, 1 other
+        cy, cx = int(rng.integers(0, NP)), int(rng.integers(0, R))
+        labels[max(0, cy - 60):cy + 60, max(0, cx - 40):cx + 40] = float(rng.choice([27, 1]))
+    fish = labels > 0
+    sv[C - 1][fish] = torch.pow(10.0, torch.rand(int(fish.sum()), device=dev, generator=g) * 3.0 - 7.2)
+    model.train()
+    trainer = Trainer(model, lr=0.005, momentum=0.95)
+    trainer.broadcast_parameters(0)
+    feeder = SurveyPatchFeeder(sv, labels, B, (S, S), seed=600 + rank)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in trainer.fit_survey(feeder, max(args.warmup, 3)):
+        pass
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for loss in trainer.fit_survey(feeder, args.steps):
+        pass
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    # the timed steps replay a CUDA graph, which the library's launch counter cannot see: count one EAGER step
+    torch.cuda.synchronize()
+    l0 = E.launch_count()
+    xb, yb = feeder.next_batch()
+    trainer._launch_step(xb, yb)
+    torch.cuda.synchronize()
+    launches = (E.launch_count() - l0 + 2) * args.steps    # + the two train_patches kernels per step
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / args.steps
+    value = world * B / (ms * 1e-3)
+    # end to end as a user loop would run it: the loss of every step is read back on the host
+    sync_all()
+    e0.record()
+    last = float("nan")
+    for loss in trainer.fit_survey(feeder, args.steps):
+        last = loss.item()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / (t.item() * 1e-3)
+    standard = (C == 4 and S == 256)
+    gflop = GFLOP_TRAIN if standard else unet_gflop(C, S, True)
+    if rank == 0:
+        peaks = measured_peaks()
+        print(json.dumps({
+            "metric": "U-Net 256x256 patches/s, train step fed from a device-resident survey (crop + augmentation + label refinement + dB on device)",
+            "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (fp32 accumulate, fp32 master weights / BN statistics / loss)", "data": "synthetic",
+            "config": {"workload": "UNet training fwd+bwd, batch %d of %dx%dx%d per GPU, samples drawn on the device from a %dx%dx%d survey" % (B, C, S, S, C, NP, R),
+                       "l2": "activations of one step (several GB) >> 126 MB L2; the survey is %d MB" % (sv.numel() * 4 // 2 ** 20),
+                       "last_loss": last},
+            "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": 4,
+                    "api": "Trainer.fit_survey(SurveyPatchFeeder): per step 12 bytes per sample of crop centres and coin flips host -> device, loss.item()"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": value / world * gflop / 1e3,
+                         "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": value / world * gflop / 1e3 / peaks["tflops_sustained"],
+                         "traffic": None, "note": "whole-step figure (sample generation included) against the sustained bf16 peak"},
+            "cpu_baseline": None}), flush=True)
+    if world > 1:
+        _teardown(dist, trainer)
 
 
 if __name__ == "__main__":
