@@ -112,6 +112,35 @@ def test_kernel_bodies_on_the_host_match_the_oracle_on_random_crops(hostlib):
         assert np.allclose(x[i], d, rtol=0, atol=1e-4, equal_nan=True), i
 
 
+def test_kernel_bodies_on_the_host_edge_cases(hostlib):
+    """Survey smaller than the patch, crops hanging over every edge or entirely outside, a one-sample survey, an
+    all-fish survey whose threshold channel is entirely inside / entirely outside the window."""
+    rng = np.random.default_rng(33)
+    for (F, NP, R, patch) in ((1, 20, 50, 64), (3, 70, 17, 32), (2, 1, 1, 32), (2, 40, 40, 32)):
+        sv = (10.0 ** rng.uniform(-9, -2, size=(F, NP, R))).astype(np.float32)
+        labels = rng.choice([0, 0, 27, 1, 9, np.nan, -100, -1], size=(NP, R)).astype(np.float32)
+        centres = np.array([[0, 0], [R - 1, NP - 1], [R // 2, NP // 2], [-patch, NP // 2], [R // 2, NP + patch],
+                            [R + 3 * patch, -3 * patch], [patch // 2 - 1, patch // 2 - 1]], np.int32)
+        n = len(centres)
+        flags = rng.integers(0, 4, n).astype(np.uint8)
+        mult = np.stack([P.noise_multiplier_field((F, patch, patch), rng) for _ in range(n)])
+        x, y = host_train_patches(hostlib, sv, labels, centres, flags, mult, patch)
+        for i in range(n):
+            d, l = P.train_patch_item(sv, labels, centres[i], flags[i] & 1, flags[i] & 2, mult[i], (patch, patch))
+            assert np.array_equal(y[i], l), (F, NP, R, patch, i)
+            assert np.allclose(x[i], d, rtol=0, atol=1e-4, equal_nan=True), (F, NP, R, patch, i)
+    for lo_hi, expect_fish in (((-6.5, -4.5), True), ((-3.5, -2.5), False)):
+        sv = (10.0 ** rng.uniform(*lo_hi, size=(2, 64, 64))).astype(np.float32)
+        labels = np.full((64, 64), 27, np.float32)
+        c = np.array([[31, 31]], np.int32)
+        x, y = host_train_patches(hostlib, sv, labels, c, np.zeros(1, np.uint8), None, 64)
+        d, l = P.train_patch_item(sv, labels, c[0], 0, 0, None, (64, 64))
+        assert np.array_equal(y[0], l)
+        # scipy's closing erodes with border_value 0: even a fully passing school loses its 3-sample rim
+        assert bool((y[0, 3:-3, 3:-3] == 1).all()) == expect_fish and bool((y[0, 0] == -100).all())
+        assert bool((y == -100).all()) == (not expect_fish)
+
+
 def test_bit_row_closing_matches_scipy(hostlib):
     from scipy.ndimage import binary_closing
     rng = np.random.default_rng(4)
