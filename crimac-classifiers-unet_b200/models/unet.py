@@ -6,6 +6,8 @@ kernels behind the C-ABI of ``include/crimac_b200.h``.
 The sub-modules (``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.ConvTranspose2d``) are kept purely as PARAMETER HOLDERS in
 the same tree positions so checkpoints load unchanged; their own ``forward`` is never used on the hot path.  There is
 no CPU / PyTorch fallback for ``UNet_Baseline``: a configuration the native path does not cover raises.
+``UNet_LateMetInject`` (reference :346-391) runs its U-Net body and the 64-channel part of its head through the same
+native calls; only its per-sample metadata MLP is torch.
 """
 import importlib
 import importlib.util
@@ -121,30 +123,34 @@ class MetaPostProcessing(nn.Module):
 
 # --------------------------------------------------------------------------------------------- autograd bridge
 class _NativeUNetFunction(torch.autograd.Function):
-    """Train-mode forward / backward of the whole network through the C-ABI (one Function for all layers)."""
+    """Train-mode forward / backward of the whole network through the C-ABI (one Function for all layers).
+
+    `params` are the 82 tensors the library differentiates, in state-table order; params[-2] is the (n_classes, 64, 1, 1)
+    head weight - the module's own parameter for UNet_Baseline, a slice of the 65-input head for UNet_LateMetInject."""
 
     @staticmethod
     def forward(ctx, x, model, *params):
         eng = model._engine_for(x, train=True)
-        state = eng.state_table(model._state_tensors())
+        state = eng.state_table(model._state_tensors(head_weight=params[-2]))
         eng.prepare(state, True)
         logits = torch.empty((x.shape[0], model.n_classes, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
         eng.forward_train(state, x, logits)
         ctx.model, ctx.eng = model, eng
-        ctx.save_for_backward(x)
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(x, params[-2])
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        (x,) = ctx.saved_tensors
+        x, head_w = ctx.saved_tensors
         model, eng = ctx.model, ctx.eng
-        params = model._param_tensors()
-        arena = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=x.device)
+        sizes = [int(torch.Size(sh).numel()) for sh in ctx.shapes]
+        arena = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
         grads, off = [], 0
-        for p in params:
-            grads.append(arena[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        state = eng.state_table(model._state_tensors())
+        for sh, n in zip(ctx.shapes, sizes):
+            grads.append(arena[off:off + n].view(sh))
+            off += n
+        state = eng.state_table(model._state_tensors(head_weight=head_w))
         eng.backward(state, x, dlogits.contiguous().float(), None, eng.grad_table(grads))
         return (None, None) + tuple(grads)
 
@@ -207,25 +213,13 @@ class UNet(nn.Module):
             print(i, m)
             self.weight_init(m)
 
-    # plain-torch composition, used only by the variants that are NOT on the hot path (UNet_LateMetInject)
-    def _features_torch(self, x):
-        skips = []
-        for block in self.down_convs:
-            x, before_pool = block(x)
-            skips.append(before_pool)
-        for i, block in enumerate(self.up_convs):
-            x = block(skips[-(i + 2)], x)
-        return x
 
+class _NativePlumbing:
+    """What a model whose body is the 5-level U-Net needs to run it through libcrimac_b200.so (mixed into UNet_Baseline
+    and UNet_LateMetInject; the sub-modules stay parameter holders)."""
 
-class UNet_Baseline(UNet):
-    """The hot-path model (reference unet.py:304-343; the only model SegPipeUNet builds, pipeline.py:390-398)."""
+    _native_head_in = 64   # input channels of the 1x1 head the library computes
 
-    def __init__(self, n_classes, in_channels, meta_in_channels=0, late_meta_inject=False, depth=5, start_filts=64,
-                 up_mode="transpose", merge_mode="concat"):
-        super().__init__(n_classes, in_channels, meta_in_channels, late_meta_inject, depth, start_filts, up_mode, merge_mode)
-
-    # ---- native plumbing
     def _check_supported(self, x):
         problems = []
         if self.up_mode != "transpose" or self.merge_mode != "concat":
@@ -234,8 +228,10 @@ class UNet_Baseline(UNet):
             problems.append("start_filts must be 64 and depth in 2..5")
         if not (1 <= self.in_channels <= 8) or not (1 <= self.n_classes <= 8):
             problems.append("in_channels and n_classes must be in 1..8")
-        if self.conv_final.in_channels != 64:
-            problems.append("late_meta_inject heads are not on the native path")
+        if self.conv_final.in_channels != self._native_head_in + self._meta_head_channels():
+            problems.append("the 1x1 head must take the 64 decoder channels (plus the late-injected metadata channels)")
+        if self.conv_final.out_channels != self.n_classes:
+            problems.append("the 1x1 head must produce n_classes channels")
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             problems.append(f"expected input (N,{self.in_channels},H,W), got {tuple(x.shape)}")
         elif x.shape[2] % (1 << (self.depth - 1)) or x.shape[3] % (1 << (self.depth - 1)):
@@ -243,10 +239,16 @@ class UNet_Baseline(UNet):
         if not x.is_cuda:
             problems.append("input must be a CUDA tensor: the U-Net hot path has no CPU fallback")
         if problems:
-            raise RuntimeError("crimac_unet_b200.UNet_Baseline cannot run this call natively: " + "; ".join(problems))
+            raise RuntimeError(f"crimac_unet_b200.{type(self).__name__} cannot run this call natively: " + "; ".join(problems))
 
-    def _state_tensors(self):
-        """The 136 tensors of state_dict() in its order, gathered without building the dict."""
+    def _meta_head_channels(self):
+        return 0
+
+    def _head_weight(self):
+        """The (n_classes, 64, 1, 1) contiguous head weight of the state table."""
+        return self.conv_final.weight
+
+    def _body_state(self):
         def bn(m):
             return [m.weight, m.bias, m.running_mean, m.running_var, m.num_batches_tracked]
 
@@ -257,7 +259,12 @@ class UNet_Baseline(UNet):
         for u in self.up_convs:
             out += [u.upconv.weight, u.upconv.bias, u.conv1.weight, u.conv1.bias, u.conv2.weight, u.conv2.bias]
             out += bn(u.bn1) + bn(u.bn2)
-        return out + [self.conv_final.weight, self.conv_final.bias]
+        return out
+
+    def _state_tensors(self, head_weight=None):
+        """The 136 tensors of UNet_Baseline.state_dict() in its order, gathered without building the
+        dict.  head_weight overrides the head's weight tensor (the autograd path passes the tensor it differentiates)."""
+        return self._body_state() + [self._head_weight() if head_weight is None else head_weight, self.conv_final.bias]
 
     def _param_tensors(self):
         return list(self.parameters())
@@ -296,14 +303,35 @@ class UNet_Baseline(UNet):
         eng.forward_infer(state, x, out, softmax)
         return out
 
+    def _train_forward(self, x, params):
+        x = self._prep_input(x)
+        if x.requires_grad:
+            raise RuntimeError("gradients w.r.t. the input echogram are not produced by the native path")
+        return _NativeUNetFunction.apply(x, self, *params)
+
+
+class UNet_Baseline(_NativePlumbing, UNet):
+    """The hot-path model (reference unet.py:304-343; the only model SegPipeUNet builds, pipeline.py:390-398)."""
+
+    def __init__(self, n_classes, in_channels, meta_in_channels=0, late_meta_inject=False, depth=5, start_filts=64,
+                 up_mode="transpose", merge_mode="concat"):
+        super().__init__(n_classes, in_channels, meta_in_channels, late_meta_inject, depth, start_filts, up_mode, merge_mode)
+
+    def _meta_head_channels(self):
+        # UNet_Baseline(..., late_meta_inject=True) builds a wider head (unet.py:286-289) that its own forward cannot feed
+        return self.conv_final.in_channels - self._native_head_in
+
+    def _check_supported(self, x):
+        if self.conv_final.in_channels != self._native_head_in:
+            raise RuntimeError("crimac_unet_b200.UNet_Baseline cannot run this call natively: late_meta_inject heads "
+                               "belong to UNet_LateMetInject")
+        super()._check_supported(x)
+
     # ---- public surface
     def forward(self, x):
         """(N,C,H,W) fp32 -> raw logits (N,n_classes,H,W) fp32, as the reference (no softmax, unet.py:339-343)."""
         if self.training:
-            x = self._prep_input(x)
-            if x.requires_grad:
-                raise RuntimeError("gradients w.r.t. the input echogram are not produced by the native path")
-            return _NativeUNetFunction.apply(x, self, *self._param_tensors())
+            return self._train_forward(x, self._param_tensors())
         return self._infer(x, softmax=False)
 
     @torch.no_grad()
@@ -351,17 +379,50 @@ class UNet_Baseline(UNet):
         return loss3[0]
 
 
-class UNet_LateMetInject(UNet):
-    """Late metadata injection variant (reference unet.py:346-391). Not on the benchmark path: plain torch modules."""
+class UNet_LateMetInject(_NativePlumbing, UNet):
+    """Late metadata injection variant (reference unet.py:346-391).
+
+    The reference concatenates the decoder's 64 channels with MetaPostProcessing(meta) and applies conv1x1(65, 3).  A 1x1
+    conv over a concatenation is the sum of two 1x1 convs, so the 64-channel part - the whole U-Net body plus
+    W[:, :64] and the bias - runs through the native library exactly like UNet_Baseline, and the metadata part
+    (a per-sample MLP and W[:, 64:]) stays a few elementwise torch ops whose gradients autograd handles:
+        logits = native(x; body, W[:, :64], b) + sum_k W[:, 64 + k] * MetaPostProcessing(meta)[k]"""
 
     def __init__(self, n_classes, in_channels, meta_in_channels, late_meta_inject=True, depth=5, start_filts=64,
                  up_mode="transpose", merge_mode="concat"):
         super().__init__(n_classes, in_channels, meta_in_channels, late_meta_inject, depth, start_filts, up_mode, merge_mode)
         self.conv_final = conv1x1(65, 3)  # hard-coded in the reference as well (unet.py:370)
+        self._w64 = None
+        self._w64_version = None
+
+    def _meta_head_channels(self):
+        return self.post_processing_weights.out_channels
+
+    def _head_weight(self):
+        """Eval path: a contiguous copy of W[:, :64], refreshed only when the parameter changes (so that the packed
+        weights are not rebuilt on every call)."""
+        w = self.conv_final.weight
+        ver = (w.data_ptr(), w._version)
+        if self._w64 is None or self._w64_version != ver or self._w64.device != w.device:
+            with torch.no_grad():
+                self._w64 = w[:, :self._native_head_in].contiguous()
+            self._w64_version = ver
+        return self._w64
+
+    def _meta_logits(self, meta_tensor):
+        w_meta = self.conv_final.weight[:, self._native_head_in:, 0, 0]                 # (n_classes, K)
+        mp = self.post_processing_weights(meta_tensor.float())                          # (N, K, H, W)
+        return (mp.unsqueeze(1) * w_meta.reshape(1, w_meta.shape[0], w_meta.shape[1], 1, 1)).sum(2)
 
     def forward(self, x, meta_tensor):
-        feats = self._features_torch(x)
-        return self.conv_final(torch.cat((feats, self.post_processing_weights(meta_tensor)), 1))
+        """(N,C,H,W) echogram + (N,M,H,W) metadata -> raw logits (N,3,H,W), as the reference (unet.py:372-391)."""
+        if self.training:
+            body = [p for m in (self.down_convs, self.up_convs) for p in m.parameters()]
+            w64 = self.conv_final.weight[:, :self._native_head_in].contiguous()        # differentiable slice
+            native = self._train_forward(x, body + [w64, self.conv_final.bias])
+        else:
+            native = self._infer(x, softmax=False)
+        return native + self._meta_logits(meta_tensor)
 
 
 if __name__ == "__main__":

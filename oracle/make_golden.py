@@ -6,6 +6,8 @@ Vectors:
                      all gradients / updated BN buffers (models/unet.py + pipeline.py:135-138,176-177)
   unet_d5.npz        reference UNet_Baseline(3, 4) (the production depth): weights regenerated from seed 0 (checksums
                      stored), eval + train logits, loss, a subset of gradients
+  unet_late_d2.npz   reference UNet_LateMetInject(3, 4, 2, depth=2) on the body weights of unet_d2.npz (only the head and
+                     metadata-MLP tensors are stored): eval + train logits, loss, gradients
   pipeline_train.npz reference get_crop_zarr + add_noise + flip_x_axis + refine_label_boundary + convert_label_indexing +
                      remove_nan_inf + db_with_limits(_scaled) + set_data_border_value on scripted random decisions
   pipeline_small.npz reference DatasetGriddedReader (preload branch) + remove_nan_inf + db_with_limits +
@@ -111,6 +113,60 @@ def golden_unet(ref, depth, hw, batch, fname, store_state, grad_subset=None):
     else:
         out["state_checksums"] = np.array([checksum(v) for v in sd.values()])
     np.savez_compressed(os.path.join(OUT, fname), **out)
+
+
+def golden_late_meta_inject(ref):
+    """tests/golden/unet_late_d2.npz: reference UNet_LateMetInject(3, 4, 2, depth=2) (models/unet.py:346-391) with the
+    body weights of unet_d2.npz, a seeded 65-input head and metadata MLP: eval logits, train logits / loss / gradients."""
+    g = np.load(os.path.join(OUT, "unet_d2.npz"))
+    body = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/") and not k.startswith("state/conv_final")}
+    torch.manual_seed(7)
+    model = ref.UNet_LateMetInject(3, 4, 2, depth=2)
+    sd = model.state_dict()
+    sd.update(body)
+    sd["conv_final.weight"] = sd["conv_final.weight"] * 4.0          # a confident head, as in the other fixtures
+    model.load_state_dict(sd)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    gen = torch.Generator().manual_seed(8)
+    meta = torch.rand((x.shape[0], 2, x.shape[2], x.shape[3]), generator=gen) * 2 - 0.5
+    out = {"meta": meta.numpy()}
+    for k, v in sd.items():
+        if k.startswith("conv_final") or k.startswith("post_processing_weights"):
+            out["state/" + k] = v.numpy()
+    model.eval()
+    with torch.no_grad():
+        out["eval_logits"] = model(x, meta).numpy()
+    # the decomposition the product uses, checked here against the reference in fp32 torch:
+    # conv1x1_65(cat(f, m)) == conv1x1_64(f; W[:, :64], b) + W[:, 64] * m
+    model.eval()
+    with torch.no_grad():
+        feats = x
+        enc = []
+        for blk in model.down_convs:
+            feats, bp = blk(feats)
+            enc.append(bp)
+        for i, blk in enumerate(model.up_convs):
+            feats = blk(enc[-(i + 2)], feats)
+        w = model.conv_final.weight
+        split = torch.nn.functional.conv2d(feats, w[:, :64], model.conv_final.bias) + \
+            w[:, 64:, 0, 0].reshape(1, 3, 1, 1) * model.post_processing_weights(meta)
+        d = (split - torch.from_numpy(out["eval_logits"])).abs().max().item()
+    print(f"unet_late_d2.npz: head decomposition vs reference eval logits max|d| = {d:.3g}")
+    assert d < 1e-5
+    model.train()
+    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([10.0, 300.0, 250.0]))
+    model.zero_grad()
+    logits = model(x, meta)
+    loss = crit(logits, y)
+    loss.backward()
+    out["train_logits"] = logits.detach().numpy()
+    out["loss"] = np.array(loss.item(), dtype=np.float64)
+    for name, p_ in model.named_parameters():
+        if name.startswith(("conv_final", "post_processing_weights")) or name in (
+                "up_convs.0.bn2.weight", "up_convs.0.bn2.bias", "up_convs.0.conv2.weight", "down_convs.0.main.0.weight",
+                "down_convs.1.main.3.weight", "up_convs.0.upconv.weight"):
+            out["grad/" + name] = p_.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "unet_late_d2.npz"), **out)
 
 
 class FakeZarrReader:
@@ -357,6 +413,7 @@ if __name__ == "__main__":
     golden_unet(ref, depth=2, hw=32, batch=2, fname="unet_d2.npz", store_state=True)
     golden_unet(ref, depth=5, hw=64, batch=2, fname="unet_d5.npz", store_state=False,
                 grad_subset=("conv_final", "main.1.", "main.4.", "bn1", "bn2", "down_convs.0.main.0", "upconv.bias"))
+    golden_late_meta_inject(ref)
     golden_pipeline()
     golden_train_pipeline()
     for f in sorted(os.listdir(OUT)):

@@ -83,10 +83,62 @@ def test_module_surface_matches_reference_contract(pkg, golden_dir):
     # no CPU fallback on the hot path
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 4, 32, 32))
-    # the non-hot-path variant is plain torch and runs anywhere
+    # the late-metadata variant keeps the reference's 142-entry state_dict and has no CPU fallback either
     lm = M.UNet_LateMetInject(3, 4, 2, depth=2)
-    out = lm(torch.zeros(1, 4, 16, 16), torch.zeros(1, 2, 16, 16))
-    assert out.shape == (1, 3, 16, 16)
+    keys = list(lm.state_dict().keys())
+    assert keys[-8:] == ["conv_final.weight", "conv_final.bias"] + [
+        f"post_processing_weights.main.{i}.{t}" for i in (0, 2, 4) for t in ("weight", "bias")]
+    assert lm.state_dict()["conv_final.weight"].shape == (3, 65, 1, 1)
+    assert len(M.UNet_LateMetInject(3, 4, 2).state_dict()) == 142
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lm(torch.zeros(1, 4, 16, 16), torch.zeros(1, 2, 16, 16))
+    with pytest.raises(RuntimeError, match="UNet_LateMetInject"):      # a wide head on the baseline class is refused
+        M.UNet_Baseline(3, 4, 2, late_meta_inject=True, depth=2)._check_supported(torch.zeros(1, 4, 16, 16))
+
+
+def test_late_meta_inject_composition_against_reference_golden(pkg, golden_dir):
+    """UNet_LateMetInject = native 64-channel network + metadata term (models/unet.py docstring).  Here the native calls
+    are replaced by the fp32 oracle (as the CHECKER: this test pins the module's host logic - the head split, the
+    autograd routing of W[:, :64] / W[:, 64:], the metadata MLP - against the reference-made fixture on the CPU; the
+    GPU test runs the same fixture through the real library)."""
+    M = importlib.import_module("crimac_unet_b200.models.unet")
+    from oracle import unet_oracle as O
+    g2 = np.load(os.path.join(golden_dir, "unet_d2.npz"))
+    gl = np.load(os.path.join(golden_dir, "unet_late_d2.npz"))
+    sd = {k[6:]: torch.from_numpy(g2[k]) for k in g2.files if k.startswith("state/") and "conv_final" not in k}
+    sd.update({k[6:]: torch.from_numpy(gl[k]) for k in gl.files if k.startswith("state/")})
+    m = M.UNet_LateMetInject(3, 4, 2, depth=2)
+    m.load_state_dict(sd, strict=True)
+    x, y, meta = torch.from_numpy(g2["x"]), torch.from_numpy(g2["y"]), torch.from_numpy(gl["meta"])
+    body_names = [n for n, _ in m.named_parameters() if n.startswith(("down_convs", "up_convs"))]
+
+    def oracle_state(head_w, params=None):
+        st = {k: v for k, v in m.state_dict(keep_vars=True).items() if not k.startswith(("conv_final", "post_"))}
+        if params is not None:
+            st.update(dict(zip(body_names, params[:-2])))
+        st["conv_final.weight"], st["conv_final.bias"] = head_w, m.conv_final.bias
+        return st
+
+    m._infer = lambda xx, softmax: O.unet_forward(oracle_state(m._head_weight()), xx, train=False)
+    m._train_forward = lambda xx, params: O.unet_forward(oracle_state(params[-2], params), xx, train=True)
+    m.eval()
+    with torch.no_grad():
+        assert np.allclose(m(x, meta).numpy(), gl["eval_logits"], rtol=0, atol=1e-4)
+    assert m._head_weight() is m._head_weight()                 # cached while the parameter is unchanged
+    m.train()
+    logits = m(x, meta)
+    loss = torch.nn.functional.cross_entropy(logits, y, weight=torch.tensor(O.CLASS_WEIGHTS))
+    loss.backward()
+    assert np.allclose(logits.detach().numpy(), gl["train_logits"], rtol=0, atol=2e-4)
+    assert abs(loss.item() - float(gl["loss"])) < 1e-5
+    named = dict(m.named_parameters())
+    n = 0
+    for k in gl.files:
+        if k.startswith("grad/"):
+            ref = gl[k]
+            assert np.linalg.norm(named[k[5:]].grad.numpy() - ref) <= 1e-3 * np.linalg.norm(ref) + 1e-9, k
+            n += 1
+    assert n >= 12 and named["conv_final.weight"].grad.shape == (3, 65, 1, 1)
 
 
 def test_patch_grid_and_sharding_host_logic(pkg):

@@ -91,6 +91,45 @@ def test_golden_depth2_from_reference(M, golden_dir):
             assert int(m.state_dict()[k[5:]]) == int(g[k])
 
 
+def test_late_meta_inject_variant_against_reference_golden(M, golden_dir):
+    """UNet_LateMetInject (reference unet.py:346-391) with its 64-channel part on the native
+    path, against outputs of the reference class itself (oracle/make_golden.py:golden_late_meta_inject)."""
+    g2 = np.load(os.path.join(golden_dir, "unet_d2.npz"))
+    gl = np.load(os.path.join(golden_dir, "unet_late_d2.npz"))
+    sd = {k[6:]: torch.from_numpy(g2[k]) for k in g2.files if k.startswith("state/") and "conv_final" not in k}
+    sd.update({k[6:]: torch.from_numpy(gl[k]) for k in gl.files if k.startswith("state/")})
+    m = M.UNet_LateMetInject(3, 4, 2, depth=2)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    x, y, meta = (torch.from_numpy(a).to(dev) for a in (g2["x"], g2["y"], gl["meta"]))
+    m.eval()
+    with torch.no_grad():
+        lg = m(x, meta)
+        lg2 = m(x, meta)
+    ref = torch.from_numpy(gl["eval_logits"])
+    assert (lg.cpu() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    assert torch.equal(lg, lg2)
+    m.train()
+    logits = m(x, meta)
+    loss = torch.nn.functional.cross_entropy(logits, y, weight=torch.tensor(O.CLASS_WEIGHTS, device=dev))
+    loss.backward()
+    ref_t = torch.from_numpy(gl["train_logits"])
+    assert (logits.detach().cpu() - ref_t).abs().max().item() < 2e-2 * ref_t.abs().max().item()
+    assert abs(loss.item() - float(gl["loss"])) < 2e-3 * float(gl["loss"])
+    named = dict(m.named_parameters())
+    assert named["conv_final.weight"].grad.shape == (3, 65, 1, 1)
+    # gradients upstream of any bf16 gradient tensor: head (both halves), metadata MLP, last BatchNorm
+    for k in gl.files:
+        if k.startswith("grad/") and k[5:].startswith(("conv_final", "post_processing_weights", "up_convs.0.bn2")):
+            assert _rel(named[k[5:]].grad.cpu(), torch.from_numpy(gl[k])) < 2e-2, k
+    for k in ("up_convs.0.conv2.weight", "down_convs.1.main.3.weight", "up_convs.0.upconv.weight"):
+        gref = torch.from_numpy(gl["grad/" + k])
+        cos = torch.nn.functional.cosine_similarity(named[k].grad.cpu().flatten(), gref.flatten(), dim=0).item()
+        assert cos > 0.9, (k, cos)
+    for n_, p_ in m.named_parameters():
+        assert p_.grad is not None and torch.isfinite(p_.grad).all(), n_
+
+
 @pytest.mark.parametrize("B,H,W,in_ch", [(4, 256, 256, 4), (2, 64, 96, 6)])
 def test_inference_probabilities_vs_fp32_oracle(M, B, H, W, in_ch):
     torch.manual_seed(0)
