@@ -713,6 +713,7 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num
   if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 31) || p.out_pitch % 16)) return cudaErrorInvalidValue;
   if (p.pool_out && ((reinterpret_cast<uintptr_t>(p.pool_out) & 31) || p.pool_pitch % 16)) return cudaErrorInvalidValue;
   if (p.b_mn && ((epi != EPI_STORE && epi != EPI_BNRED) || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
+  if (p.b_mn && p.taps == 9 && !p.halo) return cudaErrorInvalidValue;  // 3x3 MN-major weights: halo main loop only
   if (epi == EPI_BNRED && (!p.b_mn || !p.bnr_raw || !p.bnr_scale || !p.bnr_shift || !p.stats)) return cudaErrorInvalidValue;
 #define CASE(BN, EP)                                                               \
   if (block_n == BN && epi == EP && !p.b_mn)                                       \

@@ -358,11 +358,13 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   if (!encode_maps) return 0;
 
   // ---- launch descriptors (tensor maps encoded once)
-  const bool use_halo = getenv("CRIMAC_NO_HALO") == nullptr;  // A/B switch for measurements
+  // A/B switch for measurements: FORWARD 3x3 convs through the plain nine-box main loop.  Backward-data always uses the
+  // halo main loop: the MN-major view of the forward-packed 3x3 weights (b_mn) exists only there.
+  const bool use_halo = getenv("CRIMAC_NO_HALO") == nullptr;
   auto geom = [&](ConvParams& p, int H, int W, int n_total, int bn) {
     p.H = H;
     p.W = W;
-    p.halo = (p.taps == 9 && use_halo) ? 1 : 0;
+    p.halo = (p.taps == 9 && (use_halo || p.b_mn)) ? 1 : 0;
     p.tiles_x = p.halo ? (W + 7) / 8 : (W + TILE_W - 1) / TILE_W;
     p.tiles_y = p.halo ? (H + 15) / 16 : (H + TILE_H - 1) / TILE_H;
     p.n_tiles = n_total / bn;
@@ -401,10 +403,10 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         p.taps = 9;
         p.tap_mode = 0;
         p.cin = L.cout;
-        geom(p, H, W, L.cin, L.bn_bwd);
-        if ((rc = conv_map(p, gr))) return rc;
         p.b_mn = 1;
         p.b_tap_cols = L.cin;
+        geom(p, H, W, L.cin, L.bn_bwd);
+        if ((rc = conv_map(p, gr))) return rc;
         if ((rc = make_weight_map(&p.b_map, L.w_fwd, L.cout, 9 * L.cin, 64))) return rc;
         p.out = L.gin.ptr;
         p.out_pitch = L.gin.pitch;

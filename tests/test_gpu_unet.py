@@ -431,3 +431,20 @@ def test_first_conv_channel_counts(M, in_ch):
         val = m.forward_fp32(x, softmax=True)
     assert (got - ref).abs().max().item() <= PROB_TOL
     assert (val - ref).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("switches", ["CRIMAC_FC_CUDACORE"])
+def test_non_default_kernel_variants_pass_the_same_parity_tests(switches):
+    """The environment switches of INTEGRATION.md section 4 select alternative kernels.  They are read when the library
+    creates a context, so the parity tests are re-run in a child process with the switch set.  Only the CUDA-core first
+    conv is kept under test; the other switches are measurement aids whose status is stated in INTEGRATION.md."""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    for s_ in switches.split():
+        env[s_] = "1"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_unet.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "golden_depth2 or train_step_vs_oracle or trainer_reduces_the_loss or first_conv_channel_counts"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
