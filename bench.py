@@ -103,9 +103,43 @@ def cpu_train_patches_per_s(batch, reps, warm=1):
     return batch / dt, cores, dt
 
 
+def cpu_infer_patches_per_s(batch, reps, warm=1):
+    """Times the oracle port of the reference inference call (eval forward + softmax, pipeline.py:205-218; fp32 torch
+    CPU, all host cores) - BASELINE.json configs[0], the reference's own CPU-runnable case."""
+    import torch
+    from oracle import unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sys.path.insert(0, os.path.join(ROOT, "crimac-classifiers-unet_b200"))
+    import models.unet as M
+    state = {k: v.clone() for k, v in M.UNet_Baseline(3, 4).state_dict().items()}
+    x = O.synthetic_echogram(batch, 4, 256, 256, seed=0)
+    with torch.no_grad():
+        for _ in range(warm):
+            O.softmax_probs(O.unet_forward(state, x))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.softmax_probs(O.unet_forward(state, x))
+    dt = (time.perf_counter() - t0) / reps
+    return batch / dt, cores, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.mode == "infer":
+        sample_batch = 4
+        pps, cores, dt = cpu_infer_patches_per_s(sample_batch, args.steps, warm=max(1, min(args.warmup, 2)))
+        sample = f"{sample_batch} of the {args.batch} patches of a batch per step (fp32 torch CPU, {cores} threads), oracle port of the reference eval forward + softmax"
+        print(json.dumps({
+            "impl": "reference", "metric": "U-Net 256x256 patches/s, inference (softmax probabilities)", "value": pps,
+            "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "UNet inference, batch %d of 4x256x256" % args.batch, "sample": sample},
+            "cpu_baseline": {"value": pps, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": pps, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
     # bounded sample: 2 patches per step (the full batch of 32 takes ~40 s per step on 8 cores)
     sample_batch = 2

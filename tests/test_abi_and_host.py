@@ -209,6 +209,19 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
+def test_bench_reference_arm_inference_mode():
+    """BASELINE.json configs[0] (the reference's CPU-runnable inference case) through the same arm."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--mode", "infer", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["impl"] == "reference" and "inference" in d["metric"] and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
+
+
 def test_bench_flop_accounting_matches_the_survey_numbers():
     """bench.py's generic FLOP counter reproduces SURVEY.md section 8(d) / BASELINE.md exactly (4x256x256 and 6x512x512)."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
