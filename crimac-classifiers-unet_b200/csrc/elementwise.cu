@@ -354,6 +354,9 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict
     const float lse = mx + logf(sum);
     const long long y = labels[p];
     const bool use = (y != ignore_index) && y >= 0 && y < ncls;
+    // a label outside [0, n_classes) that is not ignore_index trips a device assert in PyTorch; here it poisons the
+    // loss (NaN) so that the mistake is loud without a host synchronisation
+    if (y != ignore_index && !use) la = static_cast<double>(NAN);
     const float wy = use ? cw[y] : 0.f;
 #pragma unroll
     for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
@@ -392,6 +395,67 @@ __global__ void ce_finalize_kernel(const double* partials, int nblocks, float* o
   out[0] = static_cast<float>(a / b);  // all-ignored batch -> NaN, as the reference
   out[1] = static_cast<float>(1.0 / b);
   out[2] = static_cast<float>(b);
+}
+
+// ============================================================================ validation-path loss
+// pipeline.py:222-239 (set_label_ignore_val: -70 overlap, -30 refined boundary, -100 outside data, -10 unused species
+// -> ignore; -50 below seabed -> background 0), :264 (the same weighted CE on the remapped labels) and :269-270
+// (softmax, SANDEEL channel) in one pass over the eval-mode logits.  LT = int16 (what the dataset emits) or int64.
+template <typename LT>
+__global__ void __launch_bounds__(256) eval_loss_kernel(const float* __restrict__ logits, const LT* __restrict__ labels,
+                                                        const float* __restrict__ cw, int ncls, long HW, long total,
+                                                        int prob_class, float* __restrict__ prob_out,
+                                                        long long* __restrict__ labels_out, double* partials) {
+  __shared__ double s_a[8], s_b[8];
+  double la = 0.0, lb = 0.0;
+  for (long p = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = p / HW, r = p - n * HW;
+    float z[CRIMAC_MAX_CLASSES];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) {
+        z[k] = logits[(n * ncls + k) * HW + r];
+        mx = fmaxf(mx, z[k]);
+      }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) sum += expf(z[k] - mx);
+    const float lse = mx + logf(sum);
+    long long y = static_cast<long long>(labels[p]);
+    if (y == -70 || y == -30 || y == -100 || y == -10) y = -100;
+    else if (y == -50) y = 0;
+    if (labels_out != nullptr) labels_out[p] = y;
+    const bool use = (y != -100) && y >= 0 && y < ncls;
+    if (y != -100 && !use) la = static_cast<double>(NAN);  // invalid label: PyTorch asserts, we poison the loss
+    const float wy = use ? cw[y] : 0.f;
+#pragma unroll
+    for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+      if (k < ncls) {
+        if (use && k == y) la += static_cast<double>(wy) * static_cast<double>(lse - z[k]);
+        if (k == prob_class && prob_out != nullptr) prob_out[p] = expf(z[k] - lse);
+      }
+    lb += wy;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    la += __shfl_xor_sync(0xffffffffu, la, o);
+    lb += __shfl_xor_sync(0xffffffffu, lb, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_a[threadIdx.x >> 5] = la;
+    s_b[threadIdx.x >> 5] = lb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) {
+      la += s_a[i];
+      lb += s_b[i];
+    }
+    partials[2 * blockIdx.x] = la;
+    partials[2 * blockIdx.x + 1] = lb;
+  }
 }
 
 // ============================================================================ 1x1 head backward
@@ -550,6 +614,7 @@ __global__ void __launch_bounds__(256) head_ce_fused_kernel(View act, const floa
       for (int k = 0; k < NCLS; ++k) sum += expf(z[k] - mx);
       const float lse = mx + logf(sum);
       const bool use = ok[u] && (y[u] != ignore_index) && y[u] >= 0 && y[u] < NCLS;
+      if (g == 0 && ok[u] && y[u] != ignore_index && !use) la = static_cast<double>(NAN);  // invalid label: see ce_fwd_bwd_kernel
       float wy = 0.f, zy = 0.f;
 #pragma unroll
       for (int k = 0; k < NCLS; ++k)
@@ -1126,6 +1191,23 @@ cudaError_t launch_ce(const float* logits, const long long* labels, const float*
   int blocks = grid_for(total, 256);
   if (blocks > ce_blocks()) blocks = ce_blocks();
   ce_fwd_bwd_kernel<<<blocks, 256, 0, st>>>(logits, labels, cw, ncls, HW, total, ignore_index, dlogits, partials);
+  ce_finalize_kernel<<<1, 1, 0, st>>>(partials, blocks, out3);
+  return cudaGetLastError();
+}
+cudaError_t launch_eval_loss(const float* logits, const void* labels, int label_bits, const float* cw, int ncls, int NB,
+                             long HW, int prob_class, float* prob_out, long long* labels_out, double* partials,
+                             float* out3, cudaStream_t st) {
+  const long total = NB * HW;
+  int blocks = grid_for(total, 256);
+  if (blocks > ce_blocks()) blocks = ce_blocks();
+  if (label_bits == 16)
+    eval_loss_kernel<short><<<blocks, 256, 0, st>>>(logits, static_cast<const short*>(labels), cw, ncls, HW, total,
+                                                    prob_class, prob_out, labels_out, partials);
+  else if (label_bits == 64)
+    eval_loss_kernel<long long><<<blocks, 256, 0, st>>>(logits, static_cast<const long long*>(labels), cw, ncls, HW,
+                                                        total, prob_class, prob_out, labels_out, partials);
+  else
+    return cudaErrorInvalidValue;
   ce_finalize_kernel<<<1, 1, 0, st>>>(partials, blocks, out3);
   return cudaGetLastError();
 }

@@ -102,6 +102,10 @@ cudaError_t launch_head_fwd(View act, const float* hw, const float* hb, int ncls
 int ce_blocks();
 cudaError_t launch_ce(const float* logits, const long long* labels, const float* cw, int ncls, int NB, long HW,
                       long long ignore_index, float* dlogits, double* partials, float* out3, cudaStream_t st);
+// validation path (pipeline.py:222-239,264,269-270): label remap + weighted CE + one class's softmax probability
+cudaError_t launch_eval_loss(const float* logits, const void* labels, int label_bits, const float* cw, int ncls, int NB,
+                             long HW, int prob_class, float* prob_out, long long* labels_out, double* partials,
+                             float* out3, cudaStream_t st);
 int head_bwd_blocks();
 cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act, const float* hw, int ncls, View dact,
                             float* partials, float* dw, float* db, int accumulate, cudaStream_t st);

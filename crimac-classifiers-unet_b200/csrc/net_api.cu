@@ -585,7 +585,8 @@ extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* w
   int major = 0, minor = 0;
   CRIMAC_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   CRIMAC_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
-  CRIMAC_REQUIRE(major == 10, "libcrimac_b200 runs on sm_100a (B200) only; there is no fallback path");
+  // the library carries ONE cubin, sm_100a: architecture-specific code does not load on sm_103 (B300) or any other 10.x part
+  CRIMAC_REQUIRE(major == 10 && minor == 0, "libcrimac_b200 runs on sm_100a (B200, compute capability 10.0) only; there is no fallback path");
   crimac_ctx* c = new (std::nothrow) crimac_ctx;
   CRIMAC_REQUIRE(c != nullptr, "out of host memory");
   c->cfg = *cfg;
@@ -653,6 +654,10 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
   const int sms = device_num_sms();
   const int D = c->D;
   const int last = c->dec2[D - 2];
+  // nn.BatchNorm2d raises "Expected more than 1 value per channel when training" (torch/nn/functional.py) when the
+  // deepest level has a single value per channel; a silent var = 0 would produce huge gradients instead
+  CRIMAC_REQUIRE(!train || static_cast<long>(nb) * level_h(c, D - 1) * level_w(c, D - 1) > 1,
+                 "train-mode BatchNorm needs more than 1 value per channel at the deepest level (nb*H*W/4^(depth-1) > 1)");
   auto run_conv = [&](int idx) -> int {
     Conv3& L = c->conv[idx];
     const int H = level_h(c, L.level), W = level_w(c, L.level);

@@ -180,3 +180,150 @@ extern "C" int crimac_op_wgrad_halo(const void* dy, int dy_pitch, int cout, cons
   CRIMAC_CHECK_CUDA(launch_wgrad_unpack(scratch, dw, cout, cin, 9, 0, st));
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Op-level entry points of the HBM-bound kernels (elementwise.cu, wgrad_gemm.cu's unpack, the weight packers): the
+// parity tests pin each of them against torch fp32 autograd of the same operator on identical bf16-rounded inputs.
+// Scratch: every call that needs per-block partial sums takes `scratch` of at least crimac_op_scratch_bytes() bytes.
+extern "C" size_t crimac_op_scratch_bytes() {
+  // BN backward: reduce_blocks() x 2 x C floats + 2 x C (c1, c2), C <= 1024; head: head_bwd_blocks() x (8*64+8) floats
+  // + head_bwd_blocks() x 2 doubles; statistics rows of the conv kernels are NOT part of this
+  return static_cast<size_t>(16) << 20;
+}
+
+static View mk_view(const void* p, int N, int H, int W, int C, int pitch) {
+  return View{static_cast<bf16*>(const_cast<void*>(p)), N, H, W, C, pitch};
+}
+
+// Train-mode BatchNorm, forward half 1 (unet.py:78,81,121-122): partial rows [rows][2][C] (sum, sum of squares, as the
+// conv kernels' EPI_STATS epilogue writes them) -> scale/shift for the apply pass, batch mean / inv-std for backward,
+// running statistics (momentum, unbiased variance) and num_batches_tracked.
+extern "C" int crimac_op_bn_finalize(const float* partials, int rows, int C, double count, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var,
+                                     int64_t* num_batches_tracked, float momentum, float eps, float* scale, float* shift,
+                                     float* save_mean, float* save_invstd, void* stream) {
+  CRIMAC_REQUIRE(partials && gamma && beta && scale && shift && save_mean && save_invstd, "NULL tensor");
+  CRIMAC_REQUIRE(rows >= 1 && C >= 1 && count > 1.0, "rows, C >= 1 and more than one value per channel");
+  CRIMAC_CHECK_CUDA(launch_bn_finalize(partials, rows, C, count, gamma, beta, running_mean, running_var,
+                                       reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, scale, shift,
+                                       save_mean, save_invstd, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Forward half 2: act = relu(raw*scale + shift) (+ 2x2 max-pool copy and its 2-bit-per-channel arg-max map).
+// raw/act: NHWC bf16 (N,H,W,C) views with pixel pitches; pool (optional): (N,H/2,W/2,C); pool_arg (optional with pool):
+// uint16 per (pooled pixel, 8-channel group).
+extern "C" int crimac_op_bn_apply(const void* raw, int raw_pitch, int N, int H, int W, int C, const float* scale,
+                                  const float* shift, void* act, int act_pitch, void* pool, int pool_pitch,
+                                  uint16_t* pool_arg, void* stream) {
+  CRIMAC_REQUIRE(raw && act && scale && shift, "NULL tensor");
+  CRIMAC_REQUIRE(C % 8 == 0 && raw_pitch % 8 == 0 && act_pitch % 8 == 0, "channels / pitches must be multiples of 8");
+  CRIMAC_REQUIRE(pool == nullptr || (H % 2 == 0 && W % 2 == 0 && pool_pitch % 8 == 0), "pooling needs even H, W");
+  View vp = mk_view(pool, N, H / 2, W / 2, C, pool_pitch);
+  CRIMAC_CHECK_CUDA(launch_bn_apply(mk_view(raw, N, H, W, C, raw_pitch), scale, shift, mk_view(act, N, H, W, C, act_pitch),
+                                    vp, pool ? pool_arg : nullptr, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// BatchNorm + ReLU backward (autograd of unet.py:76-83,135-136): dact = gradient w.r.t. the post-ReLU activation,
+// raw = the conv output saved in forward; writes draw (gradient w.r.t. the conv output, bf16), dgamma, dbeta and the
+// conv-bias gradient (exactly zero under train-mode BatchNorm).  gscale (optional): one device float multiplied into dact.
+extern "C" int crimac_op_bn_bwd(const void* dact, int dact_pitch, const void* raw, int raw_pitch, int N, int H, int W,
+                                int C, const float* scale, const float* shift, const float* mean, const float* invstd,
+                                void* draw, int draw_pitch, float* dgamma, float* dbeta, float* dbias,
+                                const float* gscale, void* scratch, void* stream) {
+  CRIMAC_REQUIRE(dact && raw && draw && scale && shift && mean && invstd && dgamma && dbeta && scratch, "NULL tensor");
+  CRIMAC_REQUIRE(C % 8 == 0 && C <= 1024, "C must be a multiple of 8, at most 1024");
+  float* partials = static_cast<float*>(scratch);
+  float* c1c2 = partials + static_cast<size_t>(reduce_blocks()) * 2 * C;
+  CRIMAC_CHECK_CUDA(launch_bn_bwd(mk_view(dact, N, H, W, C, dact_pitch), mk_view(raw, N, H, W, C, raw_pitch), scale, shift,
+                                  mean, invstd, mk_view(draw, N, H, W, C, draw_pitch), dgamma, dbeta, dbias, 0, partials,
+                                  c1c2, gscale, 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Max-pool backward + skip-gradient add (autograd of unet.py:86,92,132): dact[2x2 window] = dskip[window] + (first
+// maximal element ? dpool : 0), arg-max from the map crimac_op_bn_apply wrote.  dskip may be NULL (no skip branch).
+extern "C" int crimac_op_pool_bwd_add(const uint16_t* pool_arg, const void* dpool, int dpool_pitch, const void* dskip,
+                                      int dskip_pitch, void* dact, int dact_pitch, int N, int H, int W, int C,
+                                      void* stream) {
+  CRIMAC_REQUIRE(pool_arg && dpool && dact, "NULL tensor");
+  CRIMAC_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "C multiple of 8, even H and W");
+  CRIMAC_CHECK_CUDA(launch_pool_bwd_add(pool_arg, mk_view(dpool, N, H / 2, W / 2, C, dpool_pitch),
+                                        mk_view(dskip, N, H, W, C, dskip_pitch), mk_view(dact, N, H, W, C, dact_pitch),
+                                        static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// 1x1 head + class-weighted cross-entropy + head backward in ONE pass (unet.py:342, pipeline.py:135-138,176-177).
+// act: NHWC bf16 (N,H,W,64).  Outputs: dact (N,H,W,64) bf16 = UNNORMALISED gradient (multiply by out3[1]), dw (ncls,64),
+// db (ncls) normalised, out3 = {loss, 1/sum_w, sum_w}.
+extern "C" int crimac_op_head_ce(const void* act, int act_pitch, int N, int H, int W, const float* hw, const float* hb,
+                                 int ncls, const int64_t* labels, const float* cw, int64_t ignore_index, void* dact,
+                                 int dact_pitch, float* dw, float* db, float* out3, void* scratch, void* stream) {
+  CRIMAC_REQUIRE(act && hw && hb && labels && cw && dact && dw && db && out3 && scratch, "NULL tensor");
+  CRIMAC_REQUIRE(ncls >= 1 && ncls <= CRIMAC_MAX_CLASSES, "n_classes must be 1..8");
+  float* partials = static_cast<float*>(scratch);  // head_bwd_blocks() x (ncls*64 + ncls) floats < 8 MB
+  double* lp = reinterpret_cast<double*>(static_cast<uint8_t*>(scratch) + (static_cast<size_t>(8) << 20));
+  CRIMAC_CHECK_CUDA(launch_head_ce_fused(mk_view(act, N, H, W, 64, act_pitch), hw, hb, ncls,
+                                         reinterpret_cast<const long long*>(labels), cw, ignore_index,
+                                         mk_view(dact, N, H, W, 64, dact_pitch), partials, lp, dw, db, out3,
+                                         static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// The same three steps as separate kernels (the autograd path with a user-supplied loss): head forward -> logits NCHW
+// fp32; head backward from dlogits (x optional *gscale) -> dact, dw, db.
+extern "C" int crimac_op_head_fwd(const void* act, int act_pitch, int N, int H, int W, const float* hw, const float* hb,
+                                  int ncls, float* logits, void* stream) {
+  CRIMAC_REQUIRE(act && hw && hb && logits && ncls >= 1 && ncls <= CRIMAC_MAX_CLASSES, "bad argument");
+  CRIMAC_CHECK_CUDA(launch_head_fwd(mk_view(act, N, H, W, 64, act_pitch), hw, hb, ncls, logits,
+                                    static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+extern "C" int crimac_op_head_bwd(const float* dlogits, const float* gscale, const void* act, int act_pitch, int N, int H,
+                                  int W, const float* hw, int ncls, void* dact, int dact_pitch, float* dw, float* db,
+                                  void* scratch, void* stream) {
+  CRIMAC_REQUIRE(dlogits && act && hw && dact && dw && db && scratch && ncls >= 1 && ncls <= CRIMAC_MAX_CLASSES, "bad argument");
+  CRIMAC_CHECK_CUDA(launch_head_bwd(dlogits, gscale, mk_view(act, N, H, W, 64, act_pitch), hw, ncls,
+                                    mk_view(dact, N, H, W, 64, dact_pitch), static_cast<float*>(scratch), dw, db, 0,
+                                    static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Per-channel sum over pixels of an NHWC bf16 view (ConvTranspose2d bias gradient).
+extern "C" int crimac_op_colsum(const void* v, int pitch, int N, int H, int W, int C, float* out, void* scratch,
+                                void* stream) {
+  CRIMAC_REQUIRE(v && out && scratch && C % 8 == 0 && C <= 1024, "bad argument");
+  CRIMAC_CHECK_CUDA(launch_view_colsum(mk_view(v, N, H, W, C, pitch), static_cast<float*>(scratch), out, 0,
+                                       static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// fp32 parameters -> bf16 GEMM operands.  kind 0: conv (Cout,Cin,3,3) -> [Cout][tap][Cin]; kind 1: ConvTranspose
+// (Cin,Cout,2,2) -> [(ky*2+kx)*Cout + co][Cin].
+extern "C" int crimac_op_pack(int kind, const float* w, int cout, int cin, void* out, void* stream) {
+  CRIMAC_REQUIRE(w && out && (kind == 0 || kind == 1), "bad argument");
+  CRIMAC_REQUIRE(cin % 64 == 0 && cout % 8 == 0, "Cin must be a multiple of 64, Cout of 8");
+  PackTable t{};
+  t.n = 1;
+  t.e[0] = PackEntry{w, static_cast<bf16*>(out), cout, cin, 0};
+  CRIMAC_CHECK_CUDA(kind == 0 ? launch_pack_conv3x3_all(t, static_cast<cudaStream_t>(stream))
+                              : launch_pack_convt_all(t, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// The end-of-backward un-pack of up to 24 layers in one launch: scratch_i [taps_i][mn_i] -> dw_i [mn_i][taps_i], the
+// scratch is left zeroed.  Arrays are HOST arrays of n entries.
+extern "C" int crimac_op_wgrad_unpack_all(int n, float* const* scratch, float* const* dw, const int64_t* mn,
+                                          const int* taps, void* stream) {
+  CRIMAC_REQUIRE(n >= 1 && n <= 24 && scratch && dw && mn && taps, "bad argument");
+  UnpackTable t{};
+  t.n = n;
+  for (int i = 0; i < n; ++i) {
+    CRIMAC_REQUIRE(taps[i] >= 1 && taps[i] <= 9 && mn[i] >= 1, "taps must be 1..9");
+    t.e[i] = UnpackEntry{scratch[i], dw[i], static_cast<long>(mn[i]), taps[i], 0};
+  }
+  CRIMAC_CHECK_CUDA(launch_wgrad_unpack_all(t, static_cast<cudaStream_t>(stream)));
+  return 0;
+}

@@ -140,3 +140,20 @@ extern "C" int crimac_sgd_step(float* params, float* mom, const float* grads, si
   CRIMAC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// Validation step of the training loop (pipeline.py:249-270, get_predictions_dataloader): on the eval-mode logits,
+// remap the label codes (set_label_ignore_val, :222-239), evaluate the same class-weighted CE (:264) and extract the
+// softmax probability of one class (SANDEEL, :269-270) - one pass, no host work.  scratch: >= 16 KB.
+extern "C" int crimac_eval_loss(const float* logits, int nb, int n_classes, int H, int W, const void* labels,
+                                int label_bits, const float* class_w, int prob_class, float* prob_out,
+                                int64_t* labels_out, float* out3, void* scratch, void* stream) {
+  CRIMAC_REQUIRE(logits && labels && class_w && out3 && scratch, "NULL tensor");
+  CRIMAC_REQUIRE(nb >= 1 && H >= 1 && W >= 1, "empty input");
+  CRIMAC_REQUIRE(n_classes >= 1 && n_classes <= CRIMAC_MAX_CLASSES, "n_classes must be 1..8");
+  CRIMAC_REQUIRE(label_bits == 16 || label_bits == 64, "labels must be int16 or int64");
+  CRIMAC_REQUIRE(prob_out == nullptr || (prob_class >= 0 && prob_class < n_classes), "prob_class out of range");
+  CRIMAC_CHECK_CUDA(launch_eval_loss(logits, labels, label_bits, class_w, n_classes, nb, static_cast<long>(H) * W,
+                                     prob_class, prob_out, reinterpret_cast<long long*>(labels_out),
+                                     static_cast<double*>(scratch), out3, static_cast<cudaStream_t>(stream)));
+  return 0;
+}

@@ -54,6 +54,7 @@ class Context:
         self.n_state = self.L.crimac_state_count(ctypes.byref(self.cfg))
         self.n_grad = self.L.crimac_grad_count(ctypes.byref(self.cfg))
         self.prepared_key = None
+        self.fwd_stamp = 0   # counts train-mode forwards: the workspace holds the saved activations of the LAST one only
 
     def __del__(self):
         try:

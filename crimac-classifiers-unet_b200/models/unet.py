@@ -17,7 +17,6 @@ import weakref
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 def _runtime():
@@ -60,8 +59,8 @@ class DownConv(nn.Module):
     """Encoder block: (conv3x3, BN, ReLU) x 2 and an optional 2x2 max-pool (reference unet.py:63-93).
 
     ``main`` keeps the reference's Sequential indexing (0 conv, 1 bn, 2 relu, 3 conv, 4 bn, 5 relu) because the
-    state_dict keys ``main.0/1/3/4.*`` depend on it.  ``forward`` is the plain-torch composition; the native engine
-    bypasses it and only reads the parameters.
+    state_dict keys ``main.0/1/3/4.*`` depend on it.  The block is a PARAMETER HOLDER: the native engine reads its
+    tensors, and calling the block on its own raises (there is no torch / cuDNN path in this package).
     """
 
     def __init__(self, in_channels, out_channels, pooling=True):
@@ -75,8 +74,8 @@ class DownConv(nn.Module):
             self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
 
     def forward(self, x):
-        before_pool = self.main(x)
-        return (self.pool(before_pool) if self.pooling else before_pool), before_pool
+        raise RuntimeError("crimac_unet_b200.DownConv is a parameter holder: the block only runs as part of "
+                           "UNet_Baseline / UNet_LateMetInject through libcrimac_b200.so (no per-block torch path)")
 
 
 class UpConv(nn.Module):
@@ -94,10 +93,8 @@ class UpConv(nn.Module):
         self.bn2 = nn.BatchNorm2d(out_channels)
 
     def forward(self, from_down, from_up):
-        up = self.upconv(from_up)
-        merged = torch.cat((up, from_down), 1) if self.merge_mode == "concat" else up + from_down
-        y = F.relu(self.bn1(self.conv1(merged)))
-        return F.relu(self.bn2(self.conv2(y)))
+        raise RuntimeError("crimac_unet_b200.UpConv is a parameter holder: the block only runs as part of "
+                           "UNet_Baseline / UNet_LateMetInject through libcrimac_b200.so (no per-block torch path)")
 
 
 class MetaPostProcessing(nn.Module):
@@ -135,6 +132,12 @@ class _NativeUNetFunction(torch.autograd.Function):
         eng.prepare(state, True)
         logits = torch.empty((x.shape[0], model.n_classes, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
         eng.forward_train(state, x, logits)
+        model._native_mutated()          # BatchNorm running statistics were updated through raw pointers
+        # The saved activations live in the engine's workspace, not in ctx: ONE forward may be outstanding per engine.
+        # Stamp this forward so that backward can tell whether a later forward (or a parameter update) invalidated it.
+        eng.fwd_stamp += 1
+        ctx.stamp = (eng.fwd_stamp, model._native_gen, tuple(p._version for p in params))
+        ctx.params = params
         ctx.model, ctx.eng = model, eng
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.save_for_backward(x, params[-2])
@@ -144,6 +147,13 @@ class _NativeUNetFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         x, head_w = ctx.saved_tensors
         model, eng = ctx.model, ctx.eng
+        now = (eng.fwd_stamp, model._native_gen, tuple(p._version for p in ctx.params))
+        if now != ctx.stamp:
+            raise RuntimeError(
+                "crimac_unet_b200: backward() of a train-mode forward whose saved activations are gone - another "
+                "train-mode forward ran on this model (same input shape), or its parameters changed, between this "
+                "forward and its backward.  The native path keeps ONE set of saved activations per (model, H, W): run "
+                "each forward's backward before the next forward (gradient accumulation: call backward per micro-batch).")
         sizes = [int(torch.Size(sh).numel()) for sh in ctx.shapes]
         arena = torch.empty(sum(sizes), dtype=torch.float32, device=x.device)
         grads, off = [], 0
@@ -219,6 +229,13 @@ class _NativePlumbing:
     and UNet_LateMetInject; the sub-modules stay parameter holders)."""
 
     _native_head_in = 64   # input channels of the 1x1 head the library computes
+    _native_gen = 0        # bumped whenever native code wrote parameters / BN buffers through raw pointers
+
+    def _native_mutated(self):
+        """Native kernels write parameters (crimac_sgd_step) and BatchNorm running statistics (bn_finalize) through
+        raw pointers, which torch's tensor._version cannot see: every such call bumps this counter, and the eval
+        path's packed bf16 weights / folded BatchNorm are rebuilt when it has moved."""
+        self._native_gen += 1
 
     def _check_supported(self, x):
         problems = []
@@ -295,7 +312,7 @@ class _NativePlumbing:
         x = self._prep_input(x)
         eng = self._engine_for(x, train=False)
         state = eng.state_table(self._state_tensors())
-        key = self._versions()
+        key = (self._versions(), self._native_gen)
         if eng.prepared_key != key:
             eng.prepare(state, False)
             eng.prepared_key = key
@@ -356,7 +373,8 @@ class UNet_Baseline(_NativePlumbing, UNet):
         """Forward + class-weighted CE + backward in one native call (pipeline.py:171-177).
 
         Fills ``p.grad`` of every parameter (views of one flat arena kept in ``self._grad_arena``) and returns the
-        loss as a 0-dim device tensor (no host sync)."""
+        loss as a 0-dim device tensor (no host sync).  Gradients are OVERWRITTEN, not accumulated (the call is
+        ``zero_grad(); loss.backward()`` in one): accumulate over micro-batches by summing the arena yourself."""
         if not self.training:
             raise RuntimeError("train_step_fused() needs model.train()")
         x = self._prep_input(x)
@@ -367,15 +385,22 @@ class UNet_Baseline(_NativePlumbing, UNet):
         if arena is None or arena.numel() != total or arena.device != x.device:
             arena = torch.zeros(total, dtype=torch.float32, device=x.device)
             self._grad_arena = arena
-            off = 0
-            for p in params:
-                p.grad = arena[off:off + p.numel()].view_as(p)
-                off += p.numel()
-        grads = [p.grad for p in params]
+        # (re-)seat every p.grad as a view of the arena: optimizer.zero_grad(set_to_none=True), model.zero_grad() or
+        # user code may have dropped or replaced the views since the last call
+        off, base, grads = 0, arena.data_ptr(), []
+        for p in params:
+            g = p.grad
+            if g is None or g.data_ptr() != base + 4 * off or g.shape != p.shape or g.dtype != torch.float32:
+                g = arena[off:off + p.numel()].view_as(p)
+                p.grad = g
+            grads.append(g)
+            off += p.numel()
         loss3 = torch.empty(4, dtype=torch.float32, device=x.device)
         state = eng.state_table(self._state_tensors())
         eng.train_step(state, x, labels.contiguous().long(), class_weight.contiguous().float(), ignore_index,
                        eng.grad_table(grads), loss3)
+        self._native_mutated()           # BatchNorm running statistics
+        eng.fwd_stamp += 1               # the saved activations of an outstanding autograd forward are gone
         return loss3[0]
 
 

@@ -108,6 +108,7 @@ class SurveyPredictor:
         self.model, self.patch_hw, self.overlap = model, tuple(patch_hw), int(overlap)
         self.preload_n_pings, self.batch_size = int(preload_n_pings), int(batch_size)
         self.classes, self.seabed_pad = tuple(classes), int(seabed_pad)
+        self.last_chunk_patches = 0
 
     def chunk_geometry(self, start, end, n_range, n_pings_total, seabed_max=None):
         """(grid, (data_ping0, data_ping1)) for one chunk; the range extent is cut at max seabed + 50 when known."""
@@ -139,6 +140,7 @@ class SurveyPredictor:
         for (s, e) in chunks:
             smax = seabed_max_of(s, e) if seabed_max_of is not None else None
             grid, (d0, d1) = self.chunk_geometry(s, e, n_range, n_pings, smax)
+            self.last_chunk_patches = int(grid.shape[0])
             loaded = load_chunk(d0, d1, s, e)
             sv, labels, seabed = loaded if isinstance(loaded, tuple) else (loaded, None, None)
             yield s, e, self.predict_chunk(sv, d0, grid, s, e, labels=labels, seabed=seabed)

@@ -4,7 +4,11 @@ SGD(lr, momentum) + ExponentialLR, one optimizer step per batch).
 One process per GPU.  Parameters and gradients live in two flat fp32 arenas so that the gradient exchange is ONE
 NCCL all-reduce over NVLink (the path has no other collective: BatchNorm statistics stay per replica, as in the
 reference which has no SyncBN) and the optimizer is one fused kernel.  Semantics = DistributedDataParallel: the
-update uses the mean over replicas of the per-replica (weighted-mean) loss gradients.
+update uses the mean over replicas of the per-replica (weighted-mean) loss gradients.  Like DDP, constructing a
+Trainer inside an initialised process group broadcasts rank 0's parameters AND BatchNorm buffers to every replica.
+Unlike DDP (broadcast_buffers=True) the BatchNorm running statistics are NOT re-synchronised on every forward: each
+replica keeps the statistics of its own shard (the reference has no multi-GPU path to mirror); save rank 0's
+state_dict, or call `broadcast_parameters()` before a checkpoint if all ranks must write identical files.
 """
 import torch
 import torch.distributed as dist
@@ -52,6 +56,8 @@ class Trainer:
         self._graph = None
         self._graph_key = None
         self._eager_done = set()
+        if self.world > 1:
+            self.broadcast_parameters(0)   # DDP semantics: every replica starts from rank 0's weights and buffers
 
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank `src`'s weights and BN buffers."""
@@ -124,6 +130,9 @@ class Trainer:
         return loss
 
     def _advance(self):
+        # parameters and BatchNorm buffers were just written through raw pointers (fused SGD kernel, bn_finalize, also
+        # inside a CUDA-graph replay): tell the model so that its eval path re-packs weights and re-folds BatchNorm
+        self.model._native_mutated()
         self.iteration += 1
         if self.lr_step > 0 and self.iteration % self.lr_step == 0:
             self.lr *= self.lr_reduction  # ExponentialLR stepped every lr_step iterations (pipeline.py:157,188-189)

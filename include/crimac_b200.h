@@ -16,6 +16,8 @@
  *                          batch/label_transforms/{refine_label_boundary,convert_label_indexing}.py + data transforms
  *   crimac_stitch          pipeline_train_predict/save_predict.py:41-65 (fill_out_array) + label masks of
  *                          batch/label_transforms/mask_label_{overlap,seabed}.py
+ *   crimac_eval_loss       pipeline.py:222-239 (set_label_ignore_val) + :264 (validation loss) + :269-270 (softmax,
+ *                          SANDEEL channel) of get_predictions_dataloader, on the eval-mode logits
  *   crimac_forward_infer_fp32   the same forward in plain fp32 (validation mode, 1e-4 parity)
  *   crimac_op_* / crimac_dbg_*   single-kernel entry points used by the parity tests only.
  *
@@ -49,7 +51,7 @@ typedef struct crimac_config {
   int depth;         /* encoder blocks, 2..5 (reference default 5)          (unet.py:206)             */
   int start_filts;   /* must be 64                                          (unet.py:207)             */
   int max_batch;     /* largest batch a call may pass                                                 */
-  int height, width; /* patch size, multiples of 2^(depth-1) * 8 ... see crimac_create                */
+  int height, width; /* patch size, multiples of 2^(depth-1) (the reference's own constraint)          */
   int train;         /* 1: allocate saved activations + gradient scratch for forward_train/backward   */
 } crimac_config;
 
@@ -88,6 +90,16 @@ int crimac_train_step(crimac_ctx* ctx, const void* const* state, const float* x_
 /* SGD with momentum on flat fp32 arrays: v = momentum*v + g*gscale ; p -= lr*v   (torch.optim.SGD, dampening 0). */
 int crimac_sgd_step(float* params_dev, float* momentum_dev, const float* grads_dev, size_t n, float lr, float momentum,
                     float gscale, void* stream);
+
+/* Validation step (pipeline.py:249-270): remaps the raw label codes as set_label_ignore_val does (-70, -30, -100, -10 ->
+ * ignore; -50 -> background), evaluates nn.CrossEntropyLoss(weight) on the remapped labels and writes the softmax
+ * probability of class `prob_class` (SANDEEL = 1 in the reference).  logits_dev: fp32 NCHW (nb, n_classes, H, W);
+ * labels_dev: int16 (label_bits = 16, what the dataset emits) or int64 (label_bits = 64), (nb, H, W); prob_out_dev
+ * (optional) fp32 (nb, H, W); labels_out_dev (optional) int64 (nb, H, W) remapped labels; out3_dev {loss, 1/sum_w,
+ * sum_w}; scratch_dev: >= 16 KB.  A label outside [0, n_classes) after the remap makes the loss NaN. */
+int crimac_eval_loss(const float* logits_dev, int nb, int n_classes, int H, int W, const void* labels_dev,
+                     int label_bits, const float* class_w_dev, int prob_class, float* prob_out_dev,
+                     int64_t* labels_out_dev, float* out3_dev, void* scratch_dev, void* stream);
 
 /* Patch gather + sv->dB transform.  sv_dev: fp32 (F, R, P) preloaded pings [frequency][range][ping] whose column 0 is
  * survey ping data_ping0; centres_dev: int32 (n,2) patch centres (y, x) in survey coordinates (batch/samplers/
@@ -146,6 +158,32 @@ int crimac_op_wgrad(int mode, const void* f, int f_pitch, int m_total, const voi
                     int H, int W, float* scratch, float* dw, int splits, int block_n, void* stream);
 int crimac_op_wgrad_halo(const void* dy, int dy_pitch, int cout, const void* x, int x_pitch, int cin, int NB, int H, int W,
                          float* scratch, float* dw, int splits, void* stream);
+/* HBM-bound kernels one at a time (scratch: crimac_op_scratch_bytes() bytes of device memory); see csrc/ops_api.cu */
+size_t crimac_op_scratch_bytes(void);
+int crimac_op_bn_finalize(const float* partials, int rows, int C, double count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                          float eps, float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+int crimac_op_bn_apply(const void* raw, int raw_pitch, int N, int H, int W, int C, const float* scale,
+                       const float* shift, void* act, int act_pitch, void* pool, int pool_pitch, uint16_t* pool_arg,
+                       void* stream);
+int crimac_op_bn_bwd(const void* dact, int dact_pitch, const void* raw, int raw_pitch, int N, int H, int W, int C,
+                     const float* scale, const float* shift, const float* mean, const float* invstd, void* draw,
+                     int draw_pitch, float* dgamma, float* dbeta, float* dbias, const float* gscale, void* scratch,
+                     void* stream);
+int crimac_op_pool_bwd_add(const uint16_t* pool_arg, const void* dpool, int dpool_pitch, const void* dskip,
+                           int dskip_pitch, void* dact, int dact_pitch, int N, int H, int W, int C, void* stream);
+int crimac_op_head_ce(const void* act, int act_pitch, int N, int H, int W, const float* hw, const float* hb, int ncls,
+                      const int64_t* labels, const float* cw, int64_t ignore_index, void* dact, int dact_pitch,
+                      float* dw, float* db, float* out3, void* scratch, void* stream);
+int crimac_op_head_fwd(const void* act, int act_pitch, int N, int H, int W, const float* hw, const float* hb, int ncls,
+                       float* logits, void* stream);
+int crimac_op_head_bwd(const float* dlogits, const float* gscale, const void* act, int act_pitch, int N, int H, int W,
+                       const float* hw, int ncls, void* dact, int dact_pitch, float* dw, float* db, void* scratch,
+                       void* stream);
+int crimac_op_colsum(const void* v, int pitch, int N, int H, int W, int C, float* out, void* scratch, void* stream);
+int crimac_op_pack(int kind, const float* w, int cout, int cin, void* out, void* stream);
+int crimac_op_wgrad_unpack_all(int n, float* const* scratch, float* const* dw, const int64_t* mn, const int* taps,
+                               void* stream);
 int crimac_dbg_umma(const void* image_dev, int image_bytes, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                     int n_mma, int a_step_bytes, int b_step_bytes, float* out_dev, int N, void* stream);
 int crimac_dbg_tma_box(const void* x_dev, int NB, int H, int W, int C, int pitch, int box_h, int sub, int ky, int kx,

@@ -196,8 +196,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     import json
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--batch", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -205,7 +205,10 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "patches/s" and d["higher_is_better"] is True
     for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    # "reference" = the unmodified reference module from baseline/_ref (present wherever build() ran next to
+    # /root/reference), "port" = the oracle restatement when that copy is absent
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["config"]["same_batch_as_b200_arm"] is True
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
@@ -215,11 +218,11 @@ def test_bench_reference_arm_inference_mode():
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--mode", "infer", "--steps", "1",
-                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "1", "--batch", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
     assert d["impl"] == "reference" and "inference" in d["metric"] and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["value"] == d["value"]
 
 
 def test_bench_flop_accounting_matches_the_survey_numbers():

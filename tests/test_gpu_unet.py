@@ -316,13 +316,12 @@ def _structured_batch(B, H, W, seed, dev):
     return torch.clamp(x, -75.0, 0.0).to(dev), y.to(dev)
 
 
-def test_training_converges_and_trained_net_meets_argmax_tolerance(M, pkg):
-    """End to end: the data-parallel trainer (fused train step + SGD, fed from HOST batches through the double-buffered
-    copy pipeline) drives the loss down, and on the resulting confident net the bf16 path agrees with the fp32 oracle on
-    >= 99.9 % of ALL pixels (north_star), probabilities within 2e-2."""
+@pytest.fixture(scope="module")
+def trained(M, pkg):
+    """A net trained for 120 steps on structured batches by the data-parallel trainer (fused train step + SGD, fed from
+    HOST batches through the double-buffered copy pipeline).  Shared by the argmax-agreement and the gradient tests."""
     import importlib
     T = importlib.import_module("crimac_unet_b200.trainer")
-    P = importlib.import_module("crimac_unet_b200.predict")
     torch.manual_seed(0)
     m = M.UNet_Baseline(3, 4).to(dev).train()
     tr = T.Trainer(m, lr=0.005, momentum=0.95, lr_step=0)
@@ -331,6 +330,15 @@ def test_training_converges_and_trained_net_meets_argmax_tolerance(M, pkg):
         x, y = _structured_batch(8, 128, 128, seed=10 + i, dev="cpu")
         host.append((x.pin_memory(), y.pin_memory()))
     losses = [l.item() for l in tr.fit_host(host[i % 8] for i in range(120))]
+    return m, tr, losses
+
+
+def test_training_converges_and_trained_net_meets_argmax_tolerance(M, pkg, trained):
+    """End to end: the trainer drives the loss down, and on the resulting confident net the bf16 path agrees with the
+    fp32 oracle on >= 99.9 % of ALL pixels (north_star), probabilities within 2e-2."""
+    import importlib
+    P = importlib.import_module("crimac_unet_b200.predict")
+    m, _, losses = trained
     first, last = sum(losses[:5]) / 5, sum(losses[-5:]) / 5
     print(f"loss {first:.4f} -> {last:.4f} over {len(losses)} steps")
     assert all(l == l for l in losses)                  # no NaN
@@ -352,6 +360,95 @@ def test_training_converges_and_trained_net_meets_argmax_tolerance(M, pkg):
     # host-batch inference pipeline == direct call
     outs = [o.clone() for o in P.predict_host_batches(m, [x.cpu().pin_memory()] * 3)]
     assert len(outs) == 3 and all(torch.equal(o, got[:, 1:3].half().cpu()) for o in outs)
+    m.train()
+
+
+GRAD_COS, GRAD_REL = 0.99, 5e-2
+
+
+def test_whole_network_gradient_on_trained_net(M, trained):
+    """SURVEY.md section 8d's gradient tolerance on a TRAINED-LIKE net and a structured batch (a random-init net with noise
+    labels amplifies any rounding by cancellation; this one does not): every one of the 82 gradient tensors of one
+    train step against fp32 autograd of the oracle - cosine >= 0.99 and relative L2 <= 5e-2, no escape clause.
+    Conv biases in front of a BatchNorm (exactly zero gradient) are compared absolutely."""
+    m, _, _ = trained
+    m.train()
+    st0 = _state(m)
+    x, y = _structured_batch(8, 128, 128, seed=321, dev=dev)
+    ref_logits, ref_loss, ref_g, _ = O.train_step(st0, x, y)
+    loss = m.train_step_fused(x, y, torch.tensor(O.CLASS_WEIGHTS, device=dev))
+    m.load_state_dict(st0)                              # undo the running-statistics update: the fixture is shared
+    assert abs(loss.item() - ref_loss.item()) < 2e-3 * abs(ref_loss.item())
+    worst_cos, worst_rel, rows = 1.0, 0.0, []
+    for name, p in m.named_parameters():
+        if _pre_bn_bias(name):
+            wname = name[:-4] + "weight"
+            assert p.grad.abs().max().item() <= 1e-4 * ref_g[wname].abs().max().item() + 1e-7, name
+            continue
+        c, r = _cos(p.grad, ref_g[name]), _rel(p.grad, ref_g[name])
+        rows.append((name, c, r))
+        worst_cos, worst_rel = min(worst_cos, c), max(worst_rel, r)
+    rows.sort(key=lambda t: t[1])
+    print(f"trained net, {len(rows)} gradient tensors: worst cosine {worst_cos:.5f}, worst rel-L2 {worst_rel:.4f}; "
+          f"lowest: " + "; ".join(f"{n} cos {c:.4f} rel {r:.4f}" for n, c, r in rows[:4]))
+    for name, c, r in rows:
+        assert c >= GRAD_COS and r <= GRAD_REL, (name, c, r)
+
+
+def test_eval_after_native_training_step_sees_the_new_weights(M, pkg):
+    """The reference's loop validates every log_step batches (pipeline.py:182): eval, train step, eval on ONE model.
+    The native SGD kernel and bn_finalize write parameters / running statistics through raw pointers; the eval path
+    must re-pack its bf16 weights and re-fold BatchNorm after every such step."""
+    import importlib
+    T = importlib.import_module("crimac_unet_b200.trainer")
+    torch.manual_seed(0)
+    m = M.UNet_Baseline(3, 4, depth=3).to(dev)
+    tr = T.Trainer(m, lr=0.05, momentum=0.9)
+    x, y = _structured_batch(4, 64, 64, seed=5, dev=dev)
+    for use_graph_steps in (1, 3):                      # eager first step, then CUDA-graph replays
+        m.eval()
+        with torch.no_grad():
+            before = m.predict_proba(x)
+            assert (before - O.softmax_probs(O.unet_forward(_state(m), x))).abs().max().item() <= PROB_TOL
+        m.train()
+        for _ in range(use_graph_steps):
+            tr.step(x, y)
+        m.eval()
+        with torch.no_grad():
+            after = m.predict_proba(x)
+            ref = O.softmax_probs(O.unet_forward(_state(m), x))
+        assert (after - ref).abs().max().item() <= PROB_TOL
+        assert (after - before).abs().max().item() > 10 * PROB_TOL      # the step really changed the predictions
+
+
+def test_autograd_path_guards_and_grad_reseating(M):
+    torch.manual_seed(0)
+    m = M.UNet_Baseline(3, 4, depth=2).to(dev).train()
+    x = O.synthetic_echogram(2, 4, 32, 32, seed=1, device=dev)
+    y = O.synthetic_labels(2, 32, 32, seed=2, device=dev)
+    cw = torch.tensor(O.CLASS_WEIGHTS, device=dev)
+    # two train-mode forwards before a backward: the first one's saved activations are gone -> loud error, not wrong grads
+    out1 = m(x)
+    out2 = m(x)
+    with pytest.raises(RuntimeError, match="saved activations"):
+        out1.sum().backward()
+    out2.sum().backward()                                # the latest forward is fine
+    # optimizer.zero_grad(set_to_none=True) drops the arena views: train_step_fused re-seats them
+    m.train_step_fused(x, y, cw)
+    g0 = m.conv_final.weight.grad.clone()
+    torch.optim.SGD(m.parameters(), lr=0.1).zero_grad(set_to_none=True)
+    assert m.conv_final.weight.grad is None
+    m2 = m.train_step_fused(x, y, cw)
+    assert m.conv_final.weight.grad is not None and m.conv_final.weight.grad.data_ptr() >= m._grad_arena.data_ptr()
+    assert torch.isfinite(m2) and m.conv_final.weight.grad.abs().sum().item() > 0
+    assert g0.shape == m.conv_final.weight.grad.shape
+    # the parameter-holder blocks have no torch path of their own
+    with pytest.raises(RuntimeError, match="parameter holder"):
+        m.down_convs[0](x)
+    # train-mode BatchNorm over a single value per channel: PyTorch raises, so does the library
+    m1 = M.UNet_Baseline(3, 4, depth=5).to(dev).train()
+    with pytest.raises(RuntimeError, match="more than 1 value per channel"):
+        m1(O.synthetic_echogram(1, 4, 16, 16, seed=3, device=dev))
 
 
 def test_full_size_config2_batch32_parity_and_invariances(M):
