@@ -27,8 +27,6 @@ enum EpiMode : int {
   EPI_STORE = 0,  // y = acc*scale+shift, optional ReLU, optional 2x2 max-pool copy, optional convT scatter
   EPI_STATS = 1,  // raw = acc+shift stored as bf16 + per-tile per-channel sum / sum of squares (train-mode BN)
   EPI_HEAD = 2,   // folded BN + ReLU, then the 1x1 head (+softmax) per pixel; BLOCK_N must be all 64 channels
-  EPI_BNRED = 3,  // backward-data whose output is the gradient of a BatchNorm+ReLU activation: applies the ReLU mask of
-                  // that layer (from its raw output) and emits the BN-backward sums (sum g, sum g*raw) per CTA
 };
 
 struct ConvParams {
@@ -53,11 +51,6 @@ struct ConvParams {
   bf16* pool_out;        // optional (EPI_STORE): 2x2 max-pooled copy, H/2 x W/2
   int pool_pitch;
   float* stats;          // EPI_STATS: [gridDim.x][2][N_total] per-CTA partial sums (sum, sum of squares)
-                         // EPI_BNRED: same shape, (sum g, sum g*raw)
-  const bf16* bnr_raw;   // EPI_BNRED: raw (pre-BN) output of the layer whose activation gradient this kernel produces
-  int bnr_pitch;
-  const float* bnr_scale;  // that layer's BN scale / shift (mask = raw*scale+shift > 0)
-  const float* bnr_shift;
   // EPI_HEAD
   const float* head_w;   // [n_classes][64]
   const float* head_b;   // [n_classes]
@@ -90,7 +83,6 @@ struct WgradHaloParams {
   int k_tiles_total;
   int splits;
   int s_tiles, f_tiles;  // Cs/64, Cf/64
-  int nf;                // 64: nine taps per CTA; 128: eight taps with 128-wide X tiles (centre tap done separately)
   float* dw;             // scratch [9][Cs][Cf] fp32
 };
 

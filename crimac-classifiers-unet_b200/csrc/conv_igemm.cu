@@ -21,7 +21,6 @@
 #include "host_util.h"
 #include "ptx.cuh"
 #include "devfn.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -57,7 +56,7 @@ struct ConvCfg {
                                                        2 * TILE_M * CRIMAC_MAX_CLASSES * 4 /*partial-logit exchange*/)
                                                     : 0;
   static constexpr int AUX_BYTES = 512 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
-                                   2 * MAX_STAT_CH * 4 + HEAD_BYTES + 4 * BLOCK_N * 4 /*EPI_BNRED mask scale/shift x2*/;
+                                   2 * MAX_STAT_CH * 4 + HEAD_BYTES;
   static constexpr int SMEM_BYTES = OPERAND_BYTES + AUX_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
   static_assert(9 % TPS == 0, "taps per weight stage must divide 9");
@@ -92,8 +91,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   float* s_acc = s_red + 8 * BLOCK_N;                     // [2][n_total] CTA-lifetime channel sums
   float* s_head = s_acc + 2 * Cfg::MAX_STAT_CH;           // [ncls][64] + [ncls]           (BLOCK_N == 64 only)
   float* s_hx = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2 acc stages][TILE_M][classes]
-  float* s_bnr = reinterpret_cast<float*>(aux + Cfg::AUX_BYTES - 4 * BLOCK_N * 4);  // [2][mask scale | mask shift]
-  constexpr bool HAS_STATS = (EPI == EPI_STATS || EPI == EPI_BNRED);
+  constexpr bool HAS_STATS = (EPI == EPI_STATS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -402,10 +400,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         sc[i] = p.scale ? p.scale[n0 + i] : 1.0f;
         // ConvTranspose scatter: N index = (ky,kx,co) and the bias is per co
         sh[i] = p.shift ? p.shift[p.convt_cout > 0 ? (n0 + i) % p.convt_cout : n0 + i] : 0.0f;
-        if (EPI == EPI_BNRED) {
-          s_bnr[as * 2 * BLOCK_N + i] = p.bnr_scale[n0 + i];
-          s_bnr[as * 2 * BLOCK_N + BLOCK_N + i] = p.bnr_shift[n0 + i];
-        }
       }
     };
     if (fixed_n) {
@@ -446,21 +440,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       }
 
       auto chunk_body = [&](const int chunk, float (&ra)[32], float (&rb)[32]) {
-        uint4 rw[4] = {};
-        if (EPI == EPI_BNRED && valid) {
-          // raw output of the layer whose activation gradient this tile is: issued before the TMEM load so that the
-          // global-memory latency overlaps it
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              p.bnr_raw + ((static_cast<long>(img) * p.H + y) * p.W + x) * p.bnr_pitch + n0 + chunk * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rw[i] = __ldg(rp + i);
-        }
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + chunk * 32, v);
         ptx::tmem_ld_wait();
         const int ng = n0 + chunk * 32;
         float f[32];
-        if ((EPI == EPI_STORE || EPI == EPI_BNRED) && identity) {
+        if (EPI == EPI_STORE && identity) {
           // backward-data: no scale, no shift - the accumulator goes out as it is
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -490,18 +475,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         if (EPI != EPI_STATS && p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (EPI == EPI_BNRED) {
-          // ReLU backward of the producing layer: keep the gradient where its BatchNorm output was positive
-          const uint32_t* rwu = reinterpret_cast<const uint32_t*>(rw);
-          const float* bs = s_bnr + (fixed_n ? 0 : as) * 2 * BLOCK_N + chunk * 32;
-          const float* bh = bs + BLOCK_N;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 r = unpack_bf16x2(rwu[j]);
-            f[2 * j] = fmaf(r.x, bs[2 * j], bh[2 * j]) > 0.f ? f[2 * j] : 0.f;
-            f[2 * j + 1] = fmaf(r.y, bs[2 * j + 1], bh[2 * j + 1]) > 0.f ? f[2 * j + 1] : 0.f;
-          }
         }
         uint32_t pk[16];
 #pragma unroll
@@ -549,29 +522,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
         }
 
         if (HAS_STATS) {
-          // EPI_STATS: sum, sum of squares of the bf16-rounded values the BN-apply pass will read back.
-          // EPI_BNRED: sum g, sum g*raw of the rounded masked gradient the BN-backward apply pass will read back.
-          const uint32_t* rwu = reinterpret_cast<const uint32_t*>(rw);
+          // sum, sum of squares of the bf16-rounded values the BN-apply pass will read back
           if (RUN_CPW > 0 && run_stats) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
-              const float2 o = (EPI == EPI_BNRED) ? unpack_bf16x2(rwu[j]) : t;
               ra[2 * j] += t.x;
               ra[2 * j + 1] += t.y;
-              rb[2 * j] = fmaf(t.x, o.x, rb[2 * j]);
-              rb[2 * j + 1] = fmaf(t.y, o.y, rb[2 * j + 1]);
+              rb[2 * j] = fmaf(t.x, t.x, rb[2 * j]);
+              rb[2 * j + 1] = fmaf(t.y, t.y, rb[2 * j + 1]);
             }
           } else {
             float s1[32], s2[32];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 t = unpack_bf16x2(valid ? pk[j] : 0u);
-              const float2 o = (EPI == EPI_BNRED) ? unpack_bf16x2(rwu[j]) : t;
               s1[2 * j] = t.x;
               s1[2 * j + 1] = t.y;
-              s2[2 * j] = t.x * o.x;
-              s2[2 * j + 1] = t.y * o.y;
+              s2[2 * j] = t.x * t.x;
+              s2[2 * j + 1] = t.y * t.y;
             }
             xpose_reduce(s1, lane);
             xpose_reduce(s2, lane);
@@ -688,15 +657,14 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = ConvCfg<BLOCK_N, HALO>;
   auto kern = conv_igemm_kernel<BLOCK_N, EPI, HALO, BMN>;
   if (cudaError_t e = ensure_dynamic_smem(kern, Cfg::SMEM_BYTES); e != cudaSuccess) return e;
-  if ((EPI == EPI_STATS || EPI == EPI_BNRED) && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
+  if (EPI == EPI_STATS && p.n_tiles * BLOCK_N > Cfg::MAX_STAT_CH) return cudaErrorInvalidValue;
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (HALO && BLOCK_N != 256) {
     // resident weights when the whole matrix fits beside two or three halo tiles
-    static const bool off = getenv("CRIMAC_NO_RESIDENT") != nullptr;
     const int wbytes = 9 * (p.cin / KBLK) * Cfg::B_BYTES;
     ConvParams q = p;
     q.resident = 0;
-    if (!off && p.n_tiles == 1 && wbytes <= Cfg::RES_MAX_B) q.resident = (wbytes + 3 * HALO_SLOT <= Cfg::OPERAND_BYTES) ? 3 : 2;
+    if (p.n_tiles == 1 && wbytes <= Cfg::RES_MAX_B) q.resident = (wbytes + 3 * HALO_SLOT <= Cfg::OPERAND_BYTES) ? 3 : 2;
     kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(q);
     return cudaGetLastError();
   }
@@ -712,9 +680,8 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num
   // the epilogue writes 32-byte (256-bit) vectors
   if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 31) || p.out_pitch % 16)) return cudaErrorInvalidValue;
   if (p.pool_out && ((reinterpret_cast<uintptr_t>(p.pool_out) & 31) || p.pool_pitch % 16)) return cudaErrorInvalidValue;
-  if (p.b_mn && ((epi != EPI_STORE && epi != EPI_BNRED) || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
+  if (p.b_mn && (epi != EPI_STORE || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
   if (p.b_mn && p.taps == 9 && !p.halo) return cudaErrorInvalidValue;  // 3x3 MN-major weights: halo main loop only
-  if (epi == EPI_BNRED && (!p.b_mn || !p.bnr_raw || !p.bnr_scale || !p.bnr_shift || !p.stats)) return cudaErrorInvalidValue;
 #define CASE(BN, EP)                                                               \
   if (block_n == BN && epi == EP && !p.b_mn)                                       \
     return p.halo ? launch_one<BN, EP, true, false>(p, num_sms, stream) : launch_one<BN, EP, false, false>(p, num_sms, stream);
@@ -727,7 +694,6 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num
     return p.halo ? launch_one<BN, EP, true, true>(p, num_sms, stream)             \
                   : launch_one<BN, EP, false, true>(p, num_sms, stream);
   CASE_MN(64, EPI_STORE) CASE_MN(128, EPI_STORE) CASE_MN(256, EPI_STORE)
-  CASE_MN(64, EPI_BNRED) CASE_MN(128, EPI_BNRED) CASE_MN(256, EPI_BNRED)
 #undef CASE_MN
   return cudaErrorInvalidValue;
 }

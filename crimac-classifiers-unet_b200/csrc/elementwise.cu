@@ -1253,11 +1253,9 @@ static int reduce_grid(const View& v) {
 }
 // BN+ReLU backward: dact (grad wrt post-ReLU activation) -> draw (grad wrt conv output), dgamma/dbeta/dbias.
 // scratch: partials, at least reduce_blocks()*2*C floats; c1c2: 2*C floats.
-// pre_rows > 0: phase 1 has already been done by the kernel that produced dact (conv_igemm EPI_BNRED): `partials` holds
-// pre_rows rows of [sum g | sum g*raw] and dact is already ReLU-masked.
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                          float* partials, float* c1c2, const float* gscale, int pre_rows, cudaStream_t st) {
+                          float* partials, float* c1c2, const float* gscale, cudaStream_t st) {
   const int C = raw.C;
   if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
   const int grid = reduce_grid(raw);
@@ -1265,9 +1263,8 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int grid_r = grid < 148 * 3 ? grid : 148 * 3;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
-  if (pre_rows <= 0)
-    bn_bwd_reduce_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
-  partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, pre_rows > 0 ? pre_rows : grid_r, C, count, dbeta,
+  bn_bwd_reduce_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
+  partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid_r, C, count, dbeta,
                                                                 dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd,
                                                                 dbias);
   bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);

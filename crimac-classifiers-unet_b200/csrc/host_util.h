@@ -117,7 +117,7 @@ cudaError_t launch_head_ce_fused(View act, const float* hw, const float* hb, int
 int reduce_blocks();
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                          float* partials, float* c1c2, const float* gscale, int pre_rows, cudaStream_t st);
+                          float* partials, float* c1c2, const float* gscale, cudaStream_t st);
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st);
 cudaError_t launch_pool_bwd_add(const uint16_t* pool_arg, View dpool, View dskip, View dact, cudaStream_t st);
 // fp32 parameters -> bf16 GEMM operands for every layer of one kind in ONE launch (item0 is filled by the launcher)

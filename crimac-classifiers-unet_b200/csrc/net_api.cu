@@ -18,7 +18,6 @@
 #include "../../include/crimac_b200.h"
 #include <vector>
 #include <new>
-#include <cstdlib>
 
 namespace {
 
@@ -51,7 +50,6 @@ struct Conv3 {
   ConvParams fwd{}, dgrad{};
   WgradHaloParams wg{};   // all-taps halo kernel (wide, shallow layers)
   WgradParams wg_tap{};   // one-tap-per-CTA kernel (deep layers: few pixels, many channels)
-  WgradParams wg_center{};  // centre tap only (taps = 1): completes the eight-tap 128-wide halo variant
   bool wg_use_halo = true;
   float* wg_scratch = nullptr;  // [9][cout][cin] fp32, zero between steps
   int gr_idx = 0;               // which of the two dRaw buffers this layer's BatchNorm backward writes
@@ -358,13 +356,11 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   if (!encode_maps) return 0;
 
   // ---- launch descriptors (tensor maps encoded once)
-  // A/B switch for measurements: FORWARD 3x3 convs through the plain nine-box main loop.  Backward-data always uses the
-  // halo main loop: the MN-major view of the forward-packed 3x3 weights (b_mn) exists only there.
-  const bool use_halo = getenv("CRIMAC_NO_HALO") == nullptr;
+  // every 3x3 conv (forward and backward-data) runs the halo main loop; the plain box-per-tap loop serves ConvTranspose
   auto geom = [&](ConvParams& p, int H, int W, int n_total, int bn) {
     p.H = H;
     p.W = W;
-    p.halo = (p.taps == 9 && (use_halo || p.b_mn)) ? 1 : 0;
+    p.halo = (p.taps == 9) ? 1 : 0;
     p.tiles_x = p.halo ? (W + 7) / 8 : (W + TILE_W - 1) / TILE_W;
     p.tiles_y = p.halo ? (H + 15) / 16 : (H + TILE_H - 1) / TILE_H;
     p.n_tiles = n_total / bn;
@@ -425,20 +421,6 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         // measured on B200 (profiles/): the 64x64-channel halo tiles win up to Cout*Cin = 256*128, beyond that the
         // 128 x 256 one-tap tiles re-read fewer operand bytes per FLOP
         L.wg_use_halo = static_cast<long>(L.cout) * L.cin <= 256L * 128L;
-        // Cin a multiple of 128: the eight-tap variant with 128-wide X tiles (2/3 of the shared-memory traffic per FLOP)
-        // plus the centre tap as a plain GEMM into the same scratch.  Measured on B200: the eight-tap kernel runs at
-        // 1235 TFLOP/s instead of 967, but the centre-tap GEMM re-streams both operands for 1/9 of the FLOPs and is
-        // L2-bound (255 TFLOP/s): 0.357 ms instead of 0.320 ms for the 128->64 layer.  Opt-in (CRIMAC_WG128=1) until the
-        // centre tap shares the operand loads (cluster multicast).
-        static const bool nf128 = getenv("CRIMAC_WG128") != nullptr;
-        w.nf = (L.wg_use_halo && L.cin % 128 == 0 && nf128) ? 128 : 64;
-        if (w.nf == 128) {
-          WgradParams& wc = L.wg_center;
-          wgeom(wc, H, W, L.cout, L.cin, L.bn_wg, 1, 0);
-          wc.dw = L.wg_scratch ? L.wg_scratch + static_cast<size_t>(4) * L.cout * L.cin : nullptr;
-          if ((rc = make_act_map(&wc.a_map, gr, 4))) return rc;
-          if ((rc = make_act_map(&wc.b_map[0], L.in, 4))) return rc;
-        }
         WgradParams& wt = L.wg_tap;
         wgeom(wt, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
         wt.dw = L.wg_scratch;
@@ -502,7 +484,7 @@ void set_batch(WgradParams& p, int nb) {
 void set_batch(WgradHaloParams& p, int nb) {
   p.NB = nb;
   p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
-  const int tiles = p.s_tiles * (p.nf == 128 ? p.Cf / 128 : p.f_tiles);
+  const int tiles = p.s_tiles * p.f_tiles;
   int splits = (2 * device_num_sms()) / tiles;
   if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
   if (splits < 1) splits = 1;
@@ -545,7 +527,7 @@ int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, cudaStream_t st) {
 
 int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, cudaStream_t st) {
   set_batch(w, nb);
-  ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * (w.nf == 128 ? 8 : 9), 0, st);
+  ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * 9, 0, st);
   CRIMAC_CHECK_CUDA(launch_wgrad_halo(w, st));
   return 0;
 }
@@ -599,7 +581,7 @@ extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* w
   }
   if (rc == 0) rc = build(c, workspace_dev, nullptr, true);
   if (rc == 0 && cfg->train) {
-    c->overlap = getenv("CRIMAC_NO_OVERLAP") == nullptr;  // A/B switch for measurements
+    c->overlap = true;  // switched off only while crimac_profile_enable(1) times every kernel on its own
     cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     for (cudaEvent_t* ev : {&c->ev_draw[0], &c->ev_draw[1], &c->ev_wg[0], &c->ev_wg[1], &c->ev_cat, &c->ev_join})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -809,16 +791,9 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   }
   c->wg_dirty = true;  // cleared by the unpack launch at the end
 
-  // BN/ReLU backward of layer idx (dA in GA) -> dRaw in GR; then wgrad (+ dgrad into L.gin)
-  // pre_rows: BN-backward sums already produced (conv_igemm EPI_BNRED) by the kernel that wrote this layer's dA;
-  // target: the layer whose activation gradient THIS layer's backward-data produces (or -1); returns its rows in *out_rows
-  // Measured on B200 (batch 32): fusing saves 0.59 ms of bn_bwd_reduce but costs 0.51 ms in the dgrad kernels, whose
-  // epilogues have no slack on the narrow layers (the extra raw loads + mask + sums make them the bottleneck) - a wash,
-  // so it is opt-in (CRIMAC_BNRED=1) and the stand-alone HBM-bound reduce kernel stays the default.
-  static const bool fuse_bnred = getenv("CRIMAC_BNRED") != nullptr;
+  // BN/ReLU backward of layer idx (dA in GA) -> dRaw in GR; then backward-data (into L.gin) and the weight gradient
   bool wg_recorded[2] = {false, false};
-  auto conv_bwd = [&](int idx, int pre_rows, int target, int* out_rows) -> int {
-    if (out_rows) *out_rows = 0;
+  auto conv_bwd = [&](int idx) -> int {
     Conv3& L = c->conv[idx];
     const int H = level_h(c, L.level), W = level_w(c, L.level);
     View da{c->GA, nb, H, W, L.cout, L.cout};
@@ -831,27 +806,15 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 3);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
                                       grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2,
-                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, pre_rows, st));
+                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, st));
     }
     if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_draw[L.gr_idx], st));
     // backward-data first (critical path, issued first so that it is scheduled first) ...
     if (!L.first && L.gin.ptr != nullptr) {
       ConvParams p = L.dgrad;
       set_batch(p, nb);
-      int epi = EPI_STORE;
-      if (fuse_bnred && target >= 0) {
-        // the output is the activation gradient of `target`: mask it and emit that layer's BN-backward sums here
-        const Conv3& T = c->conv[target];
-        p.bnr_raw = T.raw.ptr;
-        p.bnr_pitch = T.raw.pitch;
-        p.bnr_scale = T.scale;
-        p.bnr_shift = T.shift;
-        p.stats = c->red_partials;
-        epi = EPI_BNRED;
-        if (out_rows) *out_rows = conv_grid(p.total_tiles, sms);
-      }
       ProfScope ps("conv3x3_dgrad", igemm_flops_n(p, L.cin), px * 2.0 * (L.cin + L.cout), st);
-      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_bwd, epi, sms, st));
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, L.bn_bwd, EPI_STORE, sms, st));
     }
     // ... then the weight gradient: tensor-bound and off the critical path -> side stream, where it overlaps the
     // HBM-bound BatchNorm / pooling backward kernels of the following layers (dRaw is double-buffered for this)
@@ -866,7 +829,6 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     } else {
       int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, ws) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, ws);
       if (r) return r;
-      if (L.wg_use_halo && L.wg.nf == 128 && (r = wgrad_run(c, L.wg_center, L.bn_wg, nb, ws))) return r;
     }
     if (c->overlap) {
       CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_wg[L.gr_idx], c->side));
@@ -886,11 +848,9 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
                                       grads[c->g_head_b], 0, st));
   }
   // decoder, last block first
-  int rows = 0;  // BN-backward partial rows the previous kernel left for the layer processed next
   for (int j = D - 2; j >= 0; --j) {
-    int r1 = 0;
-    if ((rc = conv_bwd(c->dec2[j], rows, c->dec1[j], &r1))) return rc;   // dgrad -> dA of dec1[j]
-    if ((rc = conv_bwd(c->dec1[j], r1, -1, nullptr))) return rc;         // dgrad wrote dCat_j
+    if ((rc = conv_bwd(c->dec2[j]))) return rc;   // dgrad -> dA of dec1[j]
+    if ((rc = conv_bwd(c->dec1[j]))) return rc;   // dgrad wrote dCat_j
     ConvT& U = c->up[j];
     // everything that only READS dCat_j and is off the critical path goes to the side stream: the ConvTranspose bias
     // gradient (HBM-bound column sum, own partial buffer) and its weight gradient; the main stream continues with the
@@ -907,21 +867,8 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     {
       ConvParams p = U.dgrad;
       set_batch(p, nb);
-      int epi = EPI_STORE;
-      rows = 0;
-      if (fuse_bnred) {
-        // -> GA = activation gradient of the block below (dec2[j-1], or the deepest encoder conv)
-        const Conv3& T = c->conv[j > 0 ? c->dec2[j - 1] : c->enc2[D - 1]];
-        p.bnr_raw = T.raw.ptr;
-        p.bnr_pitch = T.raw.pitch;
-        p.bnr_scale = T.scale;
-        p.bnr_shift = T.shift;
-        p.stats = c->red_partials;
-        epi = EPI_BNRED;
-        rows = conv_grid(p.total_tiles, sms);
-      }
       ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
-      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, epi, sms, st));
+      CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));
     }
     if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, ss))) return rc;
   }
@@ -935,12 +882,9 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       View dact{c->GA, nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
       ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 2.28, st);
       CRIMAC_CHECK_CUDA(launch_pool_bwd_add(L2.pool_arg, dpool, dskip, dact, st));
-      rows = 0;
     }
-    int r1 = 0;
-    if ((rc = conv_bwd(c->enc2[l], rows, c->enc1[l], &r1))) return rc;  // dgrad -> dA of enc1[l]
-    if ((rc = conv_bwd(c->enc1[l], r1, -1, nullptr))) return rc;        // dgrad wrote GP (grad of the pooled input), none for l == 0
-    rows = 0;
+    if ((rc = conv_bwd(c->enc2[l]))) return rc;  // dgrad -> dA of enc1[l]
+    if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
   }
   if (c->overlap) {
     CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_join, c->side));
@@ -990,4 +934,40 @@ extern "C" int crimac_train_step(crimac_ctx* c, const void* const* state, const 
                                            st));
   }
   return backward_impl(c, state, x, nullptr, l3 + 1, nb, grads, st, /*head_done=*/true);
+}
+
+// Test hook: copies one tensor the last crimac_forward_train / crimac_train_step saved for backward out of the
+// workspace into a dense NHWC bf16 buffer (nb, H, W, C).  which: 0 = raw conv output (pre-BatchNorm), 1 = activation
+// (post BN + ReLU), 2 = 2x2 max-pooled activation (encoder second convs), 3 = ConvTranspose2d output (index = decoder
+// block).  index (which < 3): encoder block l -> 2l (first conv), 2l+1 (second); decoder block j -> 2*depth + 2j, +1.
+// dims_out (host, optional): {H, W, C}.  The gradient parity test uses it to evaluate torch autograd AT the native
+// forward state (tests/test_gpu_unet.py::test_backward_at_the_native_forward_state).
+extern "C" int crimac_dbg_saved(crimac_ctx* c, int index, int which, int nb, void* dst_dev, int* dims_out, void* stream) {
+  CRIMAC_REQUIRE(c != nullptr && c->cfg.train, "train context required");
+  CRIMAC_REQUIRE(nb >= 1 && nb <= c->cfg.max_batch, "nb");
+  View v{};
+  if (which == 3) {
+    CRIMAC_REQUIRE(index >= 0 && index < static_cast<int>(c->up.size()), "decoder block index");
+    v = c->up[index].out;
+  } else {
+    CRIMAC_REQUIRE(which >= 0 && which <= 2, "which");
+    const int D = c->D;
+    int idx = -1;
+    if (index >= 0 && index < 2 * D) idx = (index & 1) ? c->enc2[index >> 1] : c->enc1[index >> 1];
+    else if (index >= 2 * D && index < 2 * D + 2 * (D - 1)) idx = ((index - 2 * D) & 1) ? c->dec2[(index - 2 * D) >> 1] : c->dec1[(index - 2 * D) >> 1];
+    CRIMAC_REQUIRE(idx >= 0, "layer index");
+    const Conv3& L = c->conv[idx];
+    v = which == 0 ? L.raw : (which == 1 ? L.act : L.pool);
+    CRIMAC_REQUIRE(v.ptr != nullptr, "this layer does not keep that tensor");
+  }
+  if (dims_out) {
+    dims_out[0] = v.H;
+    dims_out[1] = v.W;
+    dims_out[2] = v.C;
+  }
+  if (dst_dev != nullptr)
+    CRIMAC_CHECK_CUDA(cudaMemcpy2DAsync(dst_dev, static_cast<size_t>(v.C) * 2, v.ptr, static_cast<size_t>(v.pitch) * 2,
+                                        static_cast<size_t>(v.C) * 2, static_cast<size_t>(nb) * v.H * v.W,
+                                        cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
 }

@@ -2,6 +2,7 @@
 // entry points in net_api.cu drive the same launchers with maps cached in the context; these exist so the parity
 // tests can pin every kernel against the oracle in isolation.
 #include "host_util.h"
+#include "../../include/crimac_b200.h"
 
 static int pick_block_n(int n_total, int requested) {
   if (requested == 64 || requested == 128 || requested == 256) return (n_total % requested == 0) ? requested : 0;
@@ -11,7 +12,7 @@ static int pick_block_n(int n_total, int requested) {
   return 0;
 }
 
-// Generic implicit GEMM.  mode: 0 = 3x3 conv (taps 9, halo main loop; 3 = same through the 9-box main loop), 1 = 1x1 / ConvTranspose forward (taps 1; convt_cout > 0 turns on
+// Generic implicit GEMM.  mode: 0 = 3x3 conv (taps 9, halo main loop), 1 = 1x1 / ConvTranspose forward (taps 1; convt_cout > 0 turns on
 // the 2x upsampling scatter), 2 = ConvTranspose backward-data (taps 4: x is the (2H x 2W) gradient, sub-sampled).
 // x: NHWC bf16 view (NB,H,W,cin) with pixel pitch x_pitch (for mode 2: dims of x are 2H x 2W).
 // w: packed bf16 [n_total][taps*cin].   out: NHWC bf16 with pitch out_pitch.
@@ -21,14 +22,13 @@ extern "C" int crimac_op_igemm(int mode, const void* x, int NB, int H, int W, in
                                int out_pitch, int convt_cout, void* pool_out, int pool_pitch, float* stats,
                                const float* head_w, const float* head_b, float* head_out, int n_classes,
                                int head_softmax, int block_n, void* stream) {
-  CRIMAC_REQUIRE(mode >= 0 && mode <= 5, "mode");
+  CRIMAC_REQUIRE(mode >= 0 && mode <= 5 && mode != 3, "mode");
   // modes 4 / 5: backward-data of a 3x3 conv / ConvTranspose reading the FORWARD-packed weights as an MN-major operand
   // (w = [Cout][9*Cin] resp. [(kk,co)][Cin] of the forward layer; n_total = the forward layer's Cin)
   const bool b_mn = (mode == 4 || mode == 5);
   if (mode == 4) mode = 0;
   if (mode == 5) mode = 2;
-  const bool halo = (mode == 0);  // mode 3 = 3x3 conv through the plain 9-box main loop (kept for A/B measurements)
-  if (mode == 3) mode = 0;
+  const bool halo = (mode == 0);
   CRIMAC_REQUIRE(cin % 64 == 0, "cin must be a multiple of 64");
   const int bn = pick_block_n(n_total, head_w ? 64 : block_n);
   CRIMAC_REQUIRE(bn != 0, "n_total must be a multiple of 64 (and of block_n when given)");
@@ -238,7 +238,7 @@ extern "C" int crimac_op_bn_bwd(const void* dact, int dact_pitch, const void* ra
   float* c1c2 = partials + static_cast<size_t>(reduce_blocks()) * 2 * C;
   CRIMAC_CHECK_CUDA(launch_bn_bwd(mk_view(dact, N, H, W, C, dact_pitch), mk_view(raw, N, H, W, C, raw_pitch), scale, shift,
                                   mean, invstd, mk_view(draw, N, H, W, C, draw_pitch), dgamma, dbeta, dbias, 0, partials,
-                                  c1c2, gscale, 0, static_cast<cudaStream_t>(stream)));
+                                  c1c2, gscale, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

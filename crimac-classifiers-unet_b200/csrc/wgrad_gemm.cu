@@ -448,12 +448,9 @@ cudaError_t launch_wh(const WgradHaloParams& p, cudaStream_t stream) {
 }
 }  // namespace
 
-// p.nf = 64: all nine taps.  p.nf = 128 (Cf % 128 == 0): eight taps; the caller adds the centre tap with a taps = 1
-// wgrad_gemm launch into scratch + 4*Cs*Cf.
-cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) {
-  if (p.nf == 128) return (p.Cf % 128 == 0) ? launch_wh<128>(p, stream) : cudaErrorInvalidValue;
-  return launch_wh<64>(p, stream);
-}
+// All nine taps per CTA, 64 x 64 channel tiles.  (A 128-wide eight-tap variant - NF = 128, the template parameter is kept -
+// ran the MMAs at 1235 instead of 967 TFLOP/s but needed a separate, L2-bound centre-tap GEMM: net loss, removed.)
+cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) { return launch_wh<64>(p, stream); }
 
 cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,
                                 cudaStream_t stream) {

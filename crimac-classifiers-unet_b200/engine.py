@@ -146,6 +146,37 @@ def sgd_step(params_flat, momentum_flat, grads_flat, lr, momentum, gscale=1.0):
     )
 
 
+def eval_loss(logits, labels, class_w, prob_class=1, want_labels=False):
+    """Validation step on eval-mode logits (reference pipeline.py:222-239 set_label_ignore_val, :264 criterion, :269-270
+    softmax + SANDEEL channel) in one kernel.  labels: int16 or int64 (N,H,W) raw label codes.  Returns
+    (loss 0-dim device tensor, probability of `prob_class` fp32 (N,H,W), remapped int64 labels or None)."""
+    L = _lib.load()
+    if labels.dtype not in (torch.int16, torch.int64):
+        raise ValueError("labels must be int16 or int64")
+    n, ncls, h, w = logits.shape
+    logits, labels = logits.contiguous().float(), labels.contiguous()
+    prob = torch.empty((n, h, w), dtype=torch.float32, device=logits.device)
+    lab_out = torch.empty((n, h, w), dtype=torch.int64, device=logits.device) if want_labels else None
+    out3 = torch.empty(4, dtype=torch.float32, device=logits.device)
+    scratch = torch.empty(16384, dtype=torch.uint8, device=logits.device)
+    _lib.check(
+        L.crimac_eval_loss(_lib.ptr(logits), n, ncls, h, w, _lib.ptr(labels), 16 if labels.dtype == torch.int16 else 64,
+                           _lib.ptr(class_w.contiguous().float()), int(prob_class), _lib.ptr(prob), _lib.ptr(lab_out),
+                           _lib.ptr(out3), _lib.ptr(scratch), _lib.stream_ptr()),
+        "crimac_eval_loss",
+    )
+    return out3[0], prob, lab_out
+
+
+def saved_tensor(ctx, index, which, nb):
+    """Test hook (crimac_dbg_saved): a dense NHWC bf16 copy of a tensor the last train-mode forward kept for backward."""
+    dims = (ctypes.c_int * 3)()
+    _lib.check(ctx.L.crimac_dbg_saved(ctx.handle, index, which, nb, None, dims, _lib.stream_ptr()), "crimac_dbg_saved")
+    out = torch.empty((nb, dims[0], dims[1], dims[2]), dtype=torch.bfloat16, device=ctx.device)
+    _lib.check(ctx.L.crimac_dbg_saved(ctx.handle, index, which, nb, _lib.ptr(out), dims, _lib.stream_ptr()), "crimac_dbg_saved")
+    return out
+
+
 def preprocess(sv, data_ping0, centres, patch_hw, out=None, nan_mask=None):
     """sv: fp32 (F,R,P) device tensor; centres: int32 (n,2) device tensor (y,x) survey coords."""
     L = _lib.load()

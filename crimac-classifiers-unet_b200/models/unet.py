@@ -359,6 +359,19 @@ class UNet_Baseline(_NativePlumbing, UNet):
         return self._infer(x, softmax=True)
 
     @torch.no_grad()
+    def validate_batch(self, x, labels, class_weight, prob_class=1):
+        """The validation step of the reference's training loop (pipeline.py:249-270, get_predictions_dataloader) for one
+        batch, all on device: eval forward, label codes remapped as set_label_ignore_val does (-70, -30, -100, -10 ->
+        ignore; -50 -> background), the class-weighted CE on the remapped labels, softmax probability of `prob_class`
+        (SANDEEL = 1).  labels: int16 (what the dataset emits) or int64, (N,H,W).
+        Returns (loss: 0-dim device tensor, prob: fp32 (N,H,W), logits: fp32 (N,n_classes,H,W))."""
+        if self.training:
+            raise RuntimeError("validate_batch() is an eval-mode call; use model.eval() first")
+        logits = self._infer(x, softmax=False)
+        loss, prob, _ = _runtime().eval_loss(logits, labels.to(x.device), class_weight.to(x.device), prob_class)
+        return loss, prob, logits
+
+    @torch.no_grad()
     def forward_fp32(self, x, softmax=False):
         """fp32 VALIDATION mode: the eval forward through an independent plain-fp32 CUDA implementation (no bf16, no
         tensor cores) - logits, or probabilities with softmax=True.  For 1e-4 parity checks, ~50x slower."""

@@ -48,10 +48,9 @@ class Trainer:
         # The ~190 kernel launches of a step (both streams of the backward, the all-reduce, the SGD kernel) are captured
         # once in a CUDA graph and replayed: measured 3-4 % shorter steps on B200 (launch gaps).  The first step of a
         # shape runs eagerly (it creates the native context and the gradient arena), the second is captured; a change
-        # of learning rate or batch shape re-captures.  CRIMAC_NO_GRAPH=1 or use_cuda_graph=False keeps eager launches.
-        import os
+        # of learning rate or batch shape re-captures.  use_cuda_graph=False keeps eager launches.
         if use_cuda_graph is None:
-            use_cuda_graph = os.environ.get("CRIMAC_NO_GRAPH") is None and dev.type == "cuda"
+            use_cuda_graph = dev.type == "cuda"
         self.use_cuda_graph = bool(use_cuda_graph)
         self._graph = None
         self._graph_key = None

@@ -184,6 +184,9 @@ int crimac_op_colsum(const void* v, int pitch, int N, int H, int W, int C, float
 int crimac_op_pack(int kind, const float* w, int cout, int cin, void* out, void* stream);
 int crimac_op_wgrad_unpack_all(int n, float* const* scratch, float* const* dw, const int64_t* mn, const int* taps,
                                void* stream);
+/* Test hook: copy a tensor saved by the last train-mode forward (raw conv output / activation / pooled / ConvTranspose
+ * output) into a dense NHWC bf16 buffer; see csrc/net_api.cu. */
+int crimac_dbg_saved(crimac_ctx* ctx, int index, int which, int nb, void* dst_dev, int* dims_out, void* stream);
 int crimac_dbg_umma(const void* image_dev, int image_bytes, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                     int n_mma, int a_step_bytes, int b_step_bytes, float* out_dev, int N, void* stream);
 int crimac_dbg_tma_box(const void* x_dev, int NB, int H, int W, int C, int pitch, int box_h, int sub, int ky, int kx,

@@ -254,7 +254,7 @@ def test_weight_gradient_unpack_all_layers_one_launch(env):
     torch.manual_seed(11)
     shapes = [(9, 64 * 64), (4, 128 * 64), (9, 100), (9, 1024 + 300), (1, 5000)]       # ragged: not multiples of 256 / 1024
     scr = [torch.randn(t, mn, device=dev) for t, mn in shapes]
-    want = [s.t().contiguous() for s in scr]
+    want = [s.t().clone(memory_format=torch.contiguous_format) for s in scr]   # a COPY: the kernel zeroes scr
     dws = [torch.full((mn, t), 3.0, device=dev) for t, mn in shapes]
     n = len(shapes)
     a_s = (ctypes.c_void_p * n)(*[s.data_ptr() for s in scr])
@@ -302,7 +302,9 @@ def test_sgd_momentum_kernel_and_lr_schedule_match_torch_optim(env, pkg):
         torch.cuda.synchronize()
         assert torch.allclose(tr.flat_params, p_ref.detach(), rtol=1e-5, atol=1e-6), i
     assert abs(tr.lr - 0.005 * 0.5 ** 4) < 1e-15
-    assert torch.allclose(tr.flat_momentum, opt.state[p_ref]["momentum_buffer"], rtol=1e-5, atol=1e-6)
+    vb = opt.state[p_ref]["momentum_buffer"]
+    # summation-order level: the running sums reach ~30, so the absolute rounding error is ~30 * 2^-23 per step
+    assert (tr.flat_momentum - vb).abs().max().item() <= 1e-5 * vb.abs().max().item()
     # the data-parallel mean is folded into the kernel: gscale = 1/world
     p1, v1 = p0.clone(), torch.zeros(n, device=dev)
     g = torch.randn(n, device=dev)
