@@ -52,9 +52,7 @@ struct ConvCfg {
   static constexpr int OPERAND_BYTES = HALO ? (RING_BYTES > RES_BYTES ? RING_BYTES : RES_BYTES) : (STAGES * STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int MAX_STAT_CH = 4 * BLOCK_N;  // per-CTA running channel sums (EPI_STATS) over all n-tiles
-  static constexpr int HEAD_BYTES = (BLOCK_N == 64) ? ((CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 +
-                                                       2 * TILE_M * CRIMAC_MAX_CLASSES * 4 /*partial-logit exchange*/)
-                                                    : 0;
+  static constexpr int HEAD_BYTES = (BLOCK_N == 64) ? (CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES) * 4 : 0;
   static constexpr int AUX_BYTES = 512 /*barriers*/ + 4 * BLOCK_N * 4 /*scale/shift x2*/ + 8 * BLOCK_N * 4 /*stats*/ +
                                    2 * MAX_STAT_CH * 4 + HEAD_BYTES;
   static constexpr int SMEM_BYTES = OPERAND_BYTES + AUX_BYTES + 1024;
@@ -90,7 +88,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   float* s_red = s_affine + 4 * BLOCK_N;                  // [4 warps][2][BLOCK_N]
   float* s_acc = s_red + 8 * BLOCK_N;                     // [2][n_total] CTA-lifetime channel sums
   float* s_head = s_acc + 2 * Cfg::MAX_STAT_CH;           // [ncls][64] + [ncls]           (BLOCK_N == 64 only)
-  float* s_hx = s_head + CRIMAC_MAX_CLASSES * 64 + CRIMAC_MAX_CLASSES;  // [2 acc stages][TILE_M][classes]
   constexpr bool HAS_STATS = (EPI == EPI_STATS);
 
   const int warp = threadIdx.x >> 5;
@@ -111,7 +108,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], EPI_THREADS);
+      // EPI_HEAD: a tile is read out by ONE of the two warps per lane quarter (all 64 columns), see the epilogue
+      ptx::mbar_init(&tmem_empty[s], EPI == EPI_HEAD ? EPI_THREADS / EPI_COLGROUPS : EPI_THREADS);
     }
     ptx::fence_barrier_init();
   }
@@ -419,6 +417,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       const int n0 = n_tile * BLOCK_N;
       const int y = ty * TH + py, x = tx * TW + px;
       const bool valid = (y < p.H) && (x < p.W);
+      // fused head: the per-pixel dot product over all 64 channels must end up in ONE thread.  Instead of splitting the
+      // columns between the two warps of a lane quarter and exchanging partial sums through shared memory (one block
+      // barrier per tile: measured 70 us on the last layer), warp group h takes every second tile - accumulator stage
+      // `as` == h - and reads both 32-column chunks itself.
+      if (EPI == EPI_HEAD && as != h) continue;
 
       if (!fixed_n) {
         load_affine(as, n0);
@@ -435,8 +438,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       float logit[CRIMAC_MAX_CLASSES];
       if (EPI == EPI_HEAD) {
 #pragma unroll
-        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-          logit[k] = (h == 0 && k < p.n_classes) ? s_head[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
+        for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] = (k < p.n_classes) ? s_head[CRIMAC_MAX_CLASSES * 64 + k] : 0.f;
       }
 
       auto chunk_body = [&](const int chunk, float (&ra)[32], float (&rb)[32]) {
@@ -549,7 +551,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
           }
         }
       };
-      if constexpr (RUN_CPW > 0) {
+      if constexpr (EPI == EPI_HEAD) {
+#pragma unroll
+        for (int chunk = 0; chunk < NCHUNK; ++chunk) chunk_body(chunk, r1[0], r2[0]);
+      } else if constexpr (RUN_CPW > 0) {
 #pragma unroll
         for (int ci = 0; ci < RUN_CPW; ++ci) chunk_body(h + ci * EPI_COLGROUPS, r1[ci], r2[ci]);
       } else {
@@ -578,18 +583,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
       }
 
       if (EPI == EPI_HEAD) {
-        // the two column groups each hold the head's dot product over their 32 channels: group 1 hands its part over
-        float* xch = s_hx + (as * TILE_M + r) * CRIMAC_MAX_CLASSES;
-        if (h == 1) {
-#pragma unroll
-          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-            if (k < p.n_classes) xch[k] = logit[k];
-        }
-        epi_bar();
-        if (h == 0 && valid) {
-#pragma unroll
-          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-            if (k < p.n_classes) logit[k] += xch[k];
+        if (valid) {
           if (p.head_softmax) {
             float mx = logit[0];
 #pragma unroll

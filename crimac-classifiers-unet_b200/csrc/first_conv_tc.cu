@@ -477,7 +477,8 @@ cudaError_t launch_first_conv_tc(const float* x, bf16* xs, const float* w, const
     if (cudaError_t e = ensure_dynamic_smem(first_conv_tc_kernel<C>, fc_fwd_smem<C>()); e != cudaSuccess) return e; \
     long blocks = (NB * npix + 255) / 256;                                                                         \
     if (blocks > 148 * 8) blocks = 148 * 8;                                                                        \
-    split_input_kernel<C><<<static_cast<int>(blocks), 256, 0, st>>>(x, npix, NB, xs);                              \
+    if (x != nullptr) /* else: xs was written by crimac_preprocess_staged */                                        \
+      split_input_kernel<C><<<static_cast<int>(blocks), 256, 0, st>>>(x, npix, NB, xs);                            \
     CUtensorMap map;                                                                                               \
     if (x_map_for(&map, xs, NB, H, W, FcCfg<C>::P) != 0) return cudaErrorInvalidValue;                             \
     first_conv_tc_kernel<C><<<grid, FC_THREADS, fc_fwd_smem<C>(), st>>>(map, w, scale, shift, relu, NB, H, W, out,  \

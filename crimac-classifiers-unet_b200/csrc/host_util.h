@@ -114,6 +114,9 @@ cudaError_t launch_head_bwd(const float* dlogits, const float* gscale, View act,
 cudaError_t launch_head_ce_fused(View act, const float* hw, const float* hb, int ncls, const long long* labels,
                                  const float* cw, long long ignore_index, View dact, float* partials,
                                  double* loss_partials, float* dw, float* db, float* out3, cudaStream_t st);
+// pipeline_kernels.cu: patch gather + dB transform written as the first conv's bf16 hi/lo operand (0 = ok, 2 = CUDA error)
+int launch_preprocess_split(const float* sv, int F, int R, int P, int data_ping0, const int32_t* centres, int n, int ph,
+                            int pw, bf16* xs, uint8_t* nan_mask, cudaStream_t st);
 int reduce_blocks();
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,

@@ -100,6 +100,7 @@ struct crimac_ctx {
   float* loss3 = nullptr;
   ConvParams head_fused{};   // last conv with the 1x1 head in its epilogue (eval)
   int prepared_mode = -1;
+  int staged_nb = 0;         // patches crimac_preprocess_staged left in xs (consumed by the next forward with x == NULL)
 };
 
 namespace {
@@ -742,8 +743,16 @@ extern "C" int crimac_forward_infer(crimac_ctx* c, const void* const* state, con
                                     int softmax, void* stream) {
   int rc = check_call(c, state, nb);
   if (rc) return rc;
-  CRIMAC_REQUIRE(x != nullptr && out != nullptr, "NULL tensor");
+  CRIMAC_REQUIRE(out != nullptr, "NULL tensor");
   CRIMAC_REQUIRE(c->prepared_mode == 0, "call crimac_prepare(ctx, state, train=0) first");
+  if (x == nullptr) {
+    // the first conv's operand was staged by crimac_preprocess_staged: tensor-core first conv only (<= 8 frequencies)
+    CRIMAC_REQUIRE(c->staged_nb == nb, "x is NULL but crimac_preprocess_staged has not staged exactly nb patches");
+    CRIMAC_REQUIRE(first_conv_grid(nb, c->cfg.in_channels, c->cfg.height, c->cfg.width) ==
+                       first_conv_tc_grid(nb, c->cfg.height, c->cfg.width),
+                   "staged input needs the tensor-core first conv (CRIMAC_FC_CUDACORE is set)");
+  }
+  c->staged_nb = 0;
   return forward_impl(c, state, x, nb, out, softmax, false, static_cast<cudaStream_t>(stream));
 }
 
@@ -969,5 +978,29 @@ extern "C" int crimac_dbg_saved(crimac_ctx* c, int index, int which, int nb, voi
     CRIMAC_CHECK_CUDA(cudaMemcpy2DAsync(dst_dev, static_cast<size_t>(v.C) * 2, v.ptr, static_cast<size_t>(v.pitch) * 2,
                                         static_cast<size_t>(v.C) * 2, static_cast<size_t>(nb) * v.H * v.W,
                                         cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// Preprocessing that FEEDS THE FIRST CONV DIRECTLY (north_star): the patch gather + NaN fill + dB transform
+// of crimac_preprocess, written as the bf16 hi/lo NHWC operand the tensor-core first conv reads by TMA - into the
+// context's own staging buffer.  The next crimac_forward_infer(ctx, state, x_dev = NULL, nb = n, ...) consumes it; the
+// fp32 NCHW patch tensor of the reference (batch/dataset.py:192-205 -> pipeline.py:208) is never written.  Patch size =
+// the context's (height, width).
+extern "C" int crimac_preprocess_staged(crimac_ctx* c, const float* sv, int F, int R, int P, int data_ping0,
+                                        const int32_t* centres, int n, uint8_t* nan_mask, void* stream) {
+  CRIMAC_REQUIRE(c != nullptr && sv != nullptr && centres != nullptr, "NULL argument");
+  CRIMAC_REQUIRE(F == c->cfg.in_channels, "F must equal the context's in_channels");
+  CRIMAC_REQUIRE(n >= 1 && n <= c->cfg.max_batch, "n must be in 1..max_batch");
+  CRIMAC_REQUIRE(R >= 1 && P >= 1, "empty input");
+  CRIMAC_CHECK_CUDA(cudaSetDevice(c->device));
+  ProfScope ps("preprocess_staged", 0, static_cast<double>(n) * c->cfg.height * c->cfg.width * (4.0 * F + 16.0 * (F <= 4 ? 1 : 2)),
+               static_cast<cudaStream_t>(stream));
+  int rc = launch_preprocess_split(sv, F, R, P, data_ping0, centres, n, c->cfg.height, c->cfg.width, c->xs, nan_mask,
+                                   static_cast<cudaStream_t>(stream));
+  if (rc) {
+    crimac_set_error("preprocess_split_kernel launch failed");
+    return rc;
+  }
+  c->staged_nb = n;
   return 0;
 }

@@ -6,6 +6,11 @@
 
 namespace {
 
+__device__ __forceinline__ uint32_t pack_bf16x2f(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // batch/dataset.py:192-205 (get_preload_data_labels) + utils/np.py:40-46,362-375 (getGrid, new_get_crop_3d) +
 // remove_nan_inf.py:23-34 + db_with_limits.py:20-24,36-38.  One thread = 4 consecutive pings of one patch row.
 __global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict__ sv, int F, int R, int P,
@@ -47,6 +52,56 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const float* __restrict
     if (f == 0 && nan_mask != nullptr)
       *reinterpret_cast<uchar4*>(nan_mask + (static_cast<long>(b) * ph + py) * pw + 4 * x4) =
           make_uchar4(bad[0], bad[1], bad[2], bad[3]);
+  }
+}
+
+// The same gather + transform, but the result goes straight into the operand format of the first conv
+// (first_conv_tc.cu): NHWC bf16 pairs hi = bf16(v), lo = bf16(v - hi) in 16-byte chunks per pixel - one plane
+// [pixel][hi c0..3 | lo c0..3] for F <= 4, two planes [pixel][hi c0..7], [pixel][lo c0..7] for F <= 8.  The fp32 NCHW
+// patch tensor (batch/dataset.py:192-205 -> pipeline.py:208) is never materialised.  One thread = one pixel, all
+// frequencies: the reads of one frequency plane are coalesced along pings, the write is one 16-byte (two for P = 8) store.
+template <int PCH>
+__global__ void __launch_bounds__(256) preprocess_split_kernel(const float* __restrict__ sv, int F, int R, int P,
+                                                               int data_ping0, const int* __restrict__ centres, int n,
+                                                               int ph, int pw, bf16* __restrict__ xs,
+                                                               uint8_t* __restrict__ nan_mask) {
+  const long total = static_cast<long>(n) * ph * pw;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(i % pw);
+    const int py = static_cast<int>((i / pw) % ph);
+    const int b = static_cast<int>(i / (static_cast<long>(pw) * ph));
+    const int y = centres[2 * b] - ph / 2 + 1 + py;
+    const int x = centres[2 * b + 1] - pw / 2 + 1 + px - data_ping0;
+    const bool inside = y >= 0 && y < R && x >= 0 && x < P;
+    float hi[PCH], lo[PCH];
+    bool bad0 = false;
+#pragma unroll
+    for (int f = 0; f < PCH; ++f) {
+      float d = 0.f;
+      if (f < F) {
+        float s = 0.f;  // out-of-data -> 0 BEFORE the dB transform (boundary_val_data, dataset.py:194)
+        if (inside) {
+          s = __ldg(&sv[(static_cast<long>(f) * R + y) * P + x]);
+          const bool nf = !isfinite(s);
+          if (nf) s = 0.f;
+          if (f == 0) bad0 = nf;
+        }
+        d = fminf(fmaxf(10.f * log10f(s + 1e-10f), -75.f), 0.f);
+      }
+      const float h = __bfloat162float(__float2bfloat16(d));
+      hi[f] = h;
+      lo[f] = d - h;
+    }
+    uint32_t w[PCH];
+#pragma unroll
+    for (int c = 0; c < PCH / 2; ++c) {
+      w[c] = pack_bf16x2f(hi[2 * c], hi[2 * c + 1]);
+      w[PCH / 2 + c] = pack_bf16x2f(lo[2 * c], lo[2 * c + 1]);
+    }
+    *reinterpret_cast<uint4*>(xs + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (PCH == 8) *reinterpret_cast<uint4*>(xs + (total + i) * 8) = make_uint4(w[PCH - 4], w[PCH - 3], w[PCH - 2], w[PCH - 1]);
+    if (nan_mask != nullptr) nan_mask[i] = bad0 ? 1 : 0;
   }
 }
 
@@ -110,6 +165,20 @@ extern "C" int crimac_preprocess(const float* sv, int F, int R, int P, int data_
       sv, F, R, P, data_ping0, centres, n, ph, pw, out, nan_mask);
   CRIMAC_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// crimac_preprocess with the first conv's operand as the destination (see preprocess_split_kernel); xs: the staging
+// buffer of a context (crimac_preprocess_staged in net_api.cu passes it) holding n patches of (ph, pw).
+int launch_preprocess_split(const float* sv, int F, int R, int P, int data_ping0, const int32_t* centres, int n, int ph,
+                            int pw, bf16* xs, uint8_t* nan_mask, cudaStream_t st) {
+  const long total = static_cast<long>(n) * ph * pw;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (F <= 4)
+    preprocess_split_kernel<4><<<static_cast<int>(blocks), 256, 0, st>>>(sv, F, R, P, data_ping0, centres, n, ph, pw, xs, nan_mask);
+  else
+    preprocess_split_kernel<8><<<static_cast<int>(blocks), 256, 0, st>>>(sv, F, R, P, data_ping0, centres, n, ph, pw, xs, nan_mask);
+  return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 extern "C" int crimac_stitch(const float* probs, int n, int n_classes, int ph, int pw, const int32_t* centres,

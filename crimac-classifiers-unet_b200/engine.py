@@ -87,6 +87,22 @@ class Context:
             "crimac_forward_infer",
         )
 
+    def preprocess_staged(self, sv, data_ping0, centres, nan_mask):
+        """Patch gather + dB transform straight into the first conv's operand inside this context (crimac_preprocess_staged);
+        consumed by the next forward_infer(state, None, ...)."""
+        F, R, P = sv.shape
+        _lib.check(
+            self.L.crimac_preprocess_staged(self.handle, _lib.ptr(sv), F, R, P, int(data_ping0), _lib.ptr(centres),
+                                            centres.shape[0], _lib.ptr(nan_mask), _lib.stream_ptr()),
+            "crimac_preprocess_staged",
+        )
+
+    def forward_infer_staged(self, state, nb, out, softmax):
+        _lib.check(
+            self.L.crimac_forward_infer(self.handle, state, None, nb, _lib.ptr(out), int(softmax), _lib.stream_ptr()),
+            "crimac_forward_infer",
+        )
+
     def forward_train(self, state, x, logits):
         _lib.check(
             self.L.crimac_forward_train(self.handle, state, _lib.ptr(x), x.shape[0], _lib.ptr(logits), _lib.stream_ptr()),

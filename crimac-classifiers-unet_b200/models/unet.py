@@ -287,13 +287,16 @@ class _NativePlumbing:
         return list(self.parameters())
 
     def _engine_for(self, x, train):
-        rt = _runtime()
         nb, _, h, w = x.shape
-        key = (h, w, bool(train), x.device)
+        return self._engine_for_shape(nb, h, w, x.device, train)
+
+    def _engine_for_shape(self, nb, h, w, device, train):
+        rt = _runtime()
+        key = (h, w, bool(train), device)
         engines = _ENGINES.setdefault(self, {})
         eng = engines.get(key)
         if eng is None or eng.cfg.max_batch < nb:
-            eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, x.device)
+            eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, device)
             engines[key] = eng
         return eng
 
@@ -319,6 +322,35 @@ class _NativePlumbing:
         out = torch.empty((x.shape[0], self.n_classes, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device)
         eng.forward_infer(state, x, out, softmax)
         return out
+
+    @torch.no_grad()
+    def predict_proba_patches(self, sv, data_ping0, centres, patch_hw, softmax=True):
+        """Sliding-window inference without the patch tensor: gathers the patches around `centres` (int32 (n,2) device,
+        (y, x) survey coordinates) from the preloaded pings `sv` (fp32 device (F,R,P), column 0 = survey ping
+        data_ping0), applies remove_nan_inf + db_with_limits and feeds the first conv DIRECTLY (the kernel writes the
+        tensor-core operand), then the eval forward with the softmax fused - reference batch/dataset.py:192-205 ->
+        pipeline.py:205-218.  Returns (probabilities fp32 (n,n_classes,ph,pw), nan_mask uint8 (n,ph,pw))."""
+        if self.training:
+            raise RuntimeError("predict_proba_patches() is an eval-mode call; use model.eval() first")
+        ph, pw = patch_hw
+        n = centres.shape[0]
+        probe = torch.empty((0, self.in_channels, ph, pw), device=sv.device)
+        self._check_supported(probe)
+        if sv.dim() != 3 or sv.shape[0] != self.in_channels or sv.dtype != torch.float32 or not sv.is_contiguous():
+            raise RuntimeError(f"sv must be a contiguous fp32 (F={self.in_channels}, R, P) CUDA tensor")
+        if centres.dtype != torch.int32 or not centres.is_contiguous() or centres.device != sv.device:
+            raise RuntimeError("centres must be a contiguous int32 (n,2) tensor on the device of sv")
+        eng = self._engine_for_shape(n, ph, pw, sv.device, train=False)
+        state = eng.state_table(self._state_tensors())
+        key = (self._versions(), self._native_gen)
+        if eng.prepared_key != key:
+            eng.prepare(state, False)
+            eng.prepared_key = key
+        nan_mask = torch.empty((n, ph, pw), dtype=torch.uint8, device=sv.device)
+        out = torch.empty((n, self.n_classes, ph, pw), dtype=torch.float32, device=sv.device)
+        eng.preprocess_staged(sv, data_ping0, centres, nan_mask)
+        eng.forward_infer_staged(state, n, out, softmax)
+        return out, nan_mask
 
     def _train_forward(self, x, params):
         x = self._prep_input(x)

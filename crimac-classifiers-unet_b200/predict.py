@@ -3,8 +3,9 @@ pipeline_train_predict/save_predict.py:137-220 (save_survey_predictions_zarr) wi
 
     for each preload chunk of pings (utils/preload_data_split.py:22-30), sharded over GPUs by contiguous ping range:
         grid of overlapping patches        (batch/samplers/gridded.py:22-54; host arithmetic only)
-        crimac_preprocess                  gather + NaN fill + sv->dB + clip, straight from the preloaded pings
-        UNet_Baseline.predict_proba        the tcgen05 forward with the softmax fused
+        crimac_preprocess_staged           gather + NaN fill + sv->dB + clip, straight from the preloaded pings INTO the
+                                           first conv's bf16 hi/lo operand (no fp32 patch tensor in between)
+        UNet_Baseline.predict_proba_patches  the tcgen05 forward with the softmax fused
         crimac_stitch                      overlap-stitch of classes [SANDEEL, OTHER] into (2, range, pings) fp16
 
 Zarr reading / writing stays with the caller (out of scope: I/O format), which hands in device or host arrays.
@@ -104,7 +105,9 @@ def predict_host_batches(model, batches, classes=(1, 2)):
 
 class SurveyPredictor:
     def __init__(self, model, patch_hw=(256, 256), overlap=20, preload_n_pings=20000, batch_size=93, classes=(1, 2),
-                 seabed_pad=10):
+                 seabed_pad=10, direct=None):
+        # direct: preprocessing writes the first conv's operand (predict_proba_patches); default when the model has it
+        self.direct = hasattr(model, "predict_proba_patches") if direct is None else bool(direct)
         self.model, self.patch_hw, self.overlap = model, tuple(patch_hw), int(overlap)
         self.preload_n_pings, self.batch_size = int(preload_n_pings), int(batch_size)
         self.classes, self.seabed_pad = tuple(classes), int(seabed_pad)
@@ -128,8 +131,11 @@ class SurveyPredictor:
             out = torch.zeros((len(self.classes), R, end - start), dtype=torch.float16, device=dev)
         for i in range(0, centres.shape[0], self.batch_size):
             c = centres[i:i + self.batch_size].contiguous()
-            x, nan_mask = _engine.preprocess(sv, data_ping0, c, self.patch_hw)
-            probs = self.model.predict_proba(x)
+            if self.direct:
+                probs, nan_mask = self.model.predict_proba_patches(sv, data_ping0, c, self.patch_hw)
+            else:       # two-step form (kept for models without predict_proba_patches and as the A/B of the tests)
+                x, nan_mask = _engine.preprocess(sv, data_ping0, c, self.patch_hw)
+                probs = self.model.predict_proba(x)
             _engine.stitch(probs, c, nan_mask, out, start, self.overlap, labels=labels, seabed=seabed,
                            seabed_pad=self.seabed_pad, classes=self.classes)
         return out

@@ -67,8 +67,8 @@ int crimac_destroy(crimac_ctx* ctx);
  * conv epilogue).  Must be called after every change of the parameters and before the forward call that uses them. */
 int crimac_prepare(crimac_ctx* ctx, const void* const* state, int train, void* stream);
 
-/* x_dev: fp32 NCHW (nb, in_channels, H, W).  out_dev: fp32 NCHW (nb, n_classes, H, W): class probabilities
- * (softmax != 0) or raw logits. */
+/* x_dev: fp32 NCHW (nb, in_channels, H, W), or NULL when crimac_preprocess_staged has staged nb patches in ctx.
+ * out_dev: fp32 NCHW (nb, n_classes, H, W): class probabilities (softmax != 0) or raw logits. */
 int crimac_forward_infer(crimac_ctx* ctx, const void* const* state, const float* x_dev, int nb, float* out_dev,
                          int softmax, void* stream);
 /* Train-mode forward (batch statistics, running-stat update, activations kept for backward). logits_dev as above. */
@@ -108,6 +108,11 @@ int crimac_eval_loss(const float* logits_dev, int nb, int n_classes, int H, int 
  * non-finite (the pixels remove_nan_inf marks LABEL_IGNORE_VAL). */
 int crimac_preprocess(const float* sv_dev, int F, int R, int P, int data_ping0, const int32_t* centres_dev, int n,
                       int ph, int pw, float* out_dev, uint8_t* nan_dev, void* stream);
+/* The same gather + transform written STRAIGHT into the first conv's operand (bf16 hi/lo pairs, NHWC) inside ctx: the
+ * next crimac_forward_infer(ctx, state, x_dev = NULL, nb = n, ...) reads it by TMA and the fp32 NCHW patch tensor is
+ * never materialised.  Patch size = the context's (height, width); F = its in_channels; n <= max_batch. */
+int crimac_preprocess_staged(crimac_ctx* ctx, const float* sv_dev, int F, int R, int P, int data_ping0,
+                             const int32_t* centres_dev, int n, uint8_t* nan_dev, void* stream);
 /* Overlap-stitch (fill_out_array): for every patch pixel whose label would not be one of {-70 overlap frame,
  * -50 below seabed+pad on background, -100 outside [ping_start, ping_start+Pc) x [0,R) or non-finite}, write
  * probs[:, cls[k]] as fp16 into out_dev (K, R, Pc).  labels_dev: optional int16 (R, Pc) chunk labels after the

@@ -115,3 +115,79 @@ def test_sharding_covers_the_survey_once(pkg):
     for r in range(4):
         seen += Pr.shard_chunks(chunks, 4, r)
     assert seen == chunks
+
+
+@pytest.mark.parametrize("Fq", [4, 6, 1])
+def test_direct_preprocessing_feeds_the_first_conv_bit_identically(E, pkg, Fq):
+    """north_star: the preprocessing kernel feeds the first conv directly.  crimac_preprocess_staged writes the bf16
+    hi/lo NHWC operand of the tensor-core first conv; the result must equal - bit for bit - the two-step form
+    (crimac_preprocess -> fp32 NCHW patches -> the first conv's own split pass), incl. out-of-data patches, NaN / inf
+    samples and ragged edges, for the one-plane (<= 4 frequencies) and the two-plane (5..8) layout."""
+    Mm = importlib.import_module("crimac_unet_b200.models.unet")
+    torch.manual_seed(Fq)
+    R, Pn, patch = 100, 300, (64, 64)
+    g = torch.Generator(device=dev).manual_seed(1)
+    sv = torch.pow(10.0, torch.rand((Fq, R, Pn), device=dev, generator=g) * 7.0 - 9.0)
+    sv[0, 10:14, 20:40] = float("nan")
+    sv[Fq - 1, 50, 60] = float("inf")
+    sv[0, 70, 70] = -1.0                                           # negative sv -> log10 of a negative number -> NaN -> clipped like the reference
+    centres = torch.tensor([[31, 31], [31, 95], [95, 250], [-200, -200], [99, 299], [40, 5]], dtype=torch.int32, device=dev)
+    m = Mm.UNet_Baseline(3, Fq, depth=3)
+    m.load_state_dict(O.trained_like_state(m.state_dict(), 0, head_gain=2.0))
+    m = m.to(dev).eval()
+    x, nan_a = E.preprocess(sv, 7, centres, patch)
+    with torch.no_grad():
+        a = m.predict_proba(x)
+        b, nan_b = m.predict_proba_patches(sv, 7, centres, patch)
+        c, _ = m.predict_proba_patches(sv, 7, centres[:2].contiguous(), patch)      # smaller batch in the same context
+    assert torch.equal(nan_a, nan_b)
+    assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+    assert torch.equal(torch.nan_to_num(b[:2], nan=-1.0), torch.nan_to_num(c, nan=-1.0))
+
+
+def test_full_size_chunk_of_config3_against_the_oracle_pipeline(E, pkg):
+    """BASELINE configs[3] at FULL size for one preload chunk: pings [60000, 80000) of the synthetic
+    1 M-ping x 256-range survey (4 frequencies, 0.1 % NaNs, seabed 200 + 20 sin), preload_n_pings = 20000, 256x256
+    patches, overlap 20 -> 186 patches incl. the second patch row that is mostly below the data
+    (batch/samplers/gridded.py:40-47), neighbouring chunks' pings as context (batch/dataset.py:176-184).  Product =
+    SurveyPredictor (direct preprocessing -> tcgen05 forward -> stitch); oracle = numpy gather / transforms / label
+    masks per patch (oracle.patch_item) -> fp32 torch forward -> fill_out_array (save_predict.py:41-65).
+    Bounds: identical written-pixel set, values within 2.5e-2 (2e-2 bf16 + fp16 output)."""
+    Mm = importlib.import_module("crimac_unet_b200.models.unet")
+    Pr = importlib.import_module("crimac_unet_b200.predict")
+    S = importlib.import_module("crimac_unet_b200.synthetic")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    NP, R, patch, ov, preload = 1_000_000, 256, (256, 256), 20, 20000
+    s, e = 60000, 80000
+    torch.manual_seed(0)
+    m = Mm.UNet_Baseline(3, 4)
+    m.load_state_dict(O.trained_like_state(m.state_dict(), 0, head_gain=2.0))
+    m = m.to(dev).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    pred = Pr.SurveyPredictor(m, patch, ov, preload, batch_size=62)
+    seabed_all = S.synthetic_seabed(0, NP).numpy()
+    grid, (d0, d1) = pred.chunk_geometry(s, e, R, NP, seabed_max=int(seabed_all[s:e].max()))
+    ref_grid = P.get_data_grid(s, e, 0, P.end_range_from_seabed(R, seabed_all[s:e]), patch, ov)
+    assert np.array_equal(grid, ref_grid) and len(grid) == 186
+    assert (d0, d1) == tuple(P.preload_extents(ref_grid, NP, patch[1]))
+    sv_dev = S.synthetic_survey_pings(4, R, d0, d1, seed=5, device=dev)
+    sb_dev = torch.from_numpy(seabed_all[s:e].astype(np.int32)).to(dev)
+    got = pred.predict_chunk(sv_dev, d0, grid, s, e, seabed=sb_dev).float().cpu().numpy()
+    # ---- oracle
+    sv_np = sv_dev.cpu().numpy()
+    ref = np.zeros((2, R, e - s))
+    lab0 = np.zeros((R, e - s))
+    items = [P.patch_item(sv_np, d0, lab0, s, c, seabed_all, R, NP, patch, ov) for c in grid]
+    with torch.no_grad():
+        for i in range(0, len(items), 31):
+            xb = torch.from_numpy(np.stack([d for d, _ in items[i:i + 31]])).to(dev)
+            pb = O.softmax_probs(O.unet_forward(sd, xb)).cpu().numpy()
+            for j, p in enumerate(pb):
+                P.fill_out_array(ref, p, items[i + j][1], grid[i + j], s)
+    written, ref_written = got[0] != 0, ref[0] != 0
+    frac = ref_written.mean()
+    print(f"configs[3] chunk [{s},{e}): {len(grid)} patches, {frac:.4f} of the output pixels written; max |d| {np.abs(got - ref).max():.4f}")
+    assert np.array_equal(written, ref_written)
+    assert 0.7 < frac < 0.9                                            # rows below seabed + 10 and NaN pixels stay 0
+    assert np.abs(got - ref).max() <= 2.5e-2
