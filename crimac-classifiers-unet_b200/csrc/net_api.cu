@@ -101,6 +101,11 @@ struct crimac_ctx {
   ConvParams head_fused{};   // last conv with the 1x1 head in its epilogue (eval)
   int prepared_mode = -1;
   int staged_nb = 0;         // patches crimac_preprocess_staged left in xs (consumed by the next forward with x == NULL)
+  // data-parallel gradient exchange over peer memory (crimac_set_comm): buckets are reduced on `comm` while backward runs
+  crimac_comm_config comm{};
+  bool comm_on = false;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_bk_main[3] = {nullptr, nullptr, nullptr}, ev_bk_side[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
 };
 
 namespace {
@@ -517,8 +522,8 @@ double igemm_flops_n(const ConvParams& p, int n_total) {
   return 2.0 * p.NB * static_cast<double>(p.H) * p.W * n_total * p.taps * p.cin;
 }
 
-// The weight-gradient GEMMs accumulate (red.add) into their layer's zeroed scratch; crimac_backward turns all of them
-// into PyTorch-layout gradients with ONE unpack launch at its end.
+// The weight-gradient GEMMs accumulate (red.add) into their layer's zeroed scratch; crimac_backward turns them into
+// PyTorch-layout gradients with one unpack launch per gradient bucket (decoder, deep encoder, shallow encoder).
 int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, cudaStream_t st) {
   set_batch(w, nb);
   ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.M_total * w.N_total * w.taps, 0, st);
@@ -584,8 +589,11 @@ extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* w
   if (rc == 0 && cfg->train) {
     c->overlap = true;  // switched off only while crimac_profile_enable(1) times every kernel on its own
     cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
-    for (cudaEvent_t* ev : {&c->ev_draw[0], &c->ev_draw[1], &c->ev_wg[0], &c->ev_wg[1], &c->ev_cat, &c->ev_join})
+    for (cudaEvent_t* ev : {&c->ev_draw[0], &c->ev_draw[1], &c->ev_wg[0], &c->ev_wg[1], &c->ev_cat, &c->ev_join,
+                            &c->ev_bk_main[0], &c->ev_bk_main[1], &c->ev_bk_main[2], &c->ev_bk_side[0], &c->ev_bk_side[1],
+                            &c->ev_bk_side[2], &c->ev_comm})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
       crimac_set_error(std::string("side stream / event creation failed: ") + cudaGetErrorString(e));
       rc = 2;
@@ -604,6 +612,10 @@ extern "C" int crimac_destroy(crimac_ctx* c) {
     for (cudaEvent_t ev : {c->ev_draw[0], c->ev_draw[1], c->ev_wg[0], c->ev_wg[1], c->ev_cat, c->ev_join})
       if (ev) cudaEventDestroy(ev);
     if (c->side) cudaStreamDestroy(c->side);
+    for (cudaEvent_t ev : {c->ev_bk_main[0], c->ev_bk_main[1], c->ev_bk_main[2], c->ev_bk_side[0], c->ev_bk_side[1],
+                           c->ev_bk_side[2], c->ev_comm})
+      if (ev) cudaEventDestroy(ev);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   }
   delete c;
   return 0;
@@ -846,6 +858,58 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     return 0;
   };
 
+  // Gradient buckets in backward order: 0 = decoder + head (the tail of parameters()), 1 = the two deepest encoder
+  // blocks, 2 = the remaining encoder blocks.  When a bucket's last kernels have been issued, its weight-gradient scratch
+  // is un-packed ON THE SIDE STREAM (in order behind the GEMMs that filled it) and - data parallel - its slice of the
+  // flat gradient arena is all-reduced over peer memory on the communication stream while backward continues.
+  const int enc_split = D >= 3 ? D - 2 : 0;  // encoder blocks >= enc_split form bucket 1
+  auto close_bucket = [&](int b) -> int {
+    UnpackTable t{};
+    auto add3 = [&](const Conv3& L) {
+      if (!L.first) t.e[t.n++] = UnpackEntry{L.wg_scratch, grads[L.g_w], static_cast<long>(L.cout) * L.cin, 9, 0};
+    };
+    if (b == 0) {
+      for (int j = 0; j < D - 1; ++j) {
+        add3(c->conv[c->dec1[j]]);
+        add3(c->conv[c->dec2[j]]);
+        const ConvT& U = c->up[j];
+        t.e[t.n++] = UnpackEntry{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, 4, 0};
+      }
+    } else {
+      const int l0 = b == 1 ? enc_split : 0, l1 = b == 1 ? D : enc_split;
+      for (int l = l0; l < l1; ++l) {
+        add3(c->conv[c->enc1[l]]);
+        add3(c->conv[c->enc2[l]]);
+      }
+    }
+    cudaStream_t us = c->overlap ? c->side : st;
+    if (t.n > 0) {
+      ProfScope ps("wgrad_unpack", 0, 0, us);
+      CRIMAC_CHECK_CUDA(launch_wgrad_unpack_all(t, us));
+    }
+    if (!c->comm_on) return 0;
+    // arena slice of the bucket, from the gradient table (parameters() order: encoder blocks, decoder blocks, head)
+    const float* base = c->comm.peer_arenas[c->comm.rank];
+    const float* lo = b == 0 ? grads[c->up[0].g_w] : grads[c->conv[c->enc1[b == 1 ? enc_split : 0]].g_w];
+    const float* hi = b == 0 ? base + c->comm.arena_floats
+                             : (b == 1 ? grads[c->up[0].g_w] : grads[c->conv[c->enc1[enc_split]].g_w]);
+    if (hi <= lo) return 0;
+    CRIMAC_REQUIRE(lo >= base && hi <= base + c->comm.arena_floats && (lo - base) % 4 == 0,
+                   "gradient tensors are not views of the symmetric arena given to crimac_set_comm (parameters() order, 16-byte aligned)");
+    size_t count = static_cast<size_t>(hi - lo);
+    count = (count + 3) & ~static_cast<size_t>(3);   // the arena is padded to a multiple of 4 floats
+    cudaStream_t cs = st;
+    if (c->overlap) {
+      CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_bk_main[b], st));
+      CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_bk_side[b], c->side));
+      CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bk_main[b], 0));
+      CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bk_side[b], 0));
+      cs = c->comm_stream;
+    }
+    return crimac_peer_allreduce(c->comm.peer_arenas, c->comm.peer_pads, c->comm.multicast_arena, c->comm.local_state,
+                                 c->comm.rank, c->comm.world, b, static_cast<size_t>(lo - base), count, c->comm.ctas, cs);
+  };
+
   // head
   const int last = c->dec2[D - 2];
   if (!head_done) {
@@ -881,6 +945,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     }
     if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, ss))) return rc;
   }
+  if ((rc = close_bucket(0))) return rc;
   // encoder, deepest level first
   for (int l = D - 1; l >= 0; --l) {
     Conv3& L2 = c->conv[c->enc2[l]];
@@ -894,20 +959,37 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     }
     if ((rc = conv_bwd(c->enc2[l]))) return rc;  // dgrad -> dA of enc1[l]
     if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
+    if (l == enc_split && enc_split > 0 && (rc = close_bucket(1))) return rc;
   }
+  if ((rc = close_bucket(enc_split > 0 ? 2 : 1))) return rc;
   if (c->overlap) {
     CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_join, c->side));
     CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (c->comm_on) {
+      CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
+      CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_comm, 0));
+    }
   }
-  {
-    UnpackTable t{};
-    for (Conv3& L : c->conv)
-      if (!L.first) t.e[t.n++] = UnpackEntry{L.wg_scratch, grads[L.g_w], static_cast<long>(L.cout) * L.cin, 9, 0};
-    for (ConvT& U : c->up) t.e[t.n++] = UnpackEntry{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, 4, 0};
-    ProfScope ps("wgrad_unpack", 0, 3.0 * static_cast<double>(c->wg_arena_bytes), st);
-    CRIMAC_CHECK_CUDA(launch_wgrad_unpack_all(t, st));
-    c->wg_dirty = false;
+  c->wg_dirty = false;  // every layer's scratch has been un-packed (and re-zeroed) by the three bucket launches
+  return 0;
+}
+
+// Data-parallel gradient exchange: from now on every crimac_backward / crimac_train_step on this context all-reduces (sum)
+// the gradient arena over the replicas with crimac_peer_allreduce, bucket by bucket, overlapped with backward.  The
+// `grads` table of those calls must then point INTO the symmetric arena (parameters() order).  cfg == NULL switches the
+// exchange off.  Every replica must issue the same sequence of calls.
+extern "C" int crimac_set_comm(crimac_ctx* c, const crimac_comm_config* cfg) {
+  CRIMAC_REQUIRE(c != nullptr && c->cfg.train, "train context required");
+  if (cfg == nullptr) {
+    c->comm_on = false;
+    return 0;
   }
+  CRIMAC_REQUIRE(cfg->world >= 1 && cfg->world <= 8 && cfg->rank >= 0 && cfg->rank < cfg->world, "rank / world");
+  CRIMAC_REQUIRE(cfg->local_state != nullptr && cfg->arena_floats % 4 == 0, "local_state / arena_floats (multiple of 4)");
+  for (int r = 0; r < cfg->world; ++r)
+    CRIMAC_REQUIRE(cfg->peer_arenas[r] != nullptr && cfg->peer_pads[r] != nullptr, "NULL peer pointer");
+  c->comm = *cfg;
+  c->comm_on = cfg->world > 1;
   return 0;
 }
 

@@ -22,6 +22,47 @@ class _Config(ctypes.Structure):
     ]
 
 
+class _CommConfig(ctypes.Structure):
+    _fields_ = [
+        ("world", ctypes.c_int),
+        ("rank", ctypes.c_int),
+        ("peer_arenas", ctypes.c_void_p * 8),
+        ("peer_pads", ctypes.c_void_p * 8),
+        ("multicast_arena", ctypes.c_void_p),
+        ("local_state", ctypes.c_void_p),
+        ("arena_floats", ctypes.c_size_t),
+        ("ctas", ctypes.c_int),
+    ]
+
+
+AR_PAD_BYTES = 8 * 2 * 16 * 4      # CRIMAC_AR_PAD_BYTES
+AR_STATE_BYTES = 8 * 8             # 8 bytes per bucket, CRIMAC_AR_MAX_BUCKETS = 8
+
+
+def make_comm_config(world, rank, peer_arenas, peer_pads, multicast_arena, local_state_ptr, arena_floats, ctas=0):
+    cfg = _CommConfig()
+    cfg.world, cfg.rank = int(world), int(rank)
+    for r in range(world):
+        cfg.peer_arenas[r] = int(peer_arenas[r])
+        cfg.peer_pads[r] = int(peer_pads[r])
+    cfg.multicast_arena = int(multicast_arena) if multicast_arena else None
+    cfg.local_state = int(local_state_ptr)
+    cfg.arena_floats = int(arena_floats)
+    cfg.ctas = int(ctas)
+    return cfg
+
+
+def peer_allreduce(comm, bucket, offset, count, stream=None):
+    """One bucket of the peer-memory all-reduce on its own (crimac_peer_allreduce); tests and tools."""
+    L = _lib.load()
+    _lib.check(
+        L.crimac_peer_allreduce(comm.peer_arenas, comm.peer_pads, ctypes.c_void_p(comm.multicast_arena),
+                                ctypes.c_void_p(comm.local_state), comm.rank, comm.world, int(bucket),
+                                ctypes.c_size_t(offset), ctypes.c_size_t(count), comm.ctas, _lib.stream_ptr(stream)),
+        "crimac_peer_allreduce",
+    )
+
+
 def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, height, width, train):
     """Size of the device workspace a context of this shape needs (pure host computation)."""
     L = _lib.load()
@@ -63,6 +104,11 @@ class Context:
                 self.handle = None
         except Exception:
             pass
+
+    def set_comm(self, comm):
+        """Switch the bucketed peer-memory gradient all-reduce of this context on (a _CommConfig) or off (None)."""
+        self._comm = comm   # keep the structure (and the pointers in it) alive
+        _lib.check(self.L.crimac_set_comm(self.handle, ctypes.byref(comm) if comm is not None else None), "crimac_set_comm")
 
     # ---- tables
     def state_table(self, tensors):

@@ -258,6 +258,14 @@ class _NativePlumbing:
         if problems:
             raise RuntimeError(f"crimac_unet_b200.{type(self).__name__} cannot run this call natively: " + "; ".join(problems))
 
+    def _set_native_comm(self, comm):
+        """Data parallel (trainer.PeerGradientExchange): every train context of this model - existing and future - exchanges
+        its gradients over peer memory inside backward.  comm = engine._CommConfig or None."""
+        self._native_comm = comm
+        for key, eng in _ENGINES.get(self, {}).items():
+            if key[2]:
+                eng.set_comm(comm)
+
     def _meta_head_channels(self):
         return 0
 
@@ -298,6 +306,9 @@ class _NativePlumbing:
         if eng is None or eng.cfg.max_batch < nb:
             eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, device)
             engines[key] = eng
+            comm = getattr(self, "_native_comm", None)
+            if train and comm is not None:
+                eng.set_comm(comm)    # data parallel: gradients are exchanged over peer memory inside backward
         return eng
 
     def _versions(self):

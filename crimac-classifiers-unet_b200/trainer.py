@@ -16,6 +16,43 @@ import torch.distributed as dist
 from . import engine as _engine
 
 
+class PeerGradientExchange:
+    """Symmetric-memory plumbing of the peer all-reduce (csrc/peer_allreduce.cu): allocates the flat gradient arena and
+    the signal pad with torch.distributed._symmetric_memory (cuMemMap'ed on every GPU of the node, NVSwitch multicast
+    address when the fabric offers one), exchanges the handles, and builds the crimac_comm_config every native train
+    context of the model gets.  One process per GPU, NCCL process group already initialised."""
+
+    def __init__(self, total_floats, device, group=None, use_multicast=None, ctas=0):
+        import os
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("the peer-memory gradient exchange covers one NVSwitch node (<= 8 replicas)")
+        padded = (total_floats + 1023) // 1024 * 1024
+        self.arena = symm_mem.empty(padded, dtype=torch.float32, device=device)
+        self.pad = symm_mem.empty(_engine.AR_PAD_BYTES // 4, dtype=torch.int32, device=device)
+        self.arena.zero_()
+        self.pad.zero_()
+        h_arena = symm_mem.rendezvous(self.arena, group)
+        h_pad = symm_mem.rendezvous(self.pad, group)
+        self.state = torch.zeros(_engine.AR_STATE_BYTES // 4, dtype=torch.int32, device=device)
+        if use_multicast is None:
+            use_multicast = os.environ.get("CRIMAC_AR_MULTICAST", "1") != "0"
+        mc = 0
+        try:
+            if use_multicast and h_arena.has_multicast_support(device.type, device.index if device.index is not None else 0):
+                mc = int(h_arena.multicast_ptr)
+        except Exception:
+            mc = 0
+        self.multicast = mc != 0
+        self.comm = _engine.make_comm_config(self.world, self.rank, list(h_arena.buffer_ptrs), list(h_pad.buffer_ptrs),
+                                             mc, self.state.data_ptr(), padded, ctas)
+        self._handles = (h_arena, h_pad)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every pad is zero and mapped before the first flag is written
+
+
 def reduce_gradients(flat_grads, world):
     """Sum the flat gradient arena over all replicas (NCCL on GPUs, gloo in the CPU tests) and return the factor that
     turns the sum into the DDP mean; the factor is folded into the SGD kernel instead of a separate scaling pass."""
@@ -26,7 +63,7 @@ def reduce_gradients(flat_grads, world):
 
 class Trainer:
     def __init__(self, model, lr=0.005, momentum=0.95, lr_reduction=0.5, lr_step=1000, class_weight=(10.0, 300.0, 250.0),
-                 use_cuda_graph=None):
+                 use_cuda_graph=None, exchange=None):
         # defaults: reference configs/config_baseline.yaml:28-31,38 and pipeline.py:135
         self.model = model
         self.lr, self.momentum = float(lr), float(momentum)
@@ -55,7 +92,16 @@ class Trainer:
         self._graph = None
         self._graph_key = None
         self._eager_done = set()
+        # gradient exchange: "peer" = our own NVLink peer-memory all-reduce kernels, launched bucket by bucket inside
+        # backward and captured in the step's CUDA graph; "nccl" = one ncclAllReduce of the whole arena after backward
+        # (kept as the A/B baseline: Trainer(..., exchange="nccl"))
+        self.exchange = None
         if self.world > 1:
+            self.exchange = exchange if exchange is not None else ("peer" if dev.type == "cuda" else "nccl")
+            if self.exchange == "peer":
+                self.peer = PeerGradientExchange(total, dev)
+                model._grad_arena = self.peer.arena[:total]       # train_step_fused seats every p.grad in here
+                model._set_native_comm(self.peer.comm)
             self.broadcast_parameters(0)   # DDP semantics: every replica starts from rank 0's weights and buffers
 
     def broadcast_parameters(self, src=0):
@@ -117,10 +163,14 @@ class Trainer:
         return self.model.train_step_fused(x, labels, self.class_weight)
 
     def _launch_update(self):
-        """Gradient exchange + optimizer.  The NCCL all-reduce is never captured in a graph (a captured collective
-        keeps communicator resources alive and made process-group teardown hang in our runs): eager on `world` > 1."""
+        """Optimizer (+ the NCCL gradient exchange in the "nccl" A/B mode; with the peer exchange the gradients were
+        already all-reduced inside backward).  A NCCL all-reduce is never captured in a graph (a captured collective
+        keeps communicator resources alive and made process-group teardown hang in our runs)."""
         grads = self.model._grad_arena
-        gscale = reduce_gradients(grads, self.world)  # NCCL over NVLink / NVSwitch
+        if self.exchange == "nccl":
+            gscale = reduce_gradients(grads, self.world)  # NCCL over NVLink / NVSwitch
+        else:
+            gscale = 1.0 / self.world                     # peer exchange left the SUM over replicas in every arena
         _engine.sgd_step(self.flat_params, self.flat_momentum, grads, self.lr, self.momentum, gscale)
 
     def _launch_step(self, x, labels):
@@ -155,8 +205,8 @@ class Trainer:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):                 # recorded, not executed
                     self._sloss = self._launch_fwd_bwd(self._sx, self._sy)
-                    if self.world == 1:
-                        self._launch_update()             # single GPU: the SGD kernel rides in the same graph
+                    if self.exchange != "nccl":
+                        self._launch_update()             # the SGD kernel (and the peer exchange) ride in the same graph
                 self._graph, self._graph_key = g, key
             except Exception as exc:                      # e.g. a collective that cannot be captured: stay eager
                 import warnings
@@ -169,7 +219,7 @@ class Trainer:
         self._sx.copy_(x)
         self._sy.copy_(labels)
         self._graph.replay()
-        if self.world > 1:
+        if self.exchange == "nccl":
             self._launch_update()
         self._advance()
         return self._sloss.clone()

@@ -101,6 +101,35 @@ int crimac_eval_loss(const float* logits_dev, int nb, int n_classes, int H, int 
                      int label_bits, const float* class_w_dev, int prob_class, float* prob_out_dev,
                      int64_t* labels_out_dev, float* out3_dev, void* scratch_dev, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (the reference has no multi-GPU path)
+ * Sum-all-reduce of floats [offset, offset+count) of a flat fp32 gradient arena that every replica allocated
+ * SYMMETRICALLY (same size, mapped on every GPU of the node, e.g. torch.distributed._symmetric_memory), in ONE kernel on
+ * `stream`: flag exchange, each rank reduces its 1/world slice in fixed rank order and stores the sums into all arenas
+ * (multimem.ld_reduce / multimem.st through the NVSwitch when multicast_arena_dev != NULL).  Results are bit-identical on
+ * all replicas.  peer_arenas / peer_pads: HOST arrays of `world` device pointers (entry `rank` = the local one); pads:
+ * symmetric, zero-initialised, >= CRIMAC_AR_PAD_BYTES each; local_state_dev: zero-initialised, >= 8 *
+ * CRIMAC_AR_MAX_BUCKETS bytes, private to this rank.  `bucket` (0..CRIMAC_AR_MAX_BUCKETS-1) selects the flag rows, so
+ * several buckets may be in flight.  offset, count: multiples of 4.  ctas <= 0: default.  The kernel keeps its own epoch
+ * counter in local_state_dev: every rank must launch the same sequence of calls (CUDA-graph replay safe). */
+#define CRIMAC_AR_MAX_BUCKETS 8
+#define CRIMAC_AR_PAD_BYTES (CRIMAC_AR_MAX_BUCKETS * 2 * 16 * 4)
+int crimac_peer_allreduce(float* const* peer_arenas, void* const* peer_pads, float* multicast_arena_dev,
+                          void* local_state_dev, int rank, int world, int bucket, size_t offset, size_t count, int ctas,
+                          void* stream);
+
+typedef struct crimac_comm_config {
+  int world, rank;                /* replicas on this node (<= 8), this replica's index                          */
+  float* peer_arenas[8];          /* every replica's symmetric gradient arena as mapped on THIS device            */
+  void* peer_pads[8];             /* every replica's symmetric signal pad (CRIMAC_AR_PAD_BYTES, zeroed)           */
+  float* multicast_arena;         /* NVSwitch multicast address of the arena, or NULL (peer loads / stores)       */
+  void* local_state;              /* private device scratch, 8 * CRIMAC_AR_MAX_BUCKETS bytes, zeroed              */
+  size_t arena_floats;            /* arena size in floats, multiple of 4 (pad the 31 044 227 parameters up)       */
+  int ctas;                       /* CTAs of the exchange kernel (<= 0: default 64)                               */
+} crimac_comm_config;
+/* Switch the bucketed, backward-overlapped gradient all-reduce of crimac_backward / crimac_train_step on (cfg != NULL)
+ * or off (NULL); see csrc/net_api.cu.  The gradient pointers of those calls must then be views of peer_arenas[rank]. */
+int crimac_set_comm(crimac_ctx* ctx, const crimac_comm_config* cfg);
+
 /* Patch gather + sv->dB transform.  sv_dev: fp32 (F, R, P) preloaded pings [frequency][range][ping] whose column 0 is
  * survey ping data_ping0; centres_dev: int32 (n,2) patch centres (y, x) in survey coordinates (batch/samplers/
  * gridded.py:22-54); out_dev: fp32 NCHW (n, F, ph, pw) = clip(10*log10(sv+1e-10), -75, 0) with out-of-data and

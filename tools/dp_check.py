@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Multi-GPU correctness + timing check of the data-parallel train step (run on N >= 2 GPUs of one node):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py
+
+Checks: (1) after the peer-memory exchange every replica's gradient arena is bit-identical and
+equals the SUM of the per-replica gradients (computed by an independent model copy without exchange, gathered with
+NCCL) to weight-gradient summation-order accuracy; (2) after K optimisation steps (eager + CUDA-graph replays) all
+replicas hold bit-identical parameters; (3) step time with the peer exchange vs one ncclAllReduce after backward.
+Prints one JSON line on rank 0."""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from __graft_entry__ import load_package
+    load_package()
+    import crimac_unet_b200.models.unet as M
+    import crimac_unet_b200.synthetic as S
+    from crimac_unet_b200.trainer import Trainer
+    B, HW = int(os.environ.get("DP_BATCH", "8")), int(os.environ.get("DP_SIZE", "128"))
+    out = {"world": world, "batch": B, "size": HW}
+    cw = torch.tensor([10.0, 300.0, 250.0], device=dev)
+    torch.manual_seed(0)
+    model = M.UNet_Baseline(3, 4).to(dev).train()
+    tr = Trainer(model, lr=0.005, momentum=0.95)                 # peer exchange; broadcasts rank 0's weights
+    out["exchange"], out["multicast"] = tr.exchange, bool(getattr(tr, "peer", None) and tr.peer.multicast)
+    x, y = S.structured_batch(B, HW, HW, seed=100 + rank, device=dev)
+    # ---- (1) exchanged gradients == sum of per-replica gradients, identical everywhere
+    twin = M.UNet_Baseline(3, 4).to(dev).train()
+    twin.load_state_dict(model.state_dict())
+    twin.train_step_fused(x, y, cw)
+    local_g = twin._grad_arena.clone()
+    total = local_g.numel()
+    gathered = [torch.empty_like(local_g) for _ in range(world)]
+    dist.all_gather(gathered, local_g)
+    want = torch.stack(gathered).double().sum(0)
+    st0 = {k: v.clone() for k, v in model.state_dict().items()}
+    model.train_step_fused(x, y, cw)                              # backward with the bucketed exchange inside
+    torch.cuda.synchronize()
+    got = model._grad_arena.clone()
+    model.load_state_dict(st0)
+    rel = ((got.double() - want).norm() / want.norm()).item()
+    arenas = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(arenas, got)
+    out["grad_sum_rel_err"] = rel
+    out["grad_arenas_bit_identical"] = all(torch.equal(arenas[0], a) for a in arenas[1:])
+    # bucket tails: the last element of the arena and the bucket boundaries must be covered
+    nz = (got != 0).float().mean().item()
+    out["nonzero_fraction"] = nz
+    # ---- (2) replicas stay in sync over optimisation steps (eager first step, then graph replays)
+    for i in range(6):
+        tr.step(x, y)
+    torch.cuda.synchronize()
+    chk = torch.stack([tr.flat_params.double().sum(), (tr.flat_params.double() ** 2).sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out["params_bit_identical_after_6_steps"] = bool(torch.equal(lo, hi))
+    out["graph_replay"] = tr._graph is not None
+
+    # ---- (3) timing: peer exchange (in graph, overlapped) vs NCCL after backward, full-size batch
+    def bench(trainer, xx, yy, k=20):
+        for _ in range(4):
+            trainer.step(xx, yy)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            trainer.step(xx, yy)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    if os.environ.get("DP_TIMING", "1") != "0":
+        xb, yb = S.synthetic_echogram(32, 4, 256, 256, seed=1 + rank, device=dev), S.synthetic_labels(32, 256, 256, seed=9 + rank, device=dev)
+        out["ms_per_step_peer"] = bench(tr, xb, yb)
+        del tr, twin
+        torch.manual_seed(0)
+        m2 = M.UNet_Baseline(3, 4).to(dev).train()
+        tr2 = Trainer(m2, lr=0.005, momentum=0.95, exchange="nccl")
+        out["ms_per_step_nccl"] = bench(tr2, xb, yb)
+        tr2._graph = None
+    ok = out["grad_arenas_bit_identical"] and out["params_bit_identical_after_6_steps"] and rel < 1e-4
+    out["ok"] = bool(ok)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    import threading
+    threading.Timer(30.0, lambda: os._exit(0 if ok else 1)).start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    os._exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
