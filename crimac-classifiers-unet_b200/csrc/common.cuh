@@ -69,7 +69,9 @@ struct WgradParams {
   int k_tiles_total;     // NB*tiles_y*tiles_x
   int splits;            // split-K factor (gridDim.z)
   int m_tiles, n_tiles;
-  float* dw;             // fp32 gradient in PyTorch layout: index (m*N_total + n)*taps + tap ; accumulated with red.add
+  float* dw;             // scratch [taps][M_total][N_total] fp32; split-K partial tiles accumulate with red.add ...
+  float* slabs;          // ... or (deterministic mode, != nullptr) split s stores its partial tile into slabs + s*slab_stride
+  long slab_stride;      //     (same [tap][m][n] layout per slab); the unpack kernel sums the slabs in fixed order
 };
 
 // Weight gradient of a 3x3 conv with ALL nine taps per CTA: the shifted operand (dY) is loaded once per k-step as a
@@ -84,6 +86,8 @@ struct WgradHaloParams {
   int splits;
   int s_tiles, f_tiles;  // Cs/64, Cf/64
   float* dw;             // scratch [9][Cs][Cf] fp32
+  float* slabs;          // deterministic mode: per-split slabs, see WgradParams
+  long slab_stride;
 };
 
 #define CRIMAC_MAX_CLASSES 8

@@ -45,6 +45,9 @@ struct UnpackEntry {
   long mn;
   int taps;
   int item0;
+  const float* slabs = nullptr;  // deterministic mode: `splits` partial copies of scratch, slab_stride floats apart,
+  int splits = 0;                // summed in order instead of reading (and zeroing) scratch
+  long slab_stride = 0;
 };
 struct UnpackTable {
   int n;

@@ -18,6 +18,7 @@
 #include "../../include/crimac_b200.h"
 #include <vector>
 #include <new>
+#include <algorithm>
 
 namespace {
 
@@ -52,6 +53,8 @@ struct Conv3 {
   WgradParams wg_tap{};   // one-tap-per-CTA kernel (deep layers: few pixels, many channels)
   bool wg_use_halo = true;
   float* wg_scratch = nullptr;  // [9][cout][cin] fp32, zero between steps
+  float* wg_slabs = nullptr;    // deterministic mode: wg_max_splits copies of the scratch, one per split-K slice
+  int wg_max_splits = 0, wg_active = 0;  // allocated / written by the last launch
   int gr_idx = 0;               // which of the two dRaw buffers this layer's BatchNorm backward writes
 };
 struct ConvT {
@@ -63,6 +66,8 @@ struct ConvT {
   ConvParams fwd{}, dgrad{};
   WgradParams wg{};
   float* wg_scratch = nullptr;  // [4][cin][cout] fp32, zero between steps
+  float* wg_slabs = nullptr;
+  int wg_max_splits = 0, wg_active = 0;
 };
 
 int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
@@ -331,6 +336,21 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         if (q) q += static_cast<size_t>(4) * U.cin * U.cout;
       }
     }
+    if (cfg.deterministic) {
+      // fixed-order split-K: every split stores its partial tile into its own slab (<= 2 waves of 148 CTAs per layer)
+      for (Conv3& L : c->conv)
+        if (!L.first) {
+          const bool halo = static_cast<long>(L.cout) * L.cin <= 256L * 128L;
+          const int tiles = halo ? (L.cout / 64) * (L.cin / 64) : 9 * ((L.cout + 127) / 128) * (L.cin / pick_bn(L.cin));
+          L.wg_max_splits = std::max(1, (2 * 148) / tiles);
+          L.wg_slabs = bump.arr<float>(static_cast<size_t>(L.wg_max_splits) * 9 * L.cout * L.cin);
+        }
+      for (ConvT& U : c->up) {
+        const int tiles = 4 * ((U.cin + 127) / 128) * (U.cout / pick_bn(U.cout));
+        U.wg_max_splits = std::max(1, (2 * 148) / tiles);
+        U.wg_slabs = bump.arr<float>(static_cast<size_t>(U.wg_max_splits) * 4 * U.cin * U.cout);
+      }
+    }
     c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 4 * (cfg.n_classes * 64 + cfg.n_classes));
     c->fc_partials = bump.arr<float>(first_conv_wgrad_partial_floats(cfg.in_channels));
     c->ce_partials = bump.arr<double>(static_cast<size_t>(ce_blocks()) * 2);
@@ -524,15 +544,35 @@ double igemm_flops_n(const ConvParams& p, int n_total) {
 
 // The weight-gradient GEMMs accumulate (red.add) into their layer's zeroed scratch; crimac_backward turns them into
 // PyTorch-layout gradients with one unpack launch per gradient bucket (decoder, deep encoder, shallow encoder).
-int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, cudaStream_t st) {
+// active = number of split-K slices that have work (= slabs written in deterministic mode)
+int active_splits(int k_tiles_total, int splits) {
+  const int per = (k_tiles_total + splits - 1) / splits;
+  return (k_tiles_total + per - 1) / per;
+}
+
+int wgrad_run(crimac_ctx* c, WgradParams& w, int bn, int nb, cudaStream_t st, float* slabs = nullptr, int max_splits = 0,
+              int* active = nullptr) {
   set_batch(w, nb);
+  w.slabs = slabs;
+  if (slabs) {
+    if (w.splits > max_splits) w.splits = max_splits;
+    w.slab_stride = static_cast<long>(w.taps) * w.M_total * w.N_total;
+    *active = active_splits(w.k_tiles_total, w.splits);
+  }
   ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.M_total * w.N_total * w.taps, 0, st);
   CRIMAC_CHECK_CUDA(launch_wgrad_gemm(w, bn, st));
   return 0;
 }
 
-int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, cudaStream_t st) {
+int wgrad_halo_run(crimac_ctx* c, WgradHaloParams& w, int nb, cudaStream_t st, float* slabs = nullptr, int max_splits = 0,
+                   int* active = nullptr) {
   set_batch(w, nb);
+  w.slabs = slabs;
+  if (slabs) {
+    if (w.splits > max_splits) w.splits = max_splits;
+    w.slab_stride = static_cast<long>(9) * w.Cs * w.Cf;
+    *active = active_splits(w.k_tiles_total, w.splits);
+  }
   ProfScope ps("wgrad_gemm", 2.0 * nb * static_cast<double>(w.H) * w.W * w.Cs * w.Cf * 9, 0, st);
   CRIMAC_CHECK_CUDA(launch_wgrad_halo(w, st));
   return 0;
@@ -848,7 +888,8 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("first_conv_wgrad", 2.0 * px * 64 * 9 * L.cin, px * (4.0 * L.cin + 2.0 * 64), ws, 2);
       CRIMAC_CHECK_CUDA(launch_first_conv_wgrad(x, c->xs, dr, L.cin, c->fc_partials, grads[L.g_w], 0, ws));
     } else {
-      int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, ws) : wgrad_run(c, L.wg_tap, L.bn_wg, nb, ws);
+      int r = L.wg_use_halo ? wgrad_halo_run(c, L.wg, nb, ws, L.wg_slabs, L.wg_max_splits, &L.wg_active)
+                            : wgrad_run(c, L.wg_tap, L.bn_wg, nb, ws, L.wg_slabs, L.wg_max_splits, &L.wg_active);
       if (r) return r;
     }
     if (c->overlap) {
@@ -866,14 +907,27 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   auto close_bucket = [&](int b) -> int {
     UnpackTable t{};
     auto add3 = [&](const Conv3& L) {
-      if (!L.first) t.e[t.n++] = UnpackEntry{L.wg_scratch, grads[L.g_w], static_cast<long>(L.cout) * L.cin, 9, 0};
+      if (L.first) return;
+      UnpackEntry e{L.wg_scratch, grads[L.g_w], static_cast<long>(L.cout) * L.cin, 9, 0};
+      if (L.wg_slabs) {
+        e.slabs = L.wg_slabs;
+        e.splits = L.wg_active;
+        e.slab_stride = 9L * L.cout * L.cin;
+      }
+      t.e[t.n++] = e;
     };
     if (b == 0) {
       for (int j = 0; j < D - 1; ++j) {
         add3(c->conv[c->dec1[j]]);
         add3(c->conv[c->dec2[j]]);
         const ConvT& U = c->up[j];
-        t.e[t.n++] = UnpackEntry{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, 4, 0};
+        UnpackEntry e{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, 4, 0};
+        if (U.wg_slabs) {
+          e.slabs = U.wg_slabs;
+          e.splits = U.wg_active;
+          e.slab_stride = 4L * U.cin * U.cout;
+        }
+        t.e[t.n++] = e;
       }
     } else {
       const int l0 = b == 1 ? enc_split : 0, l1 = b == 1 ? D : enc_split;
@@ -943,7 +997,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
       CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));
     }
-    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, ss))) return rc;
+    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, ss, U.wg_slabs, U.wg_max_splits, &U.wg_active))) return rc;
   }
   if ((rc = close_bucket(0))) return rc;
   // encoder, deepest level first

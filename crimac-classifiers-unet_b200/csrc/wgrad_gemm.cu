@@ -153,14 +153,16 @@ __global__ void __launch_bounds__(256, 1) wgrad_gemm_kernel(const __grid_constan
       const int m = m_tile * 128 + q * 32 + lane;
       ptx::mbar_wait(acc_bar, 0);
       ptx::tc_fence_after();
-      float* row = p.dw + (static_cast<long>(tap) * p.M_total + m) * p.N_total + n_tile * BLOCK_N;
+      const bool direct = (p.splits == 1) || (p.slabs != nullptr);   // plain stores: sole writer of this element
+      float* row = (p.slabs ? p.slabs + split * p.slab_stride : p.dw) +
+                   (static_cast<long>(tap) * p.M_total + m) * p.N_total + n_tile * BLOCK_N;
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         uint32_t v[32];
         ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, v);
         ptx::tmem_ld_wait();
         if (m < p.M_total) {
-          if (p.splits == 1) {
+          if (direct) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(row + chunk * 32 + j) =
@@ -352,14 +354,16 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
       for (int g = 0; g < G; ++g) {
         const int tap = (NF == 64) ? (half ? PB5[g] : PA5[g]) : (half ? PB4[g] : PA4[g]);
         const bool live = !(NF == 64 && g == 4 && half == 0);  // lower half of the fifth group repeats tap 1
-        float* row = p.dw + (static_cast<long>(tap) * p.Cs + co) * p.Cf + f_tile * NF;
+        const bool direct = (p.splits == 1) || (p.slabs != nullptr);
+        float* row = (p.slabs ? p.slabs + split * p.slab_stride : p.dw) + (static_cast<long>(tap) * p.Cs + co) * p.Cf +
+                     f_tile * NF;
 #pragma unroll 1
         for (int chunk = 0; chunk < NF / 32; ++chunk) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * NF + chunk * 32, v);
           ptx::tmem_ld_wait();
           if (live) {
-            if (p.splits == 1) {
+            if (direct) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(row + chunk * 32 + j) =
@@ -403,14 +407,29 @@ __global__ void __launch_bounds__(256) wgrad_unpack_all_kernel(const __grid_cons
       // order each load behind the previous tap's store to the same array
       float* src = L.scratch + i0 + threadIdx.x;
       float g[9];
+      if (L.slabs != nullptr) {
+        // deterministic mode: the split-K partial tiles were stored, not added: sum them here in split order
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) g[tp] = (tp < L.taps) ? __ldcs(src + tp * L.mn) : 0.f;
+        for (int tp = 0; tp < 9; ++tp) g[tp] = 0.f;
+        for (int sp = 0; sp < L.splits; ++sp) {
+          const float* q = L.slabs + sp * L.slab_stride + i0 + threadIdx.x;
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp)
-        if (tp < L.taps) {
-          src[tp * L.mn] = 0.f;
-          s[threadIdx.x * L.taps + tp] = g[tp];
+          for (int tp = 0; tp < 9; ++tp)
+            if (tp < L.taps) g[tp] += __ldcs(q + tp * L.mn);
         }
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+          if (tp < L.taps) s[threadIdx.x * L.taps + tp] = g[tp];
+      } else {
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) g[tp] = (tp < L.taps) ? __ldcs(src + tp * L.mn) : 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+          if (tp < L.taps) {
+            src[tp * L.mn] = 0.f;
+            s[threadIdx.x * L.taps + tp] = g[tp];
+          }
+      }
     }
     __syncthreads();
     float* dst = L.dw + i0 * L.taps;

@@ -19,6 +19,7 @@ class _Config(ctypes.Structure):
         ("height", ctypes.c_int),
         ("width", ctypes.c_int),
         ("train", ctypes.c_int),
+        ("deterministic", ctypes.c_int),
     ]
 
 
@@ -63,10 +64,10 @@ def peer_allreduce(comm, bucket, offset, count, stream=None):
     )
 
 
-def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, height, width, train):
+def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, height, width, train, deterministic=False):
     """Size of the device workspace a context of this shape needs (pure host computation)."""
     L = _lib.load()
-    cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train))
+    cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train), int(deterministic))
     n = ctypes.c_size_t(0)
     _lib.check(L.crimac_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)), "crimac_workspace_bytes")
     return n.value
@@ -75,9 +76,11 @@ def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, heigh
 class Context:
     """One native context: fixed (max_batch, H, W), inference-only or train-capable."""
 
-    def __init__(self, in_channels, n_classes, depth, start_filts, max_batch, height, width, train, device):
+    def __init__(self, in_channels, n_classes, depth, start_filts, max_batch, height, width, train, device,
+                 deterministic=False):
         self.L = _lib.load()
-        self.cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train))
+        self.cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train),
+                           int(bool(deterministic) and bool(train)))
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CrimacError("the CRIMAC U-Net hot path runs on a CUDA (sm_100a) device only; there is no CPU fallback")
@@ -183,7 +186,7 @@ def forward_infer_fp32(cfg_tuple, state_tensors, x, softmax):
     """fp32 validation forward (independent CUDA-core implementation). cfg_tuple = (in_ch, n_classes, depth, start_filts)."""
     L = _lib.load()
     nb, _, h, w = x.shape
-    cfg = _Config(cfg_tuple[0], cfg_tuple[1], cfg_tuple[2], cfg_tuple[3], nb, h, w, 0)
+    cfg = _Config(cfg_tuple[0], cfg_tuple[1], cfg_tuple[2], cfg_tuple[3], nb, h, w, 0, 0)
     n = ctypes.c_size_t(0)
     _lib.check(L.crimac_fp32_workspace_bytes(ctypes.byref(cfg), nb, ctypes.byref(n)), "crimac_fp32_workspace_bytes")
     ws = torch.empty(n.value, dtype=torch.uint8, device=x.device)

@@ -300,11 +300,15 @@ class _NativePlumbing:
 
     def _engine_for_shape(self, nb, h, w, device, train):
         rt = _runtime()
-        key = (h, w, bool(train), device)
+        # the reference's fix_seeds (utils/general.py:120-128) sets torch.backends.cudnn.deterministic: honour the same
+        # switches - weight gradients are then reduced in a fixed order and a train step is bit-reproducible
+        det = bool(train) and (torch.backends.cudnn.deterministic or torch.are_deterministic_algorithms_enabled())
+        key = (h, w, bool(train), device, det)
         engines = _ENGINES.setdefault(self, {})
         eng = engines.get(key)
         if eng is None or eng.cfg.max_batch < nb:
-            eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, device)
+            eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, device,
+                             deterministic=det)
             engines[key] = eng
             comm = getattr(self, "_native_comm", None)
             if train and comm is not None:

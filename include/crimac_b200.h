@@ -53,6 +53,9 @@ typedef struct crimac_config {
   int max_batch;     /* largest batch a call may pass                                                 */
   int height, width; /* patch size, multiples of 2^(depth-1) (the reference's own constraint)          */
   int train;         /* 1: allocate saved activations + gradient scratch for forward_train/backward   */
+  int deterministic; /* 1 (train): split-K weight gradients are summed in a FIXED order (per-split slabs,     */
+                     /* ~0.9 GB more workspace) instead of red.global.add: bit-reproducible steps, the        */
+                     /* equivalent of the reference's torch.backends.cudnn.deterministic (utils/general.py)   */
 } crimac_config;
 
 const char* crimac_last_error(void);

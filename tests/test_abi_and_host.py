@@ -43,6 +43,8 @@ def test_workspace_and_argument_validation(pkg):
     train = E.workspace_bytes(4, 3, 5, 64, 32, 256, 256, 1)
     infer = E.workspace_bytes(4, 3, 5, 64, 32, 256, 256, 0)
     assert 4e9 < train < 9e9 and infer < train / 2
+    det = E.workspace_bytes(4, 3, 5, 64, 32, 256, 256, 1, deterministic=True)
+    assert 0.5e9 < det - train < 1.5e9          # per-split slabs of the fixed-order weight-gradient reduction
     with pytest.raises(L.CrimacError, match="start_filts"):
         E.workspace_bytes(4, 3, 5, 32, 1, 256, 256, 0)
     with pytest.raises(L.CrimacError, match="multiples"):
@@ -50,7 +52,7 @@ def test_workspace_and_argument_validation(pkg):
     with pytest.raises(L.CrimacError, match="in_channels"):
         E.workspace_bytes(9, 3, 5, 64, 1, 256, 256, 0)
     lib = L.load()
-    cfg = E._Config(4, 3, 5, 64, 1, 256, 256, 1)
+    cfg = E._Config(4, 3, 5, 64, 1, 256, 256, 1, 0)
     assert lib.crimac_state_count(ctypes.byref(cfg)) == 136
     assert lib.crimac_grad_count(ctypes.byref(cfg)) == 82
 
