@@ -580,8 +580,10 @@ def run_b200(args):
             "dtype": "bf16 (fp32 accumulate; first conv, BN statistics, head, loss in fp32)", "data": "synthetic",
             "config": {"workload": (WORKLOAD if standard and B == 32 else "UNet training fwd+bwd, batch %d of %dx%dx%d per GPU" % (B, C, S, S)) if args.mode == "train" else "UNet inference, batch %d of %dx%dx%d" % (B, C, S, S),
                        "global_batch": world * B, "parallelism": f"dp{world}" if world > 1 else "single GPU",
+                       "gradient_exchange": (getattr(trainer, "exchange", None) if args.mode == "train" and world > 1 else None),
+                       "exchange_multicast": (bool(getattr(getattr(trainer, "peer", None), "multicast", False)) if args.mode == "train" and world > 1 else None),
                        "launch": ("CUDA graph replay of one captured step" if getattr(trainer, "_graph", None) is not None else "eager stream launches") if args.mode == "train" else "eager stream launches",
-                       "step": "weight re-pack + forward + weighted CE + backward" + (" + NCCL all-reduce of the 124 MB gradient arena" if world > 1 else "") + " + fused SGD-momentum update" if args.mode == "train" else "forward + softmax",
+                       "step": "weight re-pack + forward + weighted CE + backward" + ((" + peer-memory all-reduce of the 124 MB gradient arena (own NVLink P2P / multimem kernels, 3 buckets launched inside backward)" if getattr(trainer, "exchange", None) == "peer" else " + NCCL all-reduce of the 124 MB gradient arena") if world > 1 else "") + " + fused SGD-momentum update" if args.mode == "train" else "forward + softmax",
                        "l2": "per-step working set (activations + gradients) is ~6 GB >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e, "api": "Trainer.fit_host: per step pinned host -> device copy of x (fp32) and labels (int64) on a copy stream (double-buffered, overlapping the previous step), UNet_Baseline.train_step_fused, gradient all-reduce, SGD, loss.item()" if args.mode == "train" else "predict.predict_host_batches: per batch pinned host -> device copy of x, UNet_Baseline.predict_proba, fp16 class-1/2 probabilities back to pinned host memory; copies double-buffered on copy streams"},

@@ -633,7 +633,13 @@ extern "C" int crimac_create(crimac_ctx** out, const crimac_config* cfg, void* w
                             &c->ev_bk_main[0], &c->ev_bk_main[1], &c->ev_bk_main[2], &c->ev_bk_side[0], &c->ev_bk_side[1],
                             &c->ev_bk_side[2], &c->ev_comm})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+      // the exchange kernels are tiny and latency-critical: highest priority, so that their CTAs take the first SM slots
+      // that free up next to the resident backward kernels
+      int lo_p = 0, hi_p = 0;
+      cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+      e = cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi_p);
+    }
     if (e != cudaSuccess) {
       crimac_set_error(std::string("side stream / event creation failed: ") + cudaGetErrorString(e));
       rc = 2;

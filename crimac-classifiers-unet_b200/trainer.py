@@ -63,7 +63,7 @@ def reduce_gradients(flat_grads, world):
 
 class Trainer:
     def __init__(self, model, lr=0.005, momentum=0.95, lr_reduction=0.5, lr_step=1000, class_weight=(10.0, 300.0, 250.0),
-                 use_cuda_graph=None, exchange=None):
+                 use_cuda_graph=None, exchange=None, exchange_ctas=0):
         # defaults: reference configs/config_baseline.yaml:28-31,38 and pipeline.py:135
         self.model = model
         self.lr, self.momentum = float(lr), float(momentum)
@@ -99,7 +99,7 @@ class Trainer:
         if self.world > 1:
             self.exchange = exchange if exchange is not None else ("peer" if dev.type == "cuda" else "nccl")
             if self.exchange == "peer":
-                self.peer = PeerGradientExchange(total, dev)
+                self.peer = PeerGradientExchange(total, dev, ctas=exchange_ctas)
                 model._grad_arena = self.peer.arena[:total]       # train_step_fused seats every p.grad in here
                 model._set_native_comm(self.peer.comm)
             self.broadcast_parameters(0)   # DDP semantics: every replica starts from rank 0's weights and buffers

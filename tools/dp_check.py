@@ -89,9 +89,41 @@ def main():
         return t.item()
 
     if os.environ.get("DP_TIMING", "1") != "0":
+        import crimac_unet_b200.engine as E
         xb, yb = S.synthetic_echogram(32, 4, 256, 256, seed=1 + rank, device=dev), S.synthetic_labels(32, 256, 256, seed=9 + rank, device=dev)
         out["ms_per_step_peer"] = bench(tr, xb, yb)
-        del tr, twin
+        # the exchange on its own: whole arena in one bucket (no overlap), vs ncclAllReduce of the same buffer
+        def t_op(fn, k=10):
+            for _ in range(3):
+                fn()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / k], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        n_pad = tr.peer.arena.numel()
+        out["ms_peer_allreduce_alone"] = t_op(lambda: E.peer_allreduce(tr.peer.comm, 7, 0, n_pad))
+        buf = torch.zeros(n_pad, device=dev)
+        out["ms_nccl_allreduce_alone"] = t_op(lambda: dist.all_reduce(buf))
+        for ctas in (16, 148):
+            torch.manual_seed(0)
+            mc = M.UNet_Baseline(3, 4).to(dev).train()
+            trc = Trainer(mc, lr=0.005, momentum=0.95, exchange_ctas=ctas)
+            out[f"ms_per_step_peer_ctas{ctas}"] = bench(trc, xb, yb)
+            trc._graph = None
+            del trc, mc
+        torch.manual_seed(0)
+        m1 = M.UNet_Baseline(3, 4).to(dev).train()
+        tr1 = Trainer(m1, lr=0.005, momentum=0.95, exchange="none")
+        out["ms_per_step_no_exchange"] = bench(tr1, xb, yb)
+        tr1._graph = None
+        del tr, twin, tr1, m1
         torch.manual_seed(0)
         m2 = M.UNet_Baseline(3, 4).to(dev).train()
         tr2 = Trainer(m2, lr=0.005, momentum=0.95, exchange="nccl")
