@@ -46,6 +46,7 @@ struct ConvParams {
   int out_pitch;         // elements per output pixel
   int relu;
   int convt_cout;        // >0: convT scatter, N index = (ky*2+kx)*convt_cout + co, output is 2H x 2W
+  int convt_add;         // convT scatter ADDS to what the destination holds (merge_mode "add": the skip activation)
   const float* scale;    // [N_total]
   const float* shift;    // [N_total]
   bf16* pool_out;        // optional (EPI_STORE): 2x2 max-pooled copy, H/2 x W/2

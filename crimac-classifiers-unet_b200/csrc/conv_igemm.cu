@@ -500,6 +500,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
             const int kk = ng / p.convt_cout, co = ng - kk * p.convt_cout;
             const long opix = (static_cast<long>(img) * (2 * p.H) + (2 * y + (kk >> 1))) * (2 * p.W) + (2 * x + (kk & 1));
             dst = p.out + opix * p.out_pitch + co;
+            if (EPI == EPI_STORE && p.convt_add) {
+              // merge_mode "add" (unet.py:131-134): the destination already holds the encoder's skip activation; the
+              // up-sampled value is added in fp32 and the sum rounded once
+              const uint4* d4 = reinterpret_cast<const uint4*>(dst);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 o = d4[i];
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  const float2 t = unpack_bf16x2(ow[w]);
+                  pk[4 * i + w] = pack_bf16x2(f[8 * i + 2 * w] + t.x, f[8 * i + 2 * w + 1] + t.y);
+                }
+              }
+            }
           } else {
             const long opix = (static_cast<long>(img) * p.H + y) * p.W + x;
             dst = p.out + opix * p.out_pitch + ng;
@@ -674,7 +689,7 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num
   // the epilogue writes 32-byte (256-bit) vectors
   if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 31) || p.out_pitch % 16)) return cudaErrorInvalidValue;
   if (p.pool_out && ((reinterpret_cast<uintptr_t>(p.pool_out) & 31) || p.pool_pitch % 16)) return cudaErrorInvalidValue;
-  if (p.b_mn && (epi != EPI_STORE || (p.taps != 9 && p.taps != 4))) return cudaErrorInvalidValue;
+  if (p.b_mn && (epi != EPI_STORE || (p.taps != 9 && p.taps != 4 && p.taps != 1))) return cudaErrorInvalidValue;
   if (p.b_mn && p.taps == 9 && !p.halo) return cudaErrorInvalidValue;  // 3x3 MN-major weights: halo main loop only
 #define CASE(BN, EP)                                                               \
   if (block_n == BN && epi == EP && !p.b_mn)                                       \

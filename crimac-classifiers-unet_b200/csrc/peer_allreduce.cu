@@ -90,7 +90,7 @@ __device__ __forceinline__ void wait_all(uint32_t* pad, int bucket, int phase, i
 }
 
 template <bool MC>
-__global__ void __launch_bounds__(AR_THREADS) peer_allreduce_kernel(const __grid_constant__ ArParams p) {
+__global__ void __launch_bounds__(AR_THREADS, 8) peer_allreduce_kernel(const __grid_constant__ ArParams p) {
   uint32_t* my_pad = p.pads[p.rank];
   const uint32_t epoch = p.state[p.bucket * 2] + 1;  // every CTA reads it before the last CTA advances it (see the end)
   // 1. ready flags (CTA 0).  The gradients were produced by earlier kernels in stream order: globally visible already.
@@ -114,23 +114,43 @@ __global__ void __launch_bounds__(AR_THREADS) peer_allreduce_kernel(const __grid
         if (i0 + u * stride < hi) mc_st(mc + i0 + u * stride, v[u]);
     }
   } else {
-    for (long i = lo + blockIdx.x * static_cast<long>(AR_THREADS) + threadIdx.x; i < hi; i += stride) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 v[AR_MAX_WORLD];
+    // NVLink latency (~2 us) bounds a thread with one load in flight: each thread keeps U vectors x G peers = 8 loads
+    // (128 bytes) in flight - 128 CTAs x 128 threads = 2 MB per rank - and walks the peers in FIXED rank order (the owner
+    // of a slice is the only one that sums it, so every replica receives the same bits)
+    constexpr int U = 4, G = 2;
+    for (long i0 = lo + blockIdx.x * static_cast<long>(AR_THREADS) + threadIdx.x; i0 < hi; i0 += U * stride) {
+      float4 acc[U];
 #pragma unroll
-      for (int r = 0; r < AR_MAX_WORLD; ++r)
-        if (r < p.world) v[r] = ld_peer(reinterpret_cast<const float4*>(p.peers[r]) + i);
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < AR_MAX_WORLD; ++r)  // fixed order: every replica receives the same bits
-        if (r < p.world) {
-          acc.x += v[r].x;
-          acc.y += v[r].y;
-          acc.z += v[r].z;
-          acc.w += v[r].w;
+      for (int r0 = 0; r0 < AR_MAX_WORLD; r0 += G) {
+        if (r0 < p.world) {
+          float4 v[G][U];
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              v[g][u] = (r0 + g < p.world && i0 + u * stride < hi)
+                            ? ld_peer(reinterpret_cast<const float4*>(p.peers[r0 + g]) + i0 + u * stride)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              acc[u].x += v[g][u].x;
+              acc[u].y += v[g][u].y;
+              acc[u].z += v[g][u].z;
+              acc[u].w += v[g][u].w;
+            }
         }
+      }
 #pragma unroll
       for (int r = 0; r < AR_MAX_WORLD; ++r)
-        if (r < p.world) st_peer(reinterpret_cast<float4*>(p.peers[r]) + i, acc);
+        if (r < p.world) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < hi) st_peer(reinterpret_cast<float4*>(p.peers[r]) + i0 + u * stride, acc[u]);
+        }
     }
   }
   // 4. done flags: my stores must be visible system-wide before any peer sees the flag
@@ -180,7 +200,7 @@ extern "C" int crimac_peer_allreduce(float* const* peer_arenas, void* const* pee
   p.bucket = bucket;
   p.off4 = static_cast<long>(offset / 4);
   p.count4 = static_cast<long>(count / 4);
-  if (ctas <= 0) ctas = 64;
+  if (ctas <= 0) ctas = 128;
   const long per = (p.count4 + world - 1) / world;
   const long want = (per + AR_THREADS - 1) / AR_THREADS;
   if (ctas > want) ctas = static_cast<int>(want < 1 ? 1 : want);

@@ -127,7 +127,7 @@ typedef struct crimac_comm_config {
   float* multicast_arena;         /* NVSwitch multicast address of the arena, or NULL (peer loads / stores)       */
   void* local_state;              /* private device scratch, 8 * CRIMAC_AR_MAX_BUCKETS bytes, zeroed              */
   size_t arena_floats;            /* arena size in floats, multiple of 4 (pad the 31 044 227 parameters up)       */
-  int ctas;                       /* CTAs of the exchange kernel (<= 0: default 64)                               */
+  int ctas;                       /* CTAs of the exchange kernel (<= 0: default 128)                              */
 } crimac_comm_config;
 /* Switch the bucketed, backward-overlapped gradient all-reduce of crimac_backward / crimac_train_step on (cfg != NULL)
  * or off (NULL); see csrc/net_api.cu.  The gradient pointers of those calls must then be views of peer_arenas[rank]. */
