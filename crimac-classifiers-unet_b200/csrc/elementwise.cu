@@ -973,6 +973,81 @@ __global__ void __launch_bounds__(256) pool_bwd_add_kernel(const uint16_t* __res
   }
 }
 
+// ============================================================================ bilinear 2x up-sampling (up_mode "upsample")
+// nn.Upsample(mode="bilinear", scale_factor=2) = F.interpolate(align_corners=False) (reference unet.py:50-56): output row
+// Y reads source rows (Y>>1) - 1 + (Y&1) and that + 1, clamped to the image, with weights 0.25 / 0.75 (even Y) resp.
+// 0.75 / 0.25 (odd Y); the same along pings.  One thread = one output pixel x 8 channels.
+__global__ void __launch_bounds__(256) upsample2x_kernel(View in, View out) {
+  const int groups = in.C >> 3;
+  const int Ho = in.H * 2, Wo = in.W * 2;
+  const long total = static_cast<long>(in.N) * Ho * Wo * groups;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long pix = i / groups;
+    const int X = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int Y = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    const int y0 = max((Y >> 1) - 1 + (Y & 1), 0), y1 = min((Y >> 1) + (Y & 1), in.H - 1);
+    const int x0 = max((X >> 1) - 1 + (X & 1), 0), x1 = min((X >> 1) + (X & 1), in.W - 1);
+    const float wy0 = (Y & 1) ? 0.75f : 0.25f, wx0 = (X & 1) ? 0.75f : 0.25f;
+    float a[8], b[8], c[8], d[8], o[8];
+    const long base = static_cast<long>(n) * in.H;
+    load8(in.ptr + ((base + y0) * in.W + x0) * in.pitch + g * 8, a);
+    load8(in.ptr + ((base + y0) * in.W + x1) * in.pitch + g * 8, b);
+    load8(in.ptr + ((base + y1) * in.W + x0) * in.pitch + g * 8, c);
+    load8(in.ptr + ((base + y1) * in.W + x1) * in.pitch + g * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = wy0 * (wx0 * a[j] + (1.f - wx0) * b[j]) + (1.f - wy0) * (wx0 * c[j] + (1.f - wx0) * d[j]);
+    store8(out.ptr + ((static_cast<long>(n) * Ho + Y) * Wo + X) * out.pitch + g * 8, o);
+  }
+}
+// Adjoint of the above: source pixel (y, x) collects dOut of the up to 4 x 4 output pixels that read it.
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(View dout, View din) {
+  const int groups = din.C >> 3;
+  const int Ho = din.H * 2, Wo = din.W * 2;
+  const long total = static_cast<long>(din.N) * din.H * din.W * groups;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    long pix = i / groups;
+    const int x = static_cast<int>(pix % din.W);
+    pix /= din.W;
+    const int y = static_cast<int>(pix % din.H);
+    const int n = static_cast<int>(pix / din.H);
+    // weights of output rows 2y-1 .. 2y+2 on source row y (edge rows also take the clamped neighbour's share)
+    float wy[4] = {y >= 1 ? 0.25f : 0.f, y == 0 ? 1.f : 0.75f, y == din.H - 1 ? 1.f : 0.75f, y <= din.H - 2 ? 0.25f : 0.f};
+    float wx[4] = {x >= 1 ? 0.25f : 0.f, x == 0 ? 1.f : 0.75f, x == din.W - 1 ? 1.f : 0.75f, x <= din.W - 2 ? 0.25f : 0.f};
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+      const int Y = 2 * y - 1 + dy;
+      if (wy[dy] == 0.f) continue;
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const int X = 2 * x - 1 + dx;
+        if (wx[dx] == 0.f) continue;
+        float v[8];
+        load8(dout.ptr + ((static_cast<long>(n) * Ho + Y) * Wo + X) * dout.pitch + g * 8, v);
+        const float w = wy[dy] * wx[dx];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(w, v[j], acc[j]);
+      }
+    }
+    store8(din.ptr + ((static_cast<long>(n) * din.H + y) * din.W + x) * din.pitch + g * 8, acc);
+  }
+}
+
+// (Cout,Cin,1,1) fp32 -> [Cout][Cin] bf16 (the 1x1 conv of up_mode "upsample": a plain cast, K contiguous already)
+__global__ void __launch_bounds__(256) pack_cast_kernel(const float* __restrict__ w, bf16* __restrict__ out, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16(w[i]);
+}
+
 // ============================================================================ first conv weight gradient
 // dW[co][ci][tap] = sum_p dRaw[p][co] * x[p + tap][ci]   (fp32 NCHW input, Cin = #frequencies, K = 9*Cin <= 72)
 // Register-tiled: a thread owns 4 output channels x KPT taps (36-72 accumulators) for one quarter of the tile's
@@ -1283,6 +1358,22 @@ cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumula
 cudaError_t launch_pool_bwd_add(const uint16_t* pool_arg, View dpool, View dskip, View dact, cudaStream_t st) {
   const long items = static_cast<long>(dact.N) * (dact.H / 2) * (dact.W / 2) * (dact.C / 8);
   pool_bwd_add_kernel<<<grid_for(items, 256), 256, 0, st>>>(pool_arg, dpool, dskip, dact);
+  return cudaGetLastError();
+}
+cudaError_t launch_upsample2x(View in, View out, cudaStream_t st) {
+  if (in.C % 8 != 0 || out.C != in.C || out.H != 2 * in.H || out.W != 2 * in.W) return cudaErrorInvalidValue;
+  const long items = static_cast<long>(in.N) * out.H * out.W * (in.C / 8);
+  upsample2x_kernel<<<grid_for(items, 256), 256, 0, st>>>(in, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_upsample2x_bwd(View dout, View din, cudaStream_t st) {
+  if (din.C % 8 != 0 || dout.C != din.C || dout.H != 2 * din.H || dout.W != 2 * din.W) return cudaErrorInvalidValue;
+  const long items = static_cast<long>(din.N) * din.H * din.W * (din.C / 8);
+  upsample2x_bwd_kernel<<<grid_for(items, 256), 256, 0, st>>>(dout, din);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_cast(const float* w, bf16* out, long n, cudaStream_t st) {
+  pack_cast_kernel<<<grid_for(n, 256), 256, 0, st>>>(w, out, n);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_conv3x3_all(PackTable& t, cudaStream_t st) {

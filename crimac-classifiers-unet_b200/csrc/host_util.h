@@ -126,6 +126,11 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
                           float* partials, float* c1c2, const float* gscale, cudaStream_t st);
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st);
 cudaError_t launch_pool_bwd_add(const uint16_t* pool_arg, View dpool, View dskip, View dact, cudaStream_t st);
+// up_mode "upsample" (unet.py:50-56): bilinear 2x (align_corners=False) forward / adjoint on NHWC bf16 views, and the
+// plain bf16 cast that packs a (Cout,Cin,1,1) weight
+cudaError_t launch_upsample2x(View in, View out, cudaStream_t st);
+cudaError_t launch_upsample2x_bwd(View dout, View din, cudaStream_t st);
+cudaError_t launch_pack_cast(const float* w, bf16* out, long n, cudaStream_t st);
 // fp32 parameters -> bf16 GEMM operands for every layer of one kind in ONE launch (item0 is filled by the launcher)
 struct PackEntry {
   const float* w;

@@ -61,6 +61,7 @@ struct ConvT {
   int cin = 0, cout = 0, level_in = 0;
   int s_w = 0, s_b = 0, g_w = 0, g_b = 0;
   View in{}, out{}, gout{}, gin{};
+  View tmp{}, dtmp{};     // up_mode "upsample": 1x1-conv output at the LOW resolution (before the bilinear 2x) and its gradient
   bf16* w_fwd = nullptr;  // backward-data reads the same matrix as an MN-major operand
   int bn_fwd = 0, bn_bwd = 0, bn_wg = 0;
   ConvParams fwd{}, dgrad{};
@@ -125,6 +126,8 @@ int validate(const crimac_config* cfg) {
   CRIMAC_REQUIRE(cfg->depth >= 2 && cfg->depth <= 5, "depth must be 2..5");
   CRIMAC_REQUIRE(cfg->start_filts == 64, "start_filts must be 64 (tensor-core tiles are 64 channels wide)");
   CRIMAC_REQUIRE(cfg->max_batch >= 1, "max_batch");
+  CRIMAC_REQUIRE((cfg->up_mode == 0 || cfg->up_mode == 1) && (cfg->merge_mode == 0 || cfg->merge_mode == 1), "up_mode / merge_mode must be 0 or 1");
+  CRIMAC_REQUIRE(!(cfg->up_mode == 1 && cfg->merge_mode == 1), "up_mode upsample is incompatible with merge_mode add (as in the reference, unet.py:243-251)");
   const int m = 1 << (cfg->depth - 1);
   CRIMAC_REQUIRE(cfg->height > 0 && cfg->width > 0 && cfg->height % m == 0 && cfg->width % m == 0,
                  "height/width must be multiples of 2^(depth-1) (the reference has the same constraint, unet.py:132)");
@@ -137,6 +140,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   const int D = c->D = cfg.depth;
   const int B = cfg.max_batch;
   const bool train = cfg.train != 0;
+  const bool add = cfg.merge_mode == 1;    // merge_mode "add": from_up + from_down instead of torch.cat (unet.py:131-134)
+  const bool ups = cfg.up_mode == 1;       // up_mode "upsample": bilinear 2x + conv1x1 instead of ConvTranspose2d (unet.py:50-56)
   Bump bump(ws);
   auto chan = [&](int l) { return cfg.start_filts << l; };
   auto dense = [&](int l, int C) {
@@ -153,7 +158,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
 
   // ---- activations
   std::vector<View> cat(D - 1), pooled(D - 1);
-  for (int j = 0; j < D - 1; ++j) cat[j] = dense(D - 2 - j, 2 * chan(D - 2 - j));
+  for (int j = 0; j < D - 1; ++j) cat[j] = dense(D - 2 - j, (add ? 1 : 2) * chan(D - 2 - j));
   for (int l = 0; l < D - 1; ++l) pooled[l] = dense(l + 1, chan(l));
 
   c->conv.clear();
@@ -205,7 +210,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     U.g_w = g_idx++;
     U.g_b = g_idx++;
     c->up.push_back(U);
-    const int i1 = new_conv(2 * co, co, l);
+    const int i1 = new_conv(add ? co : 2 * co, co, l);
     const int i2 = new_conv(co, co, l);
     c->dec1.push_back(i1);
     c->dec2.push_back(i2);
@@ -244,7 +249,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     L1.act = dense(l, chan(l));
     L2.in = L1.act;
     if (l < D - 1) {
-      L2.act = slice(cat[D - 2 - l], chan(l), chan(l));
+      L2.act = slice(cat[D - 2 - l], add ? 0 : chan(l), chan(l));   // "add": the up-sampled tensor is added in place later
       L2.pool = pooled[l];
     } else {
       L2.act = dense(l, chan(l));
@@ -255,6 +260,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     ConvT& U = c->up[j];
     U.in = (j == 0) ? c->conv[c->enc2[D - 1]].act : c->conv[c->dec2[j - 1]].act;
     U.out = slice(cat[j], 0, chan(l));
+    if (ups) U.tmp = dense(l + 1, chan(l));
     Conv3& L1 = c->conv[c->dec1[j]];
     Conv3& L2 = c->conv[c->dec2[j]];
     L1.in = cat[j];
@@ -282,8 +288,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     L.bn_wg = pick_bn(L.cin);
   }
   for (ConvT& U : c->up) {
-    U.w_fwd = bump.arr<bf16>(static_cast<size_t>(U.cin) * U.cout * 4);
-    U.bn_fwd = pick_bn(4 * U.cout);
+    U.w_fwd = bump.arr<bf16>(static_cast<size_t>(U.cin) * U.cout * (ups ? 1 : 4));
+    U.bn_fwd = pick_bn(ups ? U.cout : 4 * U.cout);
     U.bn_bwd = pick_bn(U.cin);
     U.bn_wg = pick_bn(U.cout);
   }
@@ -310,7 +316,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     c->GP = bump.arr<bf16>(lvl0 / 4);
     for (int j = 0; j < D - 1; ++j) {
       const int l = D - 2 - j;
-      c->dcat[j] = bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * 2 * chan(l));
+      c->dcat[j] = bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * (add ? 1 : 2) * chan(l));
+      if (ups) c->up[j].dtmp = dense(l + 1, chan(l));
     }
     const int cmax = chan(D - 1);
     c->stats = bump.arr<float>(max_stats);
@@ -322,7 +329,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       size_t total = 0;
       for (Conv3& L : c->conv)
         if (!L.first) total += static_cast<size_t>(9) * L.cout * L.cin;
-      for (ConvT& U : c->up) total += static_cast<size_t>(4) * U.cin * U.cout;
+      for (ConvT& U : c->up) total += static_cast<size_t>(ups ? 1 : 4) * U.cin * U.cout;
       c->wg_arena = bump.arr<float>(total);
       c->wg_arena_bytes = total * sizeof(float);
       float* q = c->wg_arena;
@@ -333,7 +340,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         }
       for (ConvT& U : c->up) {
         U.wg_scratch = q;
-        if (q) q += static_cast<size_t>(4) * U.cin * U.cout;
+        if (q) q += static_cast<size_t>(ups ? 1 : 4) * U.cin * U.cout;
       }
     }
     if (cfg.deterministic) {
@@ -346,9 +353,10 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
           L.wg_slabs = bump.arr<float>(static_cast<size_t>(L.wg_max_splits) * 9 * L.cout * L.cin);
         }
       for (ConvT& U : c->up) {
-        const int tiles = 4 * ((U.cin + 127) / 128) * (U.cout / pick_bn(U.cout));
+        const int tiles = ups ? ((U.cout + 127) / 128) * (U.cin / pick_bn(U.cin))
+                              : 4 * ((U.cin + 127) / 128) * (U.cout / pick_bn(U.cout));
         U.wg_max_splits = std::max(1, (2 * 148) / tiles);
-        U.wg_slabs = bump.arr<float>(static_cast<size_t>(U.wg_max_splits) * 4 * U.cin * U.cout);
+        U.wg_slabs = bump.arr<float>(static_cast<size_t>(U.wg_max_splits) * (ups ? 1 : 4) * U.cin * U.cout);
       }
     }
     c->head_partials = bump.arr<float>(static_cast<size_t>(head_bwd_blocks()) * 4 * (cfg.n_classes * 64 + cfg.n_classes));
@@ -372,7 +380,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       L1.gin = View{c->dcat[j], B, level_h(c, l), level_w(c, l), L1.cin, L1.cin};
       L2.gin = View{c->GA, B, level_h(c, l), level_w(c, l), L2.cin, L2.cin};
       ConvT& U = c->up[j];
-      U.gout = View{c->dcat[j], B, level_h(c, l), level_w(c, l), U.cout, 2 * U.cout};
+      U.gout = View{c->dcat[j], B, level_h(c, l), level_w(c, l), U.cout, (add ? 1 : 2) * U.cout};
       U.gin = View{c->GA, B, level_h(c, l + 1), level_w(c, l + 1), U.cin, U.cin};
     }
   } else {
@@ -462,12 +470,40 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     p.taps = 1;
     p.tap_mode = 0;
     p.cin = U.cin;
+    if (ups) {
+      // conv1x1 and bilinear up-sampling commute (both linear, the interpolation weights sum to 1): the 1x1 conv runs as
+      // a one-tap GEMM at the LOW resolution (a quarter of the pixels), the bilinear 2x follows as an HBM-bound kernel
+      geom(p, H, W, U.cout, U.bn_fwd);
+      if ((rc = make_act_map(&p.a_map[0], U.in, TILE_H))) return rc;
+      if ((rc = make_weight_map(&p.b_map, U.w_fwd, U.cout, U.cin, U.bn_fwd))) return rc;
+      p.out = U.tmp.ptr;
+      p.out_pitch = U.tmp.pitch;
+      if (train) {
+        ConvParams& d = U.dgrad;
+        d.taps = 1;
+        d.tap_mode = 0;
+        d.cin = U.cout;
+        geom(d, H, W, U.cin, U.bn_bwd);
+        if ((rc = make_act_map(&d.a_map[0], U.dtmp, TILE_H))) return rc;
+        d.b_mn = 1;
+        if ((rc = make_weight_map(&d.b_map, U.w_fwd, U.cout, U.cin, 64))) return rc;
+        d.out = U.gin.ptr;
+        d.out_pitch = U.gin.pitch;
+        WgradParams& w = U.wg;   // dW[co][ci] = sum_p dTmp[p][co] * X[p][ci]
+        wgeom(w, H, W, U.cout, U.cin, pick_bn(U.cin), 1, 0);
+        w.dw = U.wg_scratch;
+        if ((rc = make_act_map(&w.a_map, U.dtmp, 4))) return rc;
+        if ((rc = make_act_map(&w.b_map[0], U.in, 4))) return rc;
+      }
+      continue;
+    }
     geom(p, H, W, 4 * U.cout, U.bn_fwd);
     if ((rc = make_act_map(&p.a_map[0], U.in, TILE_H))) return rc;
     if ((rc = make_weight_map(&p.b_map, U.w_fwd, 4 * U.cout, U.cin, U.bn_fwd))) return rc;
     p.out = U.out.ptr;
     p.out_pitch = U.out.pitch;
     p.convt_cout = U.cout;
+    p.convt_add = add ? 1 : 0;
     if (train) {
       ConvParams& d = U.dgrad;
       d.taps = 4;
@@ -677,9 +713,14 @@ extern "C" int crimac_prepare(crimac_ctx* c, const void* const* state, int train
     PackTable t3{}, tt{};
     for (Conv3& L : c->conv)
       if (!L.first) t3.e[t3.n++] = PackEntry{S<float>(state, L.s_w), L.w_fwd, L.cout, L.cin, 0};
-    for (ConvT& U : c->up) tt.e[tt.n++] = PackEntry{S<float>(state, U.s_w), U.w_fwd, U.cout, U.cin, 0};
     CRIMAC_CHECK_CUDA(launch_pack_conv3x3_all(t3, st));
-    CRIMAC_CHECK_CUDA(launch_pack_convt_all(tt, st));
+    if (c->cfg.up_mode == 1) {
+      for (ConvT& U : c->up)   // (Cout,Cin,1,1): K contiguous already
+        CRIMAC_CHECK_CUDA(launch_pack_cast(S<float>(state, U.s_w), U.w_fwd, static_cast<long>(U.cout) * U.cin, st));
+    } else {
+      for (ConvT& U : c->up) tt.e[tt.n++] = PackEntry{S<float>(state, U.s_w), U.w_fwd, U.cout, U.cin, 0};
+      CRIMAC_CHECK_CUDA(launch_pack_convt_all(tt, st));
+    }
   }
   if (!train)
     for (Conv3& L : c->conv)
@@ -782,7 +823,14 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
     p.scale = nullptr;
     p.shift = S<float>(state, U.s_b);
     p.relu = 0;
-    {
+    if (c->cfg.up_mode == 1) {
+      {
+        ProfScope ps("up1x1_fwd", igemm_flops_n(p, U.cout), 2.0 * nb * p.H * p.W * (U.cin + U.cout), st);
+        CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_fwd, EPI_STORE, sms, st));
+      }
+      ProfScope ps("upsample2x", 0, 2.0 * nb * p.H * p.W * U.cout * 5.0, st);
+      CRIMAC_CHECK_CUDA(launch_upsample2x(with_batch(U.tmp, nb), with_batch(U.out, nb), st));
+    } else {
       ProfScope ps("convT_fwd", igemm_flops_n(p, 4 * U.cout), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
       CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_fwd, EPI_STORE, sms, st));
     }
@@ -927,11 +975,12 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
         add3(c->conv[c->dec1[j]]);
         add3(c->conv[c->dec2[j]]);
         const ConvT& U = c->up[j];
-        UnpackEntry e{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, 4, 0};
+        const int utaps = c->cfg.up_mode == 1 ? 1 : 4;
+        UnpackEntry e{U.wg_scratch, grads[U.g_w], static_cast<long>(U.cin) * U.cout, utaps, 0};
         if (U.wg_slabs) {
           e.slabs = U.wg_slabs;
           e.splits = U.wg_active;
-          e.slab_stride = 4L * U.cin * U.cout;
+          e.slab_stride = static_cast<long>(utaps) * U.cin * U.cout;
         }
         t.e[t.n++] = e;
       }
@@ -985,8 +1034,15 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     if ((rc = conv_bwd(c->dec2[j]))) return rc;   // dgrad -> dA of dec1[j]
     if ((rc = conv_bwd(c->dec1[j]))) return rc;   // dgrad wrote dCat_j
     ConvT& U = c->up[j];
-    // everything that only READS dCat_j and is off the critical path goes to the side stream: the ConvTranspose bias
-    // gradient (HBM-bound column sum, own partial buffer) and its weight gradient; the main stream continues with the
+    const bool ups = c->cfg.up_mode == 1;
+    if (ups) {
+      // adjoint of the bilinear 2x: dCat_j[:, :C] (full resolution) -> dTmp (low resolution); the 1x1 conv's backward
+      // then reads dTmp
+      ProfScope ps("upsample2x_bwd", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout * 1.25, st);
+      CRIMAC_CHECK_CUDA(launch_upsample2x_bwd(with_batch(U.gout, nb), with_batch(U.dtmp, nb), st));
+    }
+    // everything that only READS dCat_j (dTmp) and is off the critical path goes to the side stream: the bias gradient
+    // (HBM-bound column sum, own partial buffer) and the weight gradient; the main stream continues with the
     // backward-data GEMM
     cudaStream_t ss = c->overlap ? c->side : st;
     if (c->overlap) {
@@ -994,8 +1050,9 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->side, c->ev_cat, 0));
     }
     {
-      ProfScope ps("convT_bias_grad", 0, 2.0 * nb * U.gout.H * U.gout.W * U.cout, ss, 2);
-      CRIMAC_CHECK_CUDA(launch_view_colsum(with_batch(U.gout, nb), c->colsum_partials, grads[U.g_b], 0, ss));
+      const View gsrc = with_batch(ups ? U.dtmp : U.gout, nb);
+      ProfScope ps("convT_bias_grad", 0, 2.0 * nb * gsrc.H * gsrc.W * U.cout, ss, 2);
+      CRIMAC_CHECK_CUDA(launch_view_colsum(gsrc, c->colsum_partials, grads[U.g_b], 0, ss));
     }
     {
       ConvParams p = U.dgrad;
@@ -1003,7 +1060,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("convT_dgrad", igemm_flops_n(p, U.cin), 2.0 * nb * p.H * p.W * (U.cin + 4.0 * U.cout), st);
       CRIMAC_CHECK_CUDA(launch_conv_igemm(p, U.bn_bwd, EPI_STORE, sms, st));
     }
-    if ((rc = wgrad_run(c, U.wg, U.bn_wg, nb, ss, U.wg_slabs, U.wg_max_splits, &U.wg_active))) return rc;
+    if ((rc = wgrad_run(c, U.wg, ups ? pick_bn(U.cin) : U.bn_wg, nb, ss, U.wg_slabs, U.wg_max_splits, &U.wg_active))) return rc;
   }
   if ((rc = close_bucket(0))) return rc;
   // encoder, deepest level first
@@ -1012,7 +1069,8 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     if (l < D - 1) {
       const int j = D - 2 - l;
       View dpool{c->GP, nb, level_h(c, l + 1), level_w(c, l + 1), L2.cout, L2.cout};
-      View dskip{c->dcat[j] + L2.cout, nb, level_h(c, l), level_w(c, l), L2.cout, 2 * L2.cout};
+      const bool add = c->cfg.merge_mode == 1;   // "add": the skip branch receives the merged tensor's gradient as it is
+      View dskip{c->dcat[j] + (add ? 0 : L2.cout), nb, level_h(c, l), level_w(c, l), L2.cout, (add ? 1 : 2) * L2.cout};
       View dact{c->GA, nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
       ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 2.28, st);
       CRIMAC_CHECK_CUDA(launch_pool_bwd_add(L2.pool_arg, dpool, dskip, dact, st));

@@ -327,3 +327,14 @@ extern "C" int crimac_op_wgrad_unpack_all(int n, float* const* scratch, float* c
   CRIMAC_CHECK_CUDA(launch_wgrad_unpack_all(t, static_cast<cudaStream_t>(stream)));
   return 0;
 }
+
+// Bilinear 2x up-sampling of up_mode "upsample" (unet.py:50-56; align_corners=False) on NHWC bf16 views.  backward == 0:
+// lo (N,H,W,C) -> hi (N,2H,2W,C); backward != 0: the adjoint, hi = gradient at full resolution -> lo.
+extern "C" int crimac_op_upsample2x(void* lo, int lo_pitch, void* hi, int hi_pitch, int N, int H, int W, int C,
+                                    int backward, void* stream) {
+  CRIMAC_REQUIRE(lo && hi && C % 8 == 0 && lo_pitch % 8 == 0 && hi_pitch % 8 == 0, "bad argument");
+  View vl = mk_view(lo, N, H, W, C, lo_pitch), vh = mk_view(hi, N, 2 * H, 2 * W, C, hi_pitch);
+  CRIMAC_CHECK_CUDA(backward ? launch_upsample2x_bwd(vh, vl, static_cast<cudaStream_t>(stream))
+                             : launch_upsample2x(vl, vh, static_cast<cudaStream_t>(stream)));
+  return 0;
+}

@@ -20,6 +20,8 @@ class _Config(ctypes.Structure):
         ("width", ctypes.c_int),
         ("train", ctypes.c_int),
         ("deterministic", ctypes.c_int),
+        ("up_mode", ctypes.c_int),       # 0 "transpose", 1 "upsample"
+        ("merge_mode", ctypes.c_int),    # 0 "concat", 1 "add"
     ]
 
 
@@ -64,10 +66,16 @@ def peer_allreduce(comm, bucket, offset, count, stream=None):
     )
 
 
-def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, height, width, train, deterministic=False):
+_UP_MODES = {"transpose": 0, "upsample": 1}
+_MERGE_MODES = {"concat": 0, "add": 1}
+
+
+def workspace_bytes(in_channels, n_classes, depth, start_filts, max_batch, height, width, train, deterministic=False,
+                    up_mode="transpose", merge_mode="concat"):
     """Size of the device workspace a context of this shape needs (pure host computation)."""
     L = _lib.load()
-    cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train), int(deterministic))
+    cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train), int(deterministic),
+                  _UP_MODES[up_mode], _MERGE_MODES[merge_mode])
     n = ctypes.c_size_t(0)
     _lib.check(L.crimac_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)), "crimac_workspace_bytes")
     return n.value
@@ -77,10 +85,10 @@ class Context:
     """One native context: fixed (max_batch, H, W), inference-only or train-capable."""
 
     def __init__(self, in_channels, n_classes, depth, start_filts, max_batch, height, width, train, device,
-                 deterministic=False):
+                 deterministic=False, up_mode="transpose", merge_mode="concat"):
         self.L = _lib.load()
         self.cfg = _Config(in_channels, n_classes, depth, start_filts, max_batch, height, width, int(train),
-                           int(bool(deterministic) and bool(train)))
+                           int(bool(deterministic) and bool(train)), _UP_MODES[up_mode], _MERGE_MODES[merge_mode])
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CrimacError("the CRIMAC U-Net hot path runs on a CUDA (sm_100a) device only; there is no CPU fallback")
@@ -186,7 +194,7 @@ def forward_infer_fp32(cfg_tuple, state_tensors, x, softmax):
     """fp32 validation forward (independent CUDA-core implementation). cfg_tuple = (in_ch, n_classes, depth, start_filts)."""
     L = _lib.load()
     nb, _, h, w = x.shape
-    cfg = _Config(cfg_tuple[0], cfg_tuple[1], cfg_tuple[2], cfg_tuple[3], nb, h, w, 0, 0)
+    cfg = _Config(cfg_tuple[0], cfg_tuple[1], cfg_tuple[2], cfg_tuple[3], nb, h, w, 0, 0, 0, 0)
     n = ctypes.c_size_t(0)
     _lib.check(L.crimac_fp32_workspace_bytes(ctypes.byref(cfg), nb, ctypes.byref(n)), "crimac_fp32_workspace_bytes")
     ws = torch.empty(n.value, dtype=torch.uint8, device=x.device)

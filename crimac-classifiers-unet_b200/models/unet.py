@@ -239,8 +239,6 @@ class _NativePlumbing:
 
     def _check_supported(self, x):
         problems = []
-        if self.up_mode != "transpose" or self.merge_mode != "concat":
-            problems.append("only up_mode='transpose' with merge_mode='concat' is implemented natively")
         if self.start_filts != 64 or not (2 <= self.depth <= 5):
             problems.append("start_filts must be 64 and depth in 2..5")
         if not (1 <= self.in_channels <= 8) or not (1 <= self.n_classes <= 8):
@@ -282,7 +280,8 @@ class _NativePlumbing:
             c1, b1, _, c2, b2, _ = d.main
             out += [c1.weight, c1.bias] + bn(b1) + [c2.weight, c2.bias] + bn(b2)
         for u in self.up_convs:
-            out += [u.upconv.weight, u.upconv.bias, u.conv1.weight, u.conv1.bias, u.conv2.weight, u.conv2.bias]
+            up = u.upconv if self.up_mode == "transpose" else u.upconv[1]    # "upsample": Sequential(Upsample, conv1x1)
+            out += [up.weight, up.bias, u.conv1.weight, u.conv1.bias, u.conv2.weight, u.conv2.bias]
             out += bn(u.bn1) + bn(u.bn2)
         return out
 
@@ -308,7 +307,7 @@ class _NativePlumbing:
         eng = engines.get(key)
         if eng is None or eng.cfg.max_batch < nb:
             eng = rt.Context(self.in_channels, self.n_classes, self.depth, self.start_filts, nb, h, w, train, device,
-                             deterministic=det)
+                             deterministic=det, up_mode=self.up_mode, merge_mode=self.merge_mode)
             engines[key] = eng
             comm = getattr(self, "_native_comm", None)
             if train and comm is not None:
@@ -424,6 +423,9 @@ class UNet_Baseline(_NativePlumbing, UNet):
         tensor cores) - logits, or probabilities with softmax=True.  For 1e-4 parity checks, ~50x slower."""
         if self.training:
             raise RuntimeError("forward_fp32() is an eval-mode call; use model.eval() first")
+        if self.up_mode != "transpose" or self.merge_mode != "concat":
+            raise RuntimeError("the fp32 validation mode covers up_mode='transpose' with merge_mode='concat' (the only "
+                               "configuration the reference pipeline builds, pipeline.py:390-410)")
         x = self._prep_input(x)
         rt = _runtime()
         return rt.forward_infer_fp32((self.in_channels, self.n_classes, self.depth, self.start_filts),

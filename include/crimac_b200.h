@@ -56,6 +56,10 @@ typedef struct crimac_config {
   int deterministic; /* 1 (train): split-K weight gradients are summed in a FIXED order (per-split slabs,     */
                      /* ~0.9 GB more workspace) instead of red.global.add: bit-reproducible steps, the        */
                      /* equivalent of the reference's torch.backends.cudnn.deterministic (utils/general.py)   */
+  int up_mode;       /* 0: "transpose" (ConvTranspose2d k2 s2), 1: "upsample" (bilinear 2x + conv1x1)         */
+                     /*    (unet.py:47-56; the state table then holds upconv.1.{weight (Cout,Cin,1,1),bias})   */
+  int merge_mode;    /* 0: "concat" (torch.cat((up, skip), 1)), 1: "add" (up + skip; conv1 takes C channels)   */
+                     /*    (unet.py:113-118,131-134); up_mode 1 with merge_mode 1 is rejected as in the ctor   */
 } crimac_config;
 
 const char* crimac_last_error(void);
@@ -218,6 +222,8 @@ int crimac_op_head_bwd(const float* dlogits, const float* gscale, const void* ac
                        const float* hw, int ncls, void* dact, int dact_pitch, float* dw, float* db, void* scratch,
                        void* stream);
 int crimac_op_colsum(const void* v, int pitch, int N, int H, int W, int C, float* out, void* scratch, void* stream);
+int crimac_op_upsample2x(void* lo, int lo_pitch, void* hi, int hi_pitch, int N, int H, int W, int C, int backward,
+                         void* stream);
 int crimac_op_pack(int kind, const float* w, int cout, int cin, void* out, void* stream);
 int crimac_op_wgrad_unpack_all(int n, float* const* scratch, float* const* dw, const int64_t* mn, const int* taps,
                                void* stream);

@@ -69,9 +69,11 @@ def _qw(w, quant):
     return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach() if quant else w
 
 
-def unet_forward(state, x, train=False, new_stats=None, quant=False):
+def unet_forward(state, x, train=False, new_stats=None, quant=False, up_mode="transpose", merge_mode="concat"):
     """UNet_Baseline.forward (models/unet.py:327-343): encoder blocks DownConv.forward (:88-93), decoder blocks
     UpConv.forward (:124-137, concat order = upsampled first), 1x1 head (:342). Returns raw logits.
+    up_mode "upsample" = nn.Upsample(bilinear, x2) then conv1x1 (:50-56, state keys upconv.1.*); merge_mode "add" =
+    from_up + from_down (:133-134).
 
     quant=True is the MIXED-PRECISION EMULATION of the product's storage format (not the reference): every tensor the
     sm_100a path keeps in HBM as bf16 (conv outputs before BN in train mode, activations, ConvTranspose outputs,
@@ -96,8 +98,15 @@ def unet_forward(state, x, train=False, new_stats=None, quant=False):
             x = F.max_pool2d(x, 2, 2)                                                 # :86,92
     for j in range(depth - 1):
         p = f"up_convs.{j}."
-        up = F.conv_transpose2d(x, _qw(state[p + "upconv.weight"], quant), state[p + "upconv.bias"], stride=2)  # :47-49,130
-        x = torch.cat((_q(up, quant), skips[-(j + 2)]), 1)                            # :132, :336
+        if up_mode == "transpose":
+            up = F.conv_transpose2d(x, _qw(state[p + "upconv.weight"], quant), state[p + "upconv.bias"], stride=2)  # :47-49,130
+        else:
+            up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)                             # :53
+            up = F.conv2d(up, _qw(state[p + "upconv.1.weight"], quant), state[p + "upconv.1.bias"])                 # :54
+        if merge_mode == "concat":
+            x = torch.cat((_q(up, quant), skips[-(j + 2)]), 1)                        # :132, :336
+        else:
+            x = _q(up + skips[-(j + 2)], quant)                                       # :134
         x = block(x, p + "conv1.weight", p + "conv1.bias", p + "bn1")
         x = block(x, p + "conv2.weight", p + "conv2.bias", p + "bn2")
     return F.conv2d(x, state["conv_final.weight"], state["conv_final.bias"])          # conv1x1, :59-60,342
@@ -121,13 +130,13 @@ def weighted_ce(logits, labels, class_weights=CLASS_WEIGHTS, ignore_index=IGNORE
     return (wy * nll).sum() / wy.sum()
 
 
-def train_step(state, x, labels, class_weights=CLASS_WEIGHTS, quant=False):
+def train_step(state, x, labels, class_weights=CLASS_WEIGHTS, quant=False, up_mode="transpose", merge_mode="concat"):
     """pipeline.py:167-177: model.train(); outputs = model(x); loss = criterion(outputs, labels); loss.backward().
     Returns (logits, loss, grads by parameter name, updated BN buffers)."""
     names = [k for k, v in state.items() if v.dtype.is_floating_point and "running_" not in k]
     leaf = {k: (v.detach().clone().requires_grad_(True) if k in names else v) for k, v in state.items()}
     new_stats = {}
-    logits = unet_forward(leaf, x, train=True, new_stats=new_stats, quant=quant)
+    logits = unet_forward(leaf, x, train=True, new_stats=new_stats, quant=quant, up_mode=up_mode, merge_mode=merge_mode)
     loss = weighted_ce(logits, labels, class_weights)
     grads = torch.autograd.grad(loss, [leaf[k] for k in names])
     return logits.detach(), loss.detach(), dict(zip(names, grads)), new_stats

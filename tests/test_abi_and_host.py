@@ -52,7 +52,7 @@ def test_workspace_and_argument_validation(pkg):
     with pytest.raises(L.CrimacError, match="in_channels"):
         E.workspace_bytes(9, 3, 5, 64, 1, 256, 256, 0)
     lib = L.load()
-    cfg = E._Config(4, 3, 5, 64, 1, 256, 256, 1, 0)
+    cfg = E._Config(4, 3, 5, 64, 1, 256, 256, 1, 0, 0, 0)
     assert lib.crimac_state_count(ctypes.byref(cfg)) == 136
     assert lib.crimac_grad_count(ctypes.byref(cfg)) == 82
 

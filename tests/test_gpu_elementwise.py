@@ -339,3 +339,24 @@ def test_validation_loss_label_remap_and_sandeel_probability(env):
         assert torch.equal(lab_out, ref_lab)
         assert abs(out3[0].item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
         assert (prob - ref_prob).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 24, 64), (1, 1, 1, 8), (1, 5, 2, 128)])
+def test_bilinear_upsample_forward_and_adjoint(env, N, H, W, C):
+    """up_mode "upsample" (reference unet.py:50-56): nn.Upsample(mode="bilinear", scale_factor=2), align_corners=False."""
+    L, lib, dev, _ = env
+    torch.manual_seed(H * W + C)
+    cat = torch.zeros(N, 2 * H, 2 * W, 2 * C, device=dev, dtype=torch.bfloat16)        # written through a concat view
+    lo = torch.randn(N, H, W, C, device=dev).bfloat16()
+    L.check(lib.crimac_op_upsample2x(L.ptr(lo), C, L.ptr(cat), 2 * C, N, H, W, C, 0, L.stream_ptr()), "upsample2x")
+    torch.cuda.synchronize()
+    x = _nchw(lo).clone().requires_grad_(True)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    _close_bf16(_nchw(cat[..., :C]), ref.detach(), "upsample")
+    assert torch.all(cat[..., C:] == 0)
+    g = torch.randn(N, 2 * H, 2 * W, 2 * C, device=dev).bfloat16()
+    dlo = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
+    L.check(lib.crimac_op_upsample2x(L.ptr(dlo), C, L.ptr(g), 2 * C, N, H, W, C, 1, L.stream_ptr()), "upsample2x bwd")
+    torch.cuda.synchronize()
+    ref.backward(_nchw(g[..., :C]))
+    _close_bf16(_nchw(dlo), x.grad, "upsample adjoint")

@@ -401,8 +401,15 @@ def _teacher_forced_gradients(m, eng, E, x, y, nb):
             t = F.max_pool2d(t, 2, 2)
     for j in range(D - 1):
         p = f"up_convs.{j}."
-        up = F.conv_transpose2d(t, O._qw(leaf[p + "upconv.weight"], True), leaf[p + "upconv.bias"], stride=2)
-        t = torch.cat((tf(up, E.saved_tensor(eng, j, 3, nb)), skips[-(j + 2)]), 1)
+        if m.up_mode == "transpose":
+            up = F.conv_transpose2d(t, O._qw(leaf[p + "upconv.weight"], True), leaf[p + "upconv.bias"], stride=2)
+        else:   # the native path applies the 1x1 conv BEFORE the bilinear 2x (the two commute): same graph order here
+            low = F.conv2d(t, O._qw(leaf[p + "upconv.1.weight"], True), leaf[p + "upconv.1.bias"])
+            up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=False)
+        if m.merge_mode == "concat":
+            t = torch.cat((tf(up, E.saved_tensor(eng, j, 3, nb)), skips[-(j + 2)]), 1)
+        else:   # "add": the native buffer holds up + skip (rounded once)
+            t = tf(up + skips[-(j + 2)], E.saved_tensor(eng, j, 3, nb))
         t = block(t, p + "conv1.weight", p + "conv1.bias", p + "bn1", 2 * D + 2 * j)
         t = block(t, p + "conv2.weight", p + "conv2.bias", p + "bn2", 2 * D + 2 * j + 1)
     logits = F.conv2d(t, leaf["conv_final.weight"], leaf["conv_final.bias"])
@@ -682,6 +689,55 @@ def test_config4_shapes_six_frequencies_512x512(M):
     for n, g in got_g.items():
         if not _pre_bn_bias(n):
             assert _cos(g, tf_g[n]) >= GRAD_COS and _rel(g, tf_g[n]) <= GRAD_REL, n
+
+
+@pytest.mark.parametrize("variant", ["add", "upsample"])
+def test_decoder_variants_against_reference_golden(M, golden_dir, variant):
+    """the two non-default decoders of UNet.__init__ (reference unet.py:200-251) on the
+    native path - merge_mode="add" (ConvTranspose epilogue adds into the skip activation in place) and
+    up_mode="upsample" (conv1x1 as a one-tap tensor-core GEMM at the low resolution, then a bilinear 2x kernel) -
+    against outputs of the reference classes themselves (oracle/make_golden_variants.py): eval logits, train loss,
+    BatchNorm buffers, a subset of gradients; and the backward pass at the native forward state for all tensors."""
+    E = importlib.import_module("crimac_unet_b200.engine")
+    kw = dict(up_mode="transpose", merge_mode="add") if variant == "add" else dict(up_mode="upsample", merge_mode="concat")
+    g = np.load(os.path.join(golden_dir, f"unet_{variant}_d3.npz"))
+    torch.manual_seed(7)
+    m = M.UNet_Baseline(3, 4, depth=3, **kw)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["state_keys"]]            # same state_dict schema as the reference
+    sd0 = O.trained_like_state({k: v.detach().clone() for k, v in m.state_dict().items()}, seed=1, head_gain=2.0)
+    chk = np.array([float(v.double().abs().sum()) for v in sd0.values()])
+    assert np.allclose(chk, g["state_checksum"], rtol=1e-6)
+    m.load_state_dict(sd0)
+    m = m.to(dev)
+    x, y = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+        pr = m.predict_proba(x)
+    ref_ev = torch.from_numpy(g["eval_logits"])
+    assert (ev.cpu() - ref_ev).abs().max().item() < 2e-2 * ref_ev.abs().max().item()
+    assert (pr.cpu() - torch.softmax(ref_ev, 1)).abs().max().item() <= PROB_TOL
+    m.train()
+    st0 = _state(m)
+    loss = m.train_step_fused(x, y, torch.tensor(O.CLASS_WEIGHTS, device=dev))
+    assert abs(loss.item() - float(g["loss"])) < 2e-3 * float(g["loss"])
+    named = dict(m.named_parameters())
+    for k in g.files:
+        if k.startswith("grad/conv_final"):
+            assert _rel(named[k[5:]].grad.cpu(), torch.from_numpy(g[k])) < 2e-2, k
+        elif k.startswith("grad/") and not _pre_bn_bias(k[5:]):
+            assert _cos(named[k[5:]].grad.cpu(), torch.from_numpy(g[k])) > 0.9, (k, _cos(named[k[5:]].grad.cpu(), torch.from_numpy(g[k])))
+        if k.startswith("stat/") and "num_batches" not in k:
+            assert _rel(m.state_dict()[k[5:]].cpu(), torch.from_numpy(g[k])) < 1e-2, k
+    got = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    eng = m._engine_for(x, train=True)
+    m.load_state_dict(st0)
+    tf_loss, tf_g = _teacher_forced_gradients(m, eng, E, x, y, x.shape[0])
+    worst = max((_rel(gg, tf_g[n]), n) for n, gg in got.items() if not _pre_bn_bias(n))
+    print(f"{variant}: eval max|dlogit| {(ev.cpu() - ref_ev).abs().max().item():.4f}; worst gradient rel-L2 at the native forward state {worst[0]:.4f} ({worst[1]})")
+    for n, gg in got.items():
+        if not _pre_bn_bias(n):
+            assert _cos(gg, tf_g[n]) >= GRAD_COS and _rel(gg, tf_g[n]) <= GRAD_REL, (n, _cos(gg, tf_g[n]), _rel(gg, tf_g[n]))
 
 
 def test_deterministic_mode_is_bit_reproducible(M):

@@ -110,3 +110,30 @@ def test_reference_grid_geometry_of_config4():
     grid = P.get_data_grid(0, 20000, 0, 256, (256, 256), 20)
     assert len(grid) == 186 and list(grid[0]) == [107, 107] and list(grid[1]) == [107, 323]
     assert sorted(set(grid[:, 0])) == [107, 323]
+
+
+@pytest.mark.parametrize("variant,kw", [("add", dict(up_mode="transpose", merge_mode="add")),
+                                        ("upsample", dict(up_mode="upsample", merge_mode="concat"))])
+def test_oracle_decoder_variants_against_reference_golden(golden_dir, variant, kw):
+    """oracle.unet_forward / train_step with up_mode / merge_mode against outputs of the reference's own classes
+    (oracle/make_golden_variants.py, models/unet.py:47-56,113-118,131-134)."""
+    import importlib
+    import __graft_entry__ as ge
+    ge.load_package()
+    Mm = importlib.import_module("crimac_unet_b200.models.unet")
+    g = np.load(os.path.join(golden_dir, f"unet_{variant}_d3.npz"))
+    torch.manual_seed(7)
+    m = Mm.UNet_Baseline(3, 4, depth=3, **kw)
+    sd0 = O.trained_like_state({k: v.detach().clone() for k, v in m.state_dict().items()}, seed=1, head_gain=2.0)
+    assert np.allclose(np.array([float(v.double().abs().sum()) for v in sd0.values()]), g["state_checksum"], rtol=1e-6)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    with torch.no_grad():
+        ev = O.unet_forward(sd0, x, **kw)
+    assert (ev - torch.from_numpy(g["eval_logits"])).abs().max().item() < 1e-4
+    tl, loss, grads, stats = O.train_step(sd0, x, y, **kw)
+    assert (tl - torch.from_numpy(g["train_logits"])).abs().max().item() < 1e-3
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    for k in g.files:
+        if k.startswith("grad/") and not (k.endswith(".bias") and any(t in k for t in ("main.0", "main.3", "conv1", "conv2"))):
+            a, b = grads[k[5:]], torch.from_numpy(g[k])
+            assert ((a - b).norm() / (b.norm() + 1e-30)).item() < 2e-2, k
