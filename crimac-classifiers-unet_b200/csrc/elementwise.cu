@@ -1177,8 +1177,9 @@ inline int grid_for(long work_items, int threads) {
 }  // namespace
 
 // ---------------------------------------------------------------------------- launchers (used by net_api.cu / ops_api2.cu)
-// The first conv runs on the tensor cores (first_conv_tc.cu) for up to 7 frequencies; the fp32 CUDA-core kernels below
-// remain for 8 frequencies and as the A/B reference (CRIMAC_FC_CUDACORE=1).
+// The first conv runs on the tensor cores (first_conv_tc.cu) for up to 8 input channels; the fp32 CUDA-core kernels
+// below serve 9..12 channels (4 frequencies + up to 7 metadata channels, pipeline.py:392,413-425) and remain the A/B
+// reference of the tensor-core path (CRIMAC_FC_CUDACORE=1).
 static bool first_conv_use_tc(int cin) {
   static const bool off = getenv("CRIMAC_FC_CUDACORE") != nullptr;
   return !off && cin <= 8;
@@ -1205,7 +1206,7 @@ cudaError_t launch_first_conv(const float* x, bf16* xs, const float* w, const fl
     first_conv_kernel<C><<<grid, 64, 0, st>>>(x, w, scale, shift, relu, NB, H, W, out, out_pitch, stats);       \
     return cudaGetLastError();                                                                                  \
   }
-  FC(1) FC(2) FC(3) FC(4) FC(5) FC(6) FC(7) FC(8)
+  FC(1) FC(2) FC(3) FC(4) FC(5) FC(6) FC(7) FC(8) FC(9) FC(10) FC(11) FC(12)
 #undef FC
   return cudaErrorInvalidValue;
 }
@@ -1222,7 +1223,7 @@ cudaError_t launch_first_conv_wgrad(const float* x, const bf16* xs, View draw, i
     partial_sum_finalize_kernel<1><<<(64 * C * 9 + 7) / 8, 256, 0, st>>>(partials, grid * 4, 64 * C * 9, 1.0, dw, nullptr, accumulate, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); \
     return cudaGetLastError();                                                                      \
   }
-  FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8)
+  FW(1) FW(2) FW(3) FW(4) FW(5) FW(6) FW(7) FW(8) FW(9) FW(10) FW(11) FW(12)
 #undef FW
   return cudaErrorInvalidValue;
 }

@@ -121,7 +121,7 @@ int level_w(const crimac_ctx* c, int l) { return c->cfg.width >> l; }
 
 int validate(const crimac_config* cfg) {
   CRIMAC_REQUIRE(cfg != nullptr, "cfg is NULL");
-  CRIMAC_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 8, "in_channels must be 1..8");
+  CRIMAC_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 12, "in_channels must be 1..12 (frequencies + metadata channels)");
   CRIMAC_REQUIRE(cfg->n_classes >= 1 && cfg->n_classes <= CRIMAC_MAX_CLASSES, "n_classes must be 1..8");
   CRIMAC_REQUIRE(cfg->depth >= 2 && cfg->depth <= 5, "depth must be 2..5");
   CRIMAC_REQUIRE(cfg->start_filts == 64, "start_filts must be 64 (tensor-core tiles are 64 channels wide)");

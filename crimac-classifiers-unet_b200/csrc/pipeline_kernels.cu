@@ -226,3 +226,66 @@ extern "C" int crimac_eval_loss(const float* logits, int nb, int n_classes, int 
                                      static_cast<double*>(scratch), out3, static_cast<cudaStream_t>(stream)));
   return 0;
 }
+
+// Metadata input channels of get_crop_memmap (batch/dataset.py:296-349; selected by data.meta_channels in the config,
+// pipeline.py:413-425), generated on the device straight into the network input tensor.  Channel order as the reference
+// appends them: portion_year, sin / cos of portion_day, time_diff, depth_rel, depth_abs_surface, depth_abs_seabed.
+// Index conventions are the reference's own (NOT the data crop's): rows cy - ph/2 .. cy + ph/2 - 1 (unclamped), pings
+// cx - pw/2 .. cx + pw/2 - 1 with negative -> 0 and >= size -> the LAST element; arithmetic in double, stored as fp32.
+namespace {
+__global__ void __launch_bounds__(256) meta_channels_kernel(const int* __restrict__ centres, int n, int ph, int pw,
+                                                            unsigned mask, double portion_year,
+                                                            const double* __restrict__ pod, int n_pod,
+                                                            const double* __restrict__ tvd, int n_tvd,
+                                                            const double* __restrict__ seabed, int n_sb,
+                                                            float* __restrict__ out, int c_total, int c_off) {
+  const long total = static_cast<long>(n) * ph * pw;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(i % pw);
+    const int py = static_cast<int>((i / pw) % ph);
+    const int b = static_cast<int>(i / (static_cast<long>(pw) * ph));
+    const int cy = centres[2 * b], cx = centres[2 * b + 1];
+    const long plane = static_cast<long>(ph) * pw;
+    float* o = out + (static_cast<long>(b) * c_total + c_off) * plane + static_cast<long>(py) * pw + px;
+    auto clampi = [](int idx, int size) { return idx < 0 ? 0 : (idx >= size ? size - 1 : idx); };
+    int ch = 0;
+    if (mask & 1u) o[(ch++) * plane] = static_cast<float>(portion_year);
+    if (mask & 2u) {
+      const double t = pod[clampi(cx, n_pod)];
+      o[(ch++) * plane] = static_cast<float>(sin(2.0 * 3.141592653589793 * t));
+      o[(ch++) * plane] = static_cast<float>(cos(2.0 * 3.141592653589793 * t));
+    }
+    const int col = cx - pw / 2 + px;
+    if (mask & 4u) o[(ch++) * plane] = static_cast<float>(tvd[clampi(col, n_tvd)]);
+    if (mask & 56u) {
+      const double row = static_cast<double>(cy - ph / 2 + py);
+      const double sb = seabed[clampi(col, n_sb)];
+      if (mask & 8u) o[(ch++) * plane] = static_cast<float>(row / sb);
+      if (mask & 16u) o[(ch++) * plane] = static_cast<float>(row / static_cast<double>(ph));
+      if (mask & 32u) o[(ch++) * plane] = static_cast<float>((sb - row) / static_cast<double>(ph));
+    }
+  }
+}
+}  // namespace
+
+extern "C" int crimac_meta_channels(const int32_t* centres, int n, int ph, int pw, unsigned mask, double portion_year,
+                                    const double* portion_of_day, int n_pod, const double* time_diff, int n_tvd,
+                                    const double* seabed, int n_sb, float* x_out, int c_total, int c_off, void* stream) {
+  CRIMAC_REQUIRE(centres && x_out && n >= 1 && ph >= 1 && pw >= 1, "bad argument");
+  CRIMAC_REQUIRE(mask != 0 && mask < 64, "mask selects 1..6 channel kinds");
+  CRIMAC_REQUIRE(!(mask & 2u) || (portion_of_day && n_pod >= 1), "portion_of_day vector missing");
+  CRIMAC_REQUIRE(!(mask & 4u) || (time_diff && n_tvd >= 1), "time_diff vector missing");
+  CRIMAC_REQUIRE(!(mask & 56u) || (seabed && n_sb >= 1), "seabed vector missing");
+  int m = 0;
+  for (unsigned bit : {1u, 4u, 8u, 16u, 32u}) m += (mask & bit) ? 1 : 0;
+  m += (mask & 2u) ? 2 : 0;
+  CRIMAC_REQUIRE(c_off >= 0 && c_off + m <= c_total, "channel offset + metadata channels exceed the tensor");
+  const long total = static_cast<long>(n) * ph * pw;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  meta_channels_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      centres, n, ph, pw, mask, portion_year, portion_of_day, n_pod, time_diff, n_tvd, seabed, n_sb, x_out, c_total, c_off);
+  CRIMAC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -268,6 +268,38 @@ def preprocess(sv, data_ping0, centres, patch_hw, out=None, nan_mask=None):
     return out, nan_mask
 
 
+META_BITS = {"portion_year": 1, "portion_day": 2, "time_diff": 4, "depth_rel": 8, "depth_abs_surface": 16,
+             "depth_abs_seabed": 32}
+
+
+def meta_channels(x, c_off, centres, meta_channels_cfg, portion_year=0.0, portion_of_day=None, time_diff=None,
+                  seabed=None, n_range=None):
+    """Writes the metadata input channels of the reference's get_crop_memmap (batch/dataset.py:296-349) into planes
+    [c_off, c_off + M) of the network input x (n, C, ph, pw) on the device.  meta_channels_cfg: the config's
+    data.meta_channels dict (truthy entries are generated, in the reference's order); the three vectors are float64
+    device tensors (portion_of_day_vector, time_vector_diff, _seabed).  n_range: the echogram's number of range bins - if
+    it is <= ph the reference re-centres every crop vertically (dataset.py:261-262) and so does this call.
+    Returns the number of channels written."""
+    L = _lib.load()
+    mask = sum(bit for k, bit in META_BITS.items() if meta_channels_cfg.get(k))
+    n, c_total, ph, pw = x.shape
+    if n_range is not None and n_range <= ph:
+        centres = centres.clone()
+        centres[:, 0] = n_range // 2
+    for t, name in ((portion_of_day, "portion_of_day"), (time_diff, "time_diff"), (seabed, "seabed")):
+        if t is not None and (t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous float64 CUDA tensor")
+    _lib.check(
+        L.crimac_meta_channels(_lib.ptr(centres.contiguous()), n, ph, pw, ctypes.c_uint(mask), ctypes.c_double(portion_year),
+                               _lib.ptr(portion_of_day), 0 if portion_of_day is None else portion_of_day.numel(),
+                               _lib.ptr(time_diff), 0 if time_diff is None else time_diff.numel(),
+                               _lib.ptr(seabed), 0 if seabed is None else seabed.numel(),
+                               _lib.ptr(x), c_total, int(c_off), _lib.stream_ptr()),
+        "crimac_meta_channels",
+    )
+    return sum(2 if k == "portion_day" else 1 for k in META_BITS if meta_channels_cfg.get(k))
+
+
 def stitch(probs, centres, nan_mask, out, ping_start, overlap, labels=None, seabed=None, seabed_pad=10, classes=(1, 2)):
     """probs: fp32 (n,ncls,ph,pw); out: fp16 (K,R,Pc) device tensor written in place."""
     L = _lib.load()

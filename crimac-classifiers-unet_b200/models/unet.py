@@ -241,8 +241,8 @@ class _NativePlumbing:
         problems = []
         if self.start_filts != 64 or not (2 <= self.depth <= 5):
             problems.append("start_filts must be 64 and depth in 2..5")
-        if not (1 <= self.in_channels <= 8) or not (1 <= self.n_classes <= 8):
-            problems.append("in_channels and n_classes must be in 1..8")
+        if not (1 <= self.in_channels <= 12) or not (1 <= self.n_classes <= 8):
+            problems.append("in_channels must be in 1..12 and n_classes in 1..8")
         if self.conv_final.in_channels != self._native_head_in + self._meta_head_channels():
             problems.append("the 1x1 head must take the 64 decoder channels (plus the late-injected metadata channels)")
         if self.conv_final.out_channels != self.n_classes:

@@ -14,6 +14,7 @@
  *   crimac_preprocess      batch/dataset.py:192-205 + utils/np.py:362-375 + batch/data_transforms/{remove_nan_inf,db_with_limits}.py
  *   crimac_train_patches   batch/dataset.py:75-108,358-407 (Dataset.__getitem__ / get_crop_zarr) + batch/data_augmentation/*.py +
  *                          batch/label_transforms/{refine_label_boundary,convert_label_indexing}.py + data transforms
+ *   crimac_meta_channels   batch/dataset.py:296-349 (metadata input channels of get_crop_memmap; pipeline.py:413-425)
  *   crimac_stitch          pipeline_train_predict/save_predict.py:41-65 (fill_out_array) + label masks of
  *                          batch/label_transforms/mask_label_{overlap,seabed}.py
  *   crimac_eval_loss       pipeline.py:222-239 (set_label_ignore_val) + :264 (validation loss) + :269-270 (softmax,
@@ -46,7 +47,7 @@ extern "C" {
 typedef struct crimac_ctx crimac_ctx;
 
 typedef struct crimac_config {
-  int in_channels;   /* frequencies, 1..8                                   (unet.py:200 in_channels) */
+  int in_channels;   /* frequencies + metadata channels, 1..12             (unet.py:200 in_channels) */
   int n_classes;     /* 1..8                                                (unet.py:200 n_classes)   */
   int depth;         /* encoder blocks, 2..5 (reference default 5)          (unet.py:206)             */
   int start_filts;   /* must be 64                                          (unet.py:207)             */
@@ -149,6 +150,14 @@ int crimac_preprocess(const float* sv_dev, int F, int R, int P, int data_ping0, 
  * never materialised.  Patch size = the context's (height, width); F = its in_channels; n <= max_batch. */
 int crimac_preprocess_staged(crimac_ctx* ctx, const float* sv_dev, int F, int R, int P, int data_ping0,
                              const int32_t* centres_dev, int n, uint8_t* nan_dev, void* stream);
+/* Metadata input channels (batch/dataset.py:296-349), written as fp32 planes [c_off, c_off + M) of the network input
+ * x_out (n, c_total, ph, pw).  mask bits: 1 portion_year (1 channel), 2 portion_day (2: sin, cos), 4 time_diff, 8
+ * depth_rel, 16 depth_abs_surface, 32 depth_abs_seabed - appended in that order, as the reference does.  centres_dev:
+ * int32 (n,2) (y, x); the three vectors are per-ping doubles of the echogram (portion_of_day_vector, time_vector_diff,
+ * _seabed); out-of-range pings read element 0 resp. the last one, rows are not clamped (the reference's conventions). */
+int crimac_meta_channels(const int32_t* centres_dev, int n, int ph, int pw, unsigned mask, double portion_year,
+                         const double* portion_of_day_dev, int n_pod, const double* time_diff_dev, int n_tvd,
+                         const double* seabed_dev, int n_sb, float* x_out_dev, int c_total, int c_off, void* stream);
 /* Overlap-stitch (fill_out_array): for every patch pixel whose label would not be one of {-70 overlap frame,
  * -50 below seabed+pad on background, -100 outside [ping_start, ping_start+Pc) x [0,R) or non-finite}, write
  * probs[:, cls[k]] as fp16 into out_dev (K, R, Pc).  labels_dev: optional int16 (R, Pc) chunk labels after the

@@ -255,3 +255,43 @@ def noise_multiplier_field(shape, rng):
     inc = rng.binomial(1, 0.5, shape)
     m = (1 - change) + change * (inc * rng.uniform(1, 10, shape) + (1 - inc) * rng.uniform(0, 1, shape))
     return m.astype(np.float32)
+
+
+# ---- metadata input channels: get_crop_memmap, batch/dataset.py:296-349 ----------------------
+META_ORDER = ("portion_year", "portion_day", "time_diff", "depth_rel", "depth_abs_surface", "depth_abs_seabed")
+
+
+def meta_channels(centre, window, n_range, meta_cfg, portion_year, portion_of_day, time_diff, seabed):
+    """The `meta` array of get_crop_memmap (dataset.py:296-349) for one crop: float64 (M, ph, pw), channels appended in
+    the reference's order (portion_year; sin, cos of portion_day; time_diff; depth_rel; depth_abs_surface;
+    depth_abs_seabed).  A crop of an echogram with n_range <= ph is re-centred vertically first (:261-262)."""
+    ph, pw = window
+    cy, cx = int(centre[0]), int(centre[1])
+    if n_range <= ph:
+        cy = n_range // 2
+
+    def clamp(idx, size):
+        idx = np.asarray(idx).copy()
+        idx[idx < 0] = 0
+        idx[idx >= size] = size - 1          # the reference writes -1 = the last element
+        return idx
+
+    out = []
+    if meta_cfg.get("portion_year"):
+        out.append(np.full((ph, pw), float(portion_year)))
+    if meta_cfg.get("portion_day"):
+        t = portion_of_day[int(clamp(np.array([cx]), portion_of_day.size)[0])]
+        out.append(np.full((ph, pw), np.sin(2 * np.pi * t)))
+        out.append(np.full((ph, pw), np.cos(2 * np.pi * t)))
+    cols = np.arange(cx - pw // 2, cx + pw // 2)
+    rows = np.arange(cy - ph // 2, cy + ph // 2)
+    if meta_cfg.get("time_diff"):
+        out.append(time_diff[clamp(cols, time_diff.size)].reshape(1, -1) * np.ones((ph, 1)))
+    sb = seabed[clamp(cols, seabed.size)].reshape(1, -1)
+    if meta_cfg.get("depth_rel"):
+        out.append(rows.reshape(-1, 1) / sb)
+    if meta_cfg.get("depth_abs_surface"):
+        out.append(rows.reshape(-1, 1) * np.ones((1, pw)) / ph)
+    if meta_cfg.get("depth_abs_seabed"):
+        out.append((sb - rows.reshape(-1, 1)) / ph)
+    return np.stack(out, 0)

@@ -50,7 +50,10 @@ def test_workspace_and_argument_validation(pkg):
     with pytest.raises(L.CrimacError, match="multiples"):
         E.workspace_bytes(4, 3, 5, 64, 1, 250, 256, 0)
     with pytest.raises(L.CrimacError, match="in_channels"):
-        E.workspace_bytes(9, 3, 5, 64, 1, 256, 256, 0)
+        E.workspace_bytes(13, 3, 5, 64, 1, 256, 256, 0)          # 4 frequencies + 7 metadata channels = 11 is the most the reference builds
+    with pytest.raises(L.CrimacError, match="incompatible"):
+        E.workspace_bytes(4, 3, 5, 64, 1, 256, 256, 0, up_mode="upsample", merge_mode="add")
+    assert E.workspace_bytes(4, 3, 5, 64, 8, 256, 256, 1, merge_mode="add") < E.workspace_bytes(4, 3, 5, 64, 8, 256, 256, 1)
     lib = L.load()
     cfg = E._Config(4, 3, 5, 64, 1, 256, 256, 1, 0, 0, 0)
     assert lib.crimac_state_count(ctypes.byref(cfg)) == 136

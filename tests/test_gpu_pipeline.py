@@ -191,3 +191,26 @@ def test_full_size_chunk_of_config3_against_the_oracle_pipeline(E, pkg):
     assert np.array_equal(written, ref_written)
     assert 0.7 < frac < 0.9                                            # rows below seabed + 10 and NaN pixels stay 0
     assert np.abs(got - ref).max() <= 2.5e-2
+
+
+def test_metadata_channels_kernel_against_reference_golden(E, golden_dir):
+    """crimac_meta_channels against the reference's get_crop_memmap `meta` arrays (batch/dataset.py:296-349; fixture
+    made by oracle/make_golden_meta.py), written straight into planes [F, F+M) of a network input tensor."""
+    from tests.test_oracle_golden import _meta_cases
+    g = np.load(os.path.join(golden_dir, "meta_channels.npz"))
+    worst = 0.0
+    for tag, ci, mtag, c, window, n_range, cfg, vec, ref in _meta_cases(g):
+        M_, F_ = ref.shape[0], 4
+        x = torch.full((2, F_ + M_, window[0], window[1]), 7.0, device=dev)
+        centres = torch.tensor([list(c), list(c)], dtype=torch.int32, device=dev)
+        wrote = E.meta_channels(x, F_, centres, cfg, portion_year=vec["portion_year"],
+                                portion_of_day=torch.from_numpy(vec["portion_of_day"]).to(dev),
+                                time_diff=torch.from_numpy(vec["time_diff"]).to(dev),
+                                seabed=torch.from_numpy(vec["seabed"]).to(dev), n_range=n_range)
+        assert wrote == M_
+        assert torch.all(x[:, :F_] == 7.0)                       # the frequency planes are not touched
+        want = torch.from_numpy(ref).float().to(dev)             # what the model sees: batch['data'].float()
+        assert torch.equal(x[0, F_:], x[1, F_:])
+        worst = max(worst, ((x[0, F_:] - want).abs() / want.abs().clamp_min(1.0)).max().item())
+    print(f"metadata channels: worst relative deviation {worst:.2e}")
+    assert worst <= 2e-7                                         # double arithmetic on both sides, one fp32 rounding

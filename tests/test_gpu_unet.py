@@ -769,11 +769,12 @@ def test_deterministic_mode_is_bit_reproducible(M):
     assert _rel(m._grad_arena, runs[0][1]) < 1e-4
 
 
-@pytest.mark.parametrize("in_ch", [1, 3, 8])
+@pytest.mark.parametrize("in_ch", [1, 3, 8, 11])
 def test_first_conv_channel_counts(M, in_ch):
-    """Edge frequency counts of the first layer (tensor-core path: one 16-byte chunk per tap up to 4 frequencies, two
-    chunks - and two weight-gradient accumulator groups - above): forward, loss and the first conv's weight gradient
-    against the fp32 oracle on a shallow net (the gradient passes through one bf16 layer only)."""
+    """Edge input-channel counts of the first layer (tensor-core path: one 16-byte chunk per tap up to 4 channels, two
+    chunks - and two weight-gradient accumulator groups - up to 8; fp32 CUDA-core kernels for 9..12 = 4 frequencies +
+    all 7 metadata channels, pipeline.py:392,413-425): forward, loss and the first conv's weight gradient against the
+    fp32 oracle on a shallow net (the gradient passes through one bf16 layer only)."""
     torch.manual_seed(in_ch)
     m = M.UNet_Baseline(3, in_ch, depth=2).to(dev).train()
     st0 = _state(m)
