@@ -758,10 +758,62 @@ __device__ __forceinline__ void block_channel_sums(const float (&acc)[NQ][8], in
   }
 }
 
+// Optional producer of dA for the encoder's second convs: dA = dSkip + unpool(dPool) (autograd of unet.py:86,92,132) is
+// not read from memory but formed on the fly from the concat gradient's skip half, the pooled gradient and the 2-bit
+// arg-max map - the separate pool_bwd_add pass (4.6 bytes per element, written and read back) disappears.
+struct PoolMerge {
+  const uint16_t* arg;  // nullptr: dA comes from `dact`
+  View dpool, dskip;
+};
+// incoming gradient of 8 channels of pixel p (linear index over N x H x W of the full-resolution tensor)
+template <bool PM>
+struct DactLoader {
+  uint4 a, b;
+  uint32_t sel;  // PM: window position of this pixel + the arg-max word
+  __device__ __forceinline__ void issue(const View& dact, const PoolMerge& pm, long p, int g, int groups, bool ok) {
+    if (!PM) {
+      a = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
+    } else {
+      a = b = make_uint4(0, 0, 0, 0);
+      sel = 0;
+      if (ok) {
+        const unsigned W = pm.dskip.W, H = pm.dskip.H;
+        const unsigned up = static_cast<unsigned>(p);
+        const unsigned x = up % W, t = up / W, y = t % H, n = t / H;
+        const long pp = (static_cast<long>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+        a = __ldcs(reinterpret_cast<const uint4*>(pm.dskip.ptr + p * pm.dskip.pitch + g * 8));
+        b = __ldg(reinterpret_cast<const uint4*>(pm.dpool.ptr + pp * pm.dpool.pitch + g * 8));
+        sel = (static_cast<uint32_t>(((y & 1) << 1) | (x & 1)) << 16) | __ldg(pm.arg + pp * groups + g);
+      }
+    }
+  }
+  __device__ __forceinline__ void get(float (&d)[8]) const {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 t = unpack_bf16x2(aw[h]);
+      d[2 * h] = t.x;
+      d[2 * h + 1] = t.y;
+    }
+    if (PM) {
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+      const uint32_t q = sel >> 16, arg = sel & 0xffffu;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 t = unpack_bf16x2(bw[h]);
+        d[2 * h] += (((arg >> (4 * h)) & 3u) == q) ? t.x : 0.f;
+        d[2 * h + 1] += (((arg >> (4 * h + 2)) & 3u) == q) ? t.y : 0.f;
+      }
+    }
+  }
+};
+
 // phase 1: g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * raw.  (sum g * xhat is derived from the two
 // by the finalize kernel: invstd * (sum g*raw - mean * sum g); the kernel then needs only two per-channel constants
 // in registers, which doubles its occupancy - it is bound by the bytes it keeps in flight.)
-__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, View raw, const float* __restrict__ scale,
+template <bool PM>
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, PoolMerge pm, View raw,
+                                                               const float* __restrict__ scale,
                                                                const float* __restrict__ shift, float* partials) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
@@ -775,22 +827,25 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, View r
   const long stride = static_cast<long>(gridDim.x) * ppb;
   constexpr int U = 4;  // pixels per iteration: 2*U independent 16-byte loads in flight per thread
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
-    uint4 dv[U], rv[U];
+    DactLoader<PM> dl[U];
+    uint4 rv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       const bool ok = p < npix;
-      dv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
+      dl[u].issue(dact, pm, p, g, groups, ok);
       rv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+      float d[8];
+      dl[u].get(d);
+      const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const float2 d = unpack_bf16x2(dw[h]), r = unpack_bf16x2(rw[h]);
-        const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d.x : 0.f;
-        const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d.y : 0.f;
+        const float2 r = unpack_bf16x2(rw[h]);
+        const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d[2 * h] : 0.f;
+        const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d[2 * h + 1] : 0.f;
         acc[0][2 * h] += g0;
         acc[0][2 * h + 1] += g1;
         acc[1][2 * h] = fmaf(g0, r.x, acc[1][2 * h]);
@@ -861,7 +916,8 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
 // phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) = A*g + B*raw + K per channel -> bf16.
 // (The conv-bias gradient sum(dRaw) is EXACTLY zero in exact arithmetic - train-mode BatchNorm removes any bias - and the
 // reference's value is pure cancellation noise ~1e-9; it is written as 0 by the finalize kernel instead of being summed.)
-__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View raw, const float* __restrict__ scale,
+template <bool PM>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, PoolMerge pm, View raw, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd,
@@ -890,25 +946,28 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View ra
   const long stride = static_cast<long>(gridDim.x) * ppb;
   constexpr int U = 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
-    uint4 dv[U], rv[U];
+    DactLoader<PM> dl[U];
+    uint4 rv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       const bool ok = p < npix;
-      dv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
+      dl[u].issue(dact, pm, p, g, groups, ok);
       rv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       if (p < npix) {
-        const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+        float d[8];
+        dl[u].get(d);
+        const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
         float o[8];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const float2 d = unpack_bf16x2(dw[h]), r = unpack_bf16x2(rw[h]);
-          const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d.x : 0.f;
-          const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d.y : 0.f;
+          const float2 r = unpack_bf16x2(rw[h]);
+          const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d[2 * h] : 0.f;
+          const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d[2 * h + 1] : 0.f;
           o[2 * h] = fmaf(ca[2 * h], g0, fmaf(cb[2 * h], r.x, ck[2 * h]));
           o[2 * h + 1] = fmaf(ca[2 * h + 1], g1, fmaf(cb[2 * h + 1], r.y, ck[2 * h + 1]));
         }
@@ -1331,7 +1390,8 @@ static int reduce_grid(const View& v) {
 // scratch: partials, at least reduce_blocks()*2*C floats; c1c2: 2*C floats.
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                          float* partials, float* c1c2, const float* gscale, cudaStream_t st) {
+                          float* partials, float* c1c2, const float* gscale, cudaStream_t st, const uint16_t* pool_arg,
+                          View dpool, View dskip) {
   const int C = raw.C;
   if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
   const int grid = reduce_grid(raw);
@@ -1339,11 +1399,24 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int grid_r = grid < 148 * 3 ? grid : 148 * 3;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
-  bn_bwd_reduce_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
+  PoolMerge pm{pool_arg, dpool, dskip};
+  if (pool_arg != nullptr) {
+    // dA = dSkip + unpool(dPool) formed on the fly (32-bit pixel index inside the loader)
+    if (count > 4.0e9 || dskip.C != C || dpool.C != C || (raw.H & 1) || (raw.W & 1)) return cudaErrorInvalidValue;
+    pm.dskip.N = raw.N;
+    pm.dskip.H = raw.H;
+    pm.dskip.W = raw.W;
+    bn_bwd_reduce_kernel<true><<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, pm, raw, scale, shift, partials);
+  } else {
+    bn_bwd_reduce_kernel<false><<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, pm, raw, scale, shift, partials);
+  }
   partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid_r, C, count, dbeta,
                                                                 dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd,
                                                                 dbias);
-  bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
+  if (pool_arg != nullptr)
+    bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dact, pm, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
+  else
+    bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dact, pm, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
   return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {

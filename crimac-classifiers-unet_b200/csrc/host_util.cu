@@ -45,8 +45,15 @@ int make_act_map(CUtensorMap* out, const View& v, int box_h, int sub, int ky, in
   cuuint64_t strides[3] = {sx, sy, sn};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // L2 promotion: 256 B for dense views (the neighbouring 128 B are the next channel block / pixel, which the same kernel
+  // reads next); 128 B when the view is a channel SLICE of a wider buffer (one half of a concat buffer) or every second
+  // pixel (ConvTranspose backward): there a 256 B promotion drags the other half of the pixel - data this kernel never
+  // uses - through DRAM (measured in round 1: 531 MB read for 268 MB of operand on the ConvTranspose backward-data and
+  // weight-gradient launches)
+  const bool dense_run = !sub && v.C == v.pitch;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   dense_run ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     crimac_set_error("cuTensorMapEncodeTiled(activation) failed with CUresult " + std::to_string(static_cast<int>(r)));

@@ -123,7 +123,10 @@ int launch_preprocess_split(const float* sv, int F, int R, int P, int data_ping0
 int reduce_blocks();
 cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* shift, const float* mean,
                           const float* invstd, View draw, float* dgamma, float* dbeta, float* dbias, int accumulate,
-                          float* partials, float* c1c2, const float* gscale, cudaStream_t st);
+                          float* partials, float* c1c2, const float* gscale, cudaStream_t st,
+                          // optional: dact is not read; the incoming gradient is dskip + unpool(dpool) through the forward's
+                          // arg-max map (max-pool backward + skip-gradient add fused into both passes)
+                          const uint16_t* pool_arg = nullptr, View dpool = View{}, View dskip = View{});
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st);
 cudaError_t launch_pool_bwd_add(const uint16_t* pool_arg, View dpool, View dskip, View dact, cudaStream_t st);
 // up_mode "upsample" (unet.py:50-56): bilinear 2x (align_corners=False) forward / adjoint on NHWC bf16 views, and the

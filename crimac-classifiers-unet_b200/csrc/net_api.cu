@@ -908,7 +908,9 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
 
   // BN/ReLU backward of layer idx (dA in GA) -> dRaw in GR; then backward-data (into L.gin) and the weight gradient
   bool wg_recorded[2] = {false, false};
-  auto conv_bwd = [&](int idx) -> int {
+  // pool_arg != nullptr (encoder second convs below the deepest level): the incoming gradient dA = dSkip + unpool(dPool)
+  // is formed inside the BatchNorm-backward kernels instead of being materialised by a separate pass
+  auto conv_bwd = [&](int idx, const uint16_t* pool_arg = nullptr, View dpool = View{}, View dskip = View{}) -> int {
     Conv3& L = c->conv[idx];
     const int H = level_h(c, L.level), W = level_w(c, L.level);
     View da{c->GA, nb, H, W, L.cout, L.cout};
@@ -918,10 +920,11 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     // an earlier call are never waited on: the call ends with a join, and a stream capture must not depend on them.
     if (c->overlap && wg_recorded[L.gr_idx]) CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_wg[L.gr_idx], 0));
     {
-      ProfScope ps("bn_relu_bwd", 0, px * L.cout * 10.0, st, 3);
+      ProfScope ps(pool_arg ? "bn_relu_bwd_pool" : "bn_relu_bwd", 0, px * L.cout * (pool_arg ? 11.2 : 10.0), st, 3);
       CRIMAC_CHECK_CUDA(launch_bn_bwd(da, with_batch(L.raw, nb), L.scale, L.shift, L.mean, L.invstd, dr, grads[L.g_g],
                                       grads[L.g_beta], grads[L.g_b], 0, c->red_partials, c->c1c2,
-                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, st));
+                                      (head_done && idx == c->dec2[c->D - 2]) ? gscale : nullptr, st, pool_arg, dpool,
+                                      dskip));
     }
     if (c->overlap) CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_draw[L.gr_idx], st));
     // backward-data first (critical path, issued first so that it is scheduled first) ...
@@ -1067,15 +1070,15 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   for (int l = D - 1; l >= 0; --l) {
     Conv3& L2 = c->conv[c->enc2[l]];
     if (l < D - 1) {
+      // max-pool backward + skip-gradient add (autograd of unet.py:86,92,132) fused into the BatchNorm backward of this layer
       const int j = D - 2 - l;
-      View dpool{c->GP, nb, level_h(c, l + 1), level_w(c, l + 1), L2.cout, L2.cout};
       const bool add = c->cfg.merge_mode == 1;   // "add": the skip branch receives the merged tensor's gradient as it is
+      View dpool{c->GP, nb, level_h(c, l + 1), level_w(c, l + 1), L2.cout, L2.cout};
       View dskip{c->dcat[j] + (add ? 0 : L2.cout), nb, level_h(c, l), level_w(c, l), L2.cout, (add ? 1 : 2) * L2.cout};
-      View dact{c->GA, nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
-      ProfScope ps("pool_bwd_add", 0, 2.0 * nb * dact.H * dact.W * L2.cout * 2.28, st);
-      CRIMAC_CHECK_CUDA(launch_pool_bwd_add(L2.pool_arg, dpool, dskip, dact, st));
+      if ((rc = conv_bwd(c->enc2[l], L2.pool_arg, dpool, dskip))) return rc;  // dgrad -> dA of enc1[l]
+    } else {
+      if ((rc = conv_bwd(c->enc2[l]))) return rc;
     }
-    if ((rc = conv_bwd(c->enc2[l]))) return rc;  // dgrad -> dA of enc1[l]
     if ((rc = conv_bwd(c->enc1[l]))) return rc;  // dgrad wrote GP (grad of the pooled input), none for l == 0
     if (l == enc_split && enc_split > 0 && (rc = close_bucket(1))) return rc;
   }

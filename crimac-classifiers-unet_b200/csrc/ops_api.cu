@@ -242,6 +242,24 @@ extern "C" int crimac_op_bn_bwd(const void* dact, int dact_pitch, const void* ra
   return 0;
 }
 
+// The same BatchNorm + ReLU backward with the incoming gradient formed on the fly as dskip + unpool(dpool) through the
+// arg-max map of crimac_op_bn_apply (max-pool backward + skip add fused in; what the encoder's second convs run).
+extern "C" int crimac_op_bn_bwd_pool(const uint16_t* pool_arg, const void* dpool, int dpool_pitch, const void* dskip,
+                                     int dskip_pitch, const void* raw, int raw_pitch, int N, int H, int W, int C,
+                                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                                     void* draw, int draw_pitch, float* dgamma, float* dbeta, float* dbias, void* scratch,
+                                     void* stream) {
+  CRIMAC_REQUIRE(pool_arg && dpool && dskip && raw && draw && scale && shift && mean && invstd && dgamma && dbeta && scratch, "NULL tensor");
+  CRIMAC_REQUIRE(C % 8 == 0 && C <= 1024 && H % 2 == 0 && W % 2 == 0, "C multiple of 8 (<= 1024), even H and W");
+  float* partials = static_cast<float*>(scratch);
+  float* c1c2 = partials + static_cast<size_t>(reduce_blocks()) * 2 * C;
+  CRIMAC_CHECK_CUDA(launch_bn_bwd(View{}, mk_view(raw, N, H, W, C, raw_pitch), scale, shift, mean, invstd,
+                                  mk_view(draw, N, H, W, C, draw_pitch), dgamma, dbeta, dbias, 0, partials, c1c2, nullptr,
+                                  static_cast<cudaStream_t>(stream), pool_arg, mk_view(dpool, N, H / 2, W / 2, C, dpool_pitch),
+                                  mk_view(dskip, N, H, W, C, dskip_pitch)));
+  return 0;
+}
+
 // Max-pool backward + skip-gradient add (autograd of unet.py:86,92,132): dact[2x2 window] = dskip[window] + (first
 // maximal element ? dpool : 0), arg-max from the map crimac_op_bn_apply wrote.  dskip may be NULL (no skip branch).
 extern "C" int crimac_op_pool_bwd_add(const uint16_t* pool_arg, const void* dpool, int dpool_pitch, const void* dskip,

@@ -220,6 +220,10 @@ int crimac_op_bn_bwd(const void* dact, int dact_pitch, const void* raw, int raw_
                      const float* scale, const float* shift, const float* mean, const float* invstd, void* draw,
                      int draw_pitch, float* dgamma, float* dbeta, float* dbias, const float* gscale, void* scratch,
                      void* stream);
+int crimac_op_bn_bwd_pool(const uint16_t* pool_arg, const void* dpool, int dpool_pitch, const void* dskip,
+                          int dskip_pitch, const void* raw, int raw_pitch, int N, int H, int W, int C, const float* scale,
+                          const float* shift, const float* mean, const float* invstd, void* draw, int draw_pitch,
+                          float* dgamma, float* dbeta, float* dbias, void* scratch, void* stream);
 int crimac_op_pool_bwd_add(const uint16_t* pool_arg, const void* dpool, int dpool_pitch, const void* dskip,
                            int dskip_pitch, void* dact, int dact_pitch, int N, int H, int W, int C, void* stream);
 int crimac_op_head_ce(const void* act, int act_pitch, int N, int H, int W, const float* hw, const float* hb, int ncls,

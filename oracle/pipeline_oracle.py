@@ -295,3 +295,17 @@ def meta_channels(centre, window, n_range, meta_cfg, portion_year, portion_of_da
     if meta_cfg.get("depth_abs_seabed"):
         out.append((sb - rows.reshape(-1, 1)) / ph)
     return np.stack(out, 0)
+
+
+def iter_meta_golden(g):
+    """Cases of tests/golden/meta_channels.npz (oracle/make_golden_meta.py): yields (tag, case index, mask tag, centre,
+    window, n_range, meta config dict, per-ping vectors dict, the reference's `meta` array)."""
+    for tag in ("deep", "shallow"):
+        vec = dict(portion_year=float(g[f"{tag}/portion_year"]), portion_of_day=g[f"{tag}/portion_of_day"],
+                   time_diff=g[f"{tag}/time_diff"], seabed=g[f"{tag}/seabed"])
+        n_range = int(g[f"{tag}/shape"][0])
+        window = tuple(int(v) for v in g[f"{tag}/window"])
+        for ci, c in enumerate(g[f"{tag}/centres"]):
+            for mtag in ("all", "some"):
+                cfg = {str(k): True for k in g[f"mask_{mtag}"]}
+                yield tag, ci, mtag, c, window, n_range, cfg, vec, g[f"{tag}/{ci}/{mtag}"]

@@ -171,6 +171,50 @@ def test_maxpool_backward_with_skip_add_is_bit_exact(env, N, H, W, C, skip):
     assert (_nchw(act) == 0).float().mean().item() > 0.3       # the tie-break really was exercised
 
 
+@pytest.mark.parametrize("N,H,W,C", [(2, 32, 32, 64), (1, 16, 48, 256), (3, 8, 8, 512)])
+def test_batchnorm_backward_with_fused_maxpool_backward_and_skip_add(env, N, H, W, C):
+    """What the encoder's second convs run: BatchNorm + ReLU backward whose incoming gradient dA = dSkip + unpool(dPool)
+    (autograd of unet.py:86,92,132) is formed inside the kernel from the forward's arg-max map - against torch autograd of
+    conv-output -> BatchNorm(train) -> ReLU -> {skip branch, MaxPool2d(2,2)} on the same bf16-rounded inputs."""
+    L, lib, dev, scratch = env
+    torch.manual_seed(C + H)
+    raw = (torch.randn(N, H, W, C, device=dev) * 1.1 + 0.1).bfloat16()
+    gamma = (torch.rand(C, device=dev) + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device=dev) * 0.3).requires_grad_(True)
+    x64 = raw.double().reshape(-1, C)
+    mean = x64.mean(0).float()
+    invstd = (1.0 / torch.sqrt(x64.var(0, unbiased=False) + 1e-5)).float()
+    scale = (gamma.detach() * invstd).contiguous()
+    shift = (beta.detach() - mean * scale).contiguous()
+    act = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
+    pool = torch.zeros(N, H // 2, W // 2, C, device=dev, dtype=torch.bfloat16)
+    arg = torch.zeros(N, H // 2, W // 2, C // 8, device=dev, dtype=torch.int16)
+    L.check(lib.crimac_op_bn_apply(L.ptr(raw), C, N, H, W, C, L.ptr(scale), L.ptr(shift), L.ptr(act), C, L.ptr(pool), C,
+                                   L.ptr(arg), L.stream_ptr()), "crimac_op_bn_apply")
+    dpool = (torch.randn(N, H // 2, W // 2, C, device=dev) * 0.02).bfloat16()
+    dcat = (torch.randn(N, H, W, 2 * C, device=dev) * 0.01).bfloat16()
+    dskip = dcat[..., C:]
+    draw = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
+    dgamma, dbeta, dbias = (torch.full((C,), 7.0, device=dev) for _ in range(3))
+    L.check(lib.crimac_op_bn_bwd_pool(L.ptr(arg), L.ptr(dpool), C, L.ptr(dskip), 2 * C, L.ptr(raw), C, N, H, W, C,
+                                      L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.ptr(draw), C, L.ptr(dgamma),
+                                      L.ptr(dbeta), L.ptr(dbias), L.ptr(scratch), L.stream_ptr()), "crimac_op_bn_bwd_pool")
+    torch.cuda.synchronize()
+    # reference: the pool routes to the first maximum of the STORED (bf16) activation, as the forward kernel decided
+    x = _nchw(raw).clone().requires_grad_(True)
+    y = F.batch_norm(x, None, None, gamma, beta, training=True, eps=1e-5)
+    a = torch.relu(y)
+    a_st = a + (_nchw(act) - a).detach()
+    (F.max_pool2d(a_st, 2) * _nchw(dpool)).sum().backward(retain_graph=True)
+    (a_st * _nchw(dskip)).sum().backward()
+    sure = (y.detach().abs() > 1e-5)
+    tol = 2 ** -8 * x.grad.abs().max().item()
+    err = ((_nchw(draw) - x.grad).abs() * sure).max().item()
+    assert err <= tol, f"dRaw: max abs err {err} > {tol}"
+    assert _rel(dgamma, gamma.grad) < 2e-4 and _rel(dbeta, beta.grad) < 2e-4
+    assert torch.all(dbias == 0)
+
+
 @pytest.mark.parametrize("ncls,N,H,W", [(3, 2, 32, 32), (2, 1, 24, 40), (8, 1, 16, 16)])
 def test_head_cross_entropy_fused_forward_backward(env, ncls, N, H, W):
     L, lib, dev, scratch = env

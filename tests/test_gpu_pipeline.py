@@ -196,10 +196,9 @@ def test_full_size_chunk_of_config3_against_the_oracle_pipeline(E, pkg):
 def test_metadata_channels_kernel_against_reference_golden(E, golden_dir):
     """crimac_meta_channels against the reference's get_crop_memmap `meta` arrays (batch/dataset.py:296-349; fixture
     made by oracle/make_golden_meta.py), written straight into planes [F, F+M) of a network input tensor."""
-    from tests.test_oracle_golden import _meta_cases
     g = np.load(os.path.join(golden_dir, "meta_channels.npz"))
     worst = 0.0
-    for tag, ci, mtag, c, window, n_range, cfg, vec, ref in _meta_cases(g):
+    for tag, ci, mtag, c, window, n_range, cfg, vec, ref in P.iter_meta_golden(g):
         M_, F_ = ref.shape[0], 4
         x = torch.full((2, F_ + M_, window[0], window[1]), 7.0, device=dev)
         centres = torch.tensor([list(c), list(c)], dtype=torch.int32, device=dev)

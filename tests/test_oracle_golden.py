@@ -139,25 +139,13 @@ def test_oracle_decoder_variants_against_reference_golden(golden_dir, variant, k
             assert ((a - b).norm() / (b.norm() + 1e-30)).item() < 2e-2, k
 
 
-def _meta_cases(g):
-    for tag in ("deep", "shallow"):
-        vec = dict(portion_year=float(g[f"{tag}/portion_year"]), portion_of_day=g[f"{tag}/portion_of_day"],
-                   time_diff=g[f"{tag}/time_diff"], seabed=g[f"{tag}/seabed"])
-        n_range = int(g[f"{tag}/shape"][0])
-        window = tuple(int(v) for v in g[f"{tag}/window"])
-        for ci, c in enumerate(g[f"{tag}/centres"]):
-            for mtag in ("all", "some"):
-                cfg = {k: True for k in g[f"mask_{mtag}"]}
-                yield tag, ci, mtag, c, window, n_range, cfg, vec, g[f"{tag}/{ci}/{mtag}"]
-
-
 def test_oracle_metadata_channels_against_reference_golden(golden_dir):
     """oracle.meta_channels against the `meta` arrays of the reference's get_crop_memmap (batch/dataset.py:296-349) run on a
     fake echogram (oracle/make_golden_meta.py): crops inside, across every edge and outside the data, all / some
     channel kinds, and the re-centring branch of an echogram shallower than the window."""
     g = np.load(os.path.join(golden_dir, "meta_channels.npz"))
     n = 0
-    for tag, ci, mtag, c, window, n_range, cfg, vec, ref in _meta_cases(g):
+    for tag, ci, mtag, c, window, n_range, cfg, vec, ref in P.iter_meta_golden(g):
         got = P.meta_channels(c, window, n_range, cfg, **vec)
         assert got.shape == ref.shape, (tag, ci, mtag)
         assert np.array_equal(got, ref), (tag, ci, mtag)
