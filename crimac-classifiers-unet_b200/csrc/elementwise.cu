@@ -764,6 +764,7 @@ __device__ __forceinline__ void block_channel_sums(const float (&acc)[NQ][8], in
 struct PoolMerge {
   const uint16_t* arg;  // nullptr: dA comes from `dact`
   View dpool, dskip;
+  int w_shift, h_shift;  // log2 of W / H when both are powers of two (index math by shifts), else -1
 };
 // incoming gradient of 8 channels of pixel p (linear index over N x H x W of the full-resolution tensor)
 template <bool PM>
@@ -779,7 +780,18 @@ struct DactLoader {
       if (ok) {
         const unsigned W = pm.dskip.W, H = pm.dskip.H;
         const unsigned up = static_cast<unsigned>(p);
-        const unsigned x = up % W, t = up / W, y = t % H, n = t / H;
+        unsigned x, y, n;
+        if (pm.w_shift >= 0) {
+          x = up & (W - 1);
+          const unsigned t = up >> pm.w_shift;
+          y = t & (H - 1);
+          n = t >> pm.h_shift;
+        } else {
+          x = up % W;
+          const unsigned t = up / W;
+          y = t % H;
+          n = t / H;
+        }
         const long pp = (static_cast<long>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
         a = __ldcs(reinterpret_cast<const uint4*>(pm.dskip.ptr + p * pm.dskip.pitch + g * 8));
         b = __ldg(reinterpret_cast<const uint4*>(pm.dpool.ptr + pp * pm.dpool.pitch + g * 8));
@@ -1399,8 +1411,13 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   const int grid_r = grid < 148 * 3 ? grid : 148 * 3;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
-  PoolMerge pm{pool_arg, dpool, dskip};
+  PoolMerge pm{pool_arg, dpool, dskip, -1, -1};
   if (pool_arg != nullptr) {
+    if ((raw.W & (raw.W - 1)) == 0 && (raw.H & (raw.H - 1)) == 0) {
+      pm.w_shift = pm.h_shift = 0;
+      while ((1 << pm.w_shift) < raw.W) ++pm.w_shift;
+      while ((1 << pm.h_shift) < raw.H) ++pm.h_shift;
+    }
     // dA = dSkip + unpool(dPool) formed on the fly (32-bit pixel index inside the loader)
     if (count > 4.0e9 || dskip.C != C || dpool.C != C || (raw.H & 1) || (raw.W & 1)) return cudaErrorInvalidValue;
     pm.dskip.N = raw.N;

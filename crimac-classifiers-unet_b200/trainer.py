@@ -53,6 +53,27 @@ class PeerGradientExchange:
         dist.barrier(group)          # every pad is zero and mapped before the first flag is written
 
 
+def gradient_buckets(model):
+    """The three slices of the flat gradient arena (parameters() order) the native backward all-reduces as it goes, in the
+    order they become final: (name, offset, count) in floats.  Bucket 0 = decoder blocks + head (the tail of the arena),
+    1 = the two deepest encoder blocks, 2 = the remaining encoder blocks; the last one is padded to the arena's
+    1024-float granularity.  Mirrors close_bucket() in csrc/net_api.cu (which derives the same ranges from the gradient
+    pointers); used by the tests and for documentation."""
+    sizes, off = {}, 0
+    for name, p in model.named_parameters():
+        sizes[name] = (off, p.numel())
+        off += p.numel()
+    total, depth = off, model.depth
+    padded = (total + 1023) // 1024 * 1024
+    split = depth - 2 if depth >= 3 else 0
+    first_up = sizes["up_convs.0.upconv.weight" if model.up_mode == "transpose" else "up_convs.0.upconv.1.weight"][0]
+    first_deep = sizes[f"down_convs.{split}.main.0.weight"][0]
+    out = [("decoder+head", first_up, padded - first_up), ("deep encoder", first_deep, first_up - first_deep)]
+    if split > 0:
+        out.append(("shallow encoder", 0, first_deep))
+    return out
+
+
 def reduce_gradients(flat_grads, world):
     """Sum the flat gradient arena over all replicas (NCCL on GPUs, gloo in the CPU tests) and return the factor that
     turns the sum into the DDP mean; the factor is folded into the SGD kernel instead of a separate scaling pass."""

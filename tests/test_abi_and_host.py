@@ -162,6 +162,26 @@ def test_patch_grid_and_sharding_host_logic(pkg):
     assert Pr.shard_chunks(chunks[:3], 8, 5) == []   # ragged: more ranks than chunks
 
 
+def test_gradient_buckets_tile_the_arena(pkg):
+    """Host mirror of the native backward's bucket ranges (trainer.gradient_buckets / csrc/net_api.cu close_bucket): the
+    buckets tile the padded arena exactly, start on 16-byte boundaries (the exchange kernel moves float4) and the big
+    tensors are in the buckets that close first."""
+    T = importlib.import_module("crimac_unet_b200.trainer")
+    M = importlib.import_module("crimac_unet_b200.models.unet")
+    for depth, kw in ((5, {}), (3, dict(merge_mode="add")), (2, {}), (4, dict(up_mode="upsample"))):
+        m = M.UNet_Baseline(3, 4, depth=depth, **kw)
+        total = sum(p.numel() for p in m.parameters())
+        b = T.gradient_buckets(m)
+        assert len(b) == (3 if depth >= 3 else 2)
+        spans = sorted((o, o + n) for _, o, n in b)
+        assert spans[0][0] == 0 and spans[-1][1] == (total + 1023) // 1024 * 1024
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+        assert all(o % 4 == 0 and n % 4 == 0 for _, o, n in b)
+    m = M.UNet_Baseline(3, 4)
+    b = dict((name, n) for name, _, n in T.gradient_buckets(m))
+    assert b["decoder+head"] > 12_000_000 and b["deep encoder"] > 17_000_000 and b["shallow encoder"] < 1_300_000
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[3])
