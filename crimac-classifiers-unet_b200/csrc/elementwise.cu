@@ -824,7 +824,7 @@ struct DactLoader {
 // by the finalize kernel: invstd * (sum g*raw - mean * sum g); the kernel then needs only two per-channel constants
 // in registers, which doubles its occupancy - it is bound by the bytes it keeps in flight.)
 template <bool PM>
-__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, PoolMerge pm, View raw,
+__global__ void __launch_bounds__(256, PM ? 2 : 3) bn_bwd_reduce_kernel(View dact, PoolMerge pm, View raw,
                                                                const float* __restrict__ scale,
                                                                const float* __restrict__ shift, float* partials) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
@@ -837,7 +837,9 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, PoolMe
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  constexpr int U = 4;  // pixels per iteration: 2*U independent 16-byte loads in flight per thread
+  // pixels per iteration: 2*U independent 16-byte loads in flight per thread (the pool-merging variant issues three
+  // loads and an index computation per pixel: two pixels keep it inside its register budget without spilling)
+  constexpr int U = PM ? 2 : 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
     DactLoader<PM> dl[U];
     uint4 rv[U];
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, PoolMer
     }
   }
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  constexpr int U = 4;
+  constexpr int U = PM ? 2 : 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
     DactLoader<PM> dl[U];
     uint4 rv[U];
@@ -1408,7 +1410,8 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
   const int grid = reduce_grid(raw);
   // the reduce kernel fits three blocks per SM: one full wave (a 592-block grid would leave a 1/3-occupancy tail wave)
-  const int grid_r = grid < 148 * 3 ? grid : 148 * 3;
+  const int per_sm = pool_arg != nullptr ? 2 : 3;   // resident blocks per SM of the reduce kernel (register budget)
+  const int grid_r = grid < 148 * per_sm ? grid : 148 * per_sm;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
   PoolMerge pm{pool_arg, dpool, dskip, -1, -1};

@@ -41,6 +41,23 @@ ncu)
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:wgrad_halo|wgrad_gemm" -c 21 -s 63 -o gpurun_out/prof_wgrad $CMD > gpurun_out/ncu_wgrad.log 2>&1
   echo "ncu wgrad exit $?"
   python tools/ncu_summary.py report gpurun_out/prof_wgrad.ncu-rep gpurun_out/ncu_wgrad_train.csv; rm -f gpurun_out/prof_wgrad.ncu-rep ;;
+ncu_elem)
+  CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --quick"
+  $CMD > gpurun_out/plain4.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:bn_bwd|bn_apply|bn_finalize|head_ce|first_conv|partial_sum|view_colsum|unpack|pack_|sgd" -c 60 -s 330 -o gpurun_out/prof_elem $CMD > gpurun_out/ncu_elem.log 2>&1
+  echo "ncu elem exit $?"
+  python tools/ncu_summary.py report gpurun_out/prof_elem.ncu-rep gpurun_out/ncu_elem_train.csv; rm -f gpurun_out/prof_elem.ncu-rep ;;
+ncu_infer)
+  CMD="python bench.py --mode infer --steps 1 --warmup 3 --no-cpu-baseline"
+  $CMD > gpurun_out/plain5.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:conv_igemm|first_conv" -c 22 -s 66 -o gpurun_out/prof_infer $CMD > gpurun_out/ncu_infer.log 2>&1
+  echo "ncu infer exit $?"
+  python tools/ncu_summary.py report gpurun_out/prof_infer.ncu-rep gpurun_out/ncu_conv_infer.csv; rm -f gpurun_out/prof_infer.ncu-rep ;;
+stress)
+  timeout 600 python bench.py --mode train --in-ch 6 --size 512 --batch 64 --steps 5 --warmup 3 --no-cpu-baseline --quick > gpurun_out/bench_stress_train.json 2> gpurun_out/bench_stress_train.err
+  echo "bench stress train exit $?"; cat gpurun_out/bench_stress_train.json; tail -3 gpurun_out/bench_stress_train.err
+  timeout 600 python bench.py --mode infer --in-ch 6 --size 512 --batch 64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stress_infer.json 2> gpurun_out/bench_stress_infer.err
+  echo "bench stress infer exit $?"; cat gpurun_out/bench_stress_infer.json; tail -3 gpurun_out/bench_stress_infer.err ;;
 *) echo "unknown step $what" ;;
 esac
 done
