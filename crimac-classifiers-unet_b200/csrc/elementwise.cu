@@ -837,9 +837,8 @@ __global__ void __launch_bounds__(256, PM ? 2 : 3) bn_bwd_reduce_kernel(View dac
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  // pixels per iteration: 2*U independent 16-byte loads in flight per thread (the pool-merging variant issues three
-  // loads and an index computation per pixel: two pixels keep it inside its register budget without spilling)
-  constexpr int U = PM ? 2 : 4;
+  // pixels per iteration: 2*U (pool-merging variant: 3*U) independent 16-byte loads in flight per thread
+  constexpr int U = 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
     DactLoader<PM> dl[U];
     uint4 rv[U];
@@ -958,7 +957,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, PoolMer
     }
   }
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  constexpr int U = PM ? 2 : 4;
+  constexpr int U = 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
     DactLoader<PM> dl[U];
     uint4 rv[U];
