@@ -44,6 +44,9 @@ struct ConvParams {
   // epilogue
   bf16* out;
   int out_pitch;         // elements per output pixel
+  bf16* out2;            // optional second destination: output channels >= out_split go to out2 (channel - out_split)
+  int out2_pitch;        //   (backward-data of a conv that read a concat: the two halves of the concat gradient are
+  int out_split;         //   kept as two DENSE tensors - every reader takes one half only)
   int relu;
   int convt_cout;        // >0: convT scatter, N index = (ky*2+kx)*convt_cout + co, output is 2H x 2W
   int convt_add;         // convT scatter ADDS to what the destination holds (merge_mode "add": the skip activation)

@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
             }
           } else {
             const long opix = (static_cast<long>(img) * p.H + y) * p.W + x;
-            dst = p.out + opix * p.out_pitch + ng;
+            dst = (p.out2 != nullptr && ng >= p.out_split) ? p.out2 + opix * p.out2_pitch + (ng - p.out_split)
+                                                           : p.out + opix * p.out_pitch + ng;
           }
           store32(dst, pk);
           store32(dst + 16, pk + 8);
@@ -689,6 +690,8 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int block_n, int epi, int num
   // the epilogue writes 32-byte (256-bit) vectors
   if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 31) || p.out_pitch % 16)) return cudaErrorInvalidValue;
   if (p.pool_out && ((reinterpret_cast<uintptr_t>(p.pool_out) & 31) || p.pool_pitch % 16)) return cudaErrorInvalidValue;
+  if (p.out2 && ((reinterpret_cast<uintptr_t>(p.out2) & 31) || p.out2_pitch % 16 || p.out_split % 32 || p.convt_cout > 0 || epi != EPI_STORE))
+    return cudaErrorInvalidValue;
   if (p.b_mn && (epi != EPI_STORE || (p.taps != 9 && p.taps != 4 && p.taps != 1))) return cudaErrorInvalidValue;
   if (p.b_mn && p.taps == 9 && !p.halo) return cudaErrorInvalidValue;  // 3x3 MN-major weights: halo main loop only
 #define CASE(BN, EP)                                                               \

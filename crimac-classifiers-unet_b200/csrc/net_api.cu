@@ -44,6 +44,8 @@ struct Conv3 {
   int s_w = 0, s_b = 0, s_g = 0, s_beta = 0, s_rm = 0, s_rv = 0, s_nbt = 0;
   int g_w = 0, g_b = 0, g_g = 0, g_beta = 0;
   View in{}, raw{}, act{}, pool{}, gin{};
+  bf16* gin2 = nullptr;  // decoder first convs ("concat"): input-gradient channels >= gin_split go to this dense tensor
+  int gin_split = 0;
   uint16_t* pool_arg = nullptr;  // train: 2-bit arg-max map of the fused max-pool (one uint16 per 8 channels)
   bf16* w_fwd = nullptr;  // backward-data reads the same matrix as an MN-major operand
   float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr;
@@ -89,7 +91,8 @@ struct crimac_ctx {
   cudaStream_t side = nullptr;       // weight-gradient GEMMs run here, concurrently with the HBM-bound backward kernels
   cudaEvent_t ev_draw[2] = {nullptr, nullptr}, ev_wg[2] = {nullptr, nullptr}, ev_cat = nullptr, ev_join = nullptr;
   bool overlap = true;
-  std::vector<bf16*> dcat;
+  std::vector<bf16*> dcat;   // gradient of decoder block j's merged input: "concat": the up-sampled half (dense, C channels);
+  std::vector<bf16*> dskip;  //   the skip half lives in dskip[j] (dense, C channels).  "add": dcat[j] is both
   float* stats = nullptr;
   float* red_partials = nullptr;
   float* colsum_partials = nullptr;  // ConvTranspose bias-gradient partials (side stream: must not share red_partials)
@@ -296,6 +299,7 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
   c->xs = bump.arr<bf16>(first_conv_split_elems(B, cfg.in_channels, cfg.height, cfg.width));
   // ---- training scratch
   c->dcat.assign(D - 1, nullptr);
+  c->dskip.assign(D - 1, nullptr);
   if (train) {
     const size_t lvl0 = static_cast<size_t>(B) * cfg.height * cfg.width * cfg.start_filts;
     c->GA = bump.arr<bf16>(lvl0);
@@ -316,7 +320,10 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
     c->GP = bump.arr<bf16>(lvl0 / 4);
     for (int j = 0; j < D - 1; ++j) {
       const int l = D - 2 - j;
-      c->dcat[j] = bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * (add ? 1 : 2) * chan(l));
+      // two DENSE halves instead of one concat-shaped gradient: the ConvTranspose backward reads only the first, the
+      // encoder's skip branch only the second - strided half-reads of a 2C-wide buffer cost DRAM row bandwidth
+      c->dcat[j] = bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * chan(l));
+      c->dskip[j] = add ? c->dcat[j] : bump.arr<bf16>(static_cast<size_t>(B) * level_h(c, l) * level_w(c, l) * chan(l));
       if (ups) c->up[j].dtmp = dense(l + 1, chan(l));
     }
     const int cmax = chan(D - 1);
@@ -377,10 +384,14 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
       const int l = D - 2 - j;
       Conv3& L1 = c->conv[c->dec1[j]];
       Conv3& L2 = c->conv[c->dec2[j]];
-      L1.gin = View{c->dcat[j], B, level_h(c, l), level_w(c, l), L1.cin, L1.cin};
+      L1.gin = View{c->dcat[j], B, level_h(c, l), level_w(c, l), chan(l), chan(l)};
+      if (!add) {   // channels [C, 2C) of the concat gradient = the skip half
+        L1.gin2 = c->dskip[j];
+        L1.gin_split = chan(l);
+      }
       L2.gin = View{c->GA, B, level_h(c, l), level_w(c, l), L2.cin, L2.cin};
       ConvT& U = c->up[j];
-      U.gout = View{c->dcat[j], B, level_h(c, l), level_w(c, l), U.cout, (add ? 1 : 2) * U.cout};
+      U.gout = View{c->dcat[j], B, level_h(c, l), level_w(c, l), U.cout, U.cout};
       U.gin = View{c->GA, B, level_h(c, l + 1), level_w(c, l + 1), U.cin, U.cin};
     }
   } else {
@@ -440,6 +451,9 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         if ((rc = make_weight_map(&p.b_map, L.w_fwd, L.cout, 9 * L.cin, 64))) return rc;
         p.out = L.gin.ptr;
         p.out_pitch = L.gin.pitch;
+        p.out2 = L.gin2;
+        p.out2_pitch = L.gin_split;
+        p.out_split = L.gin_split;
         WgradHaloParams& w = L.wg;
         w.Cs = L.cout;
         w.Cf = L.cin;
@@ -1072,9 +1086,8 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
     if (l < D - 1) {
       // max-pool backward + skip-gradient add (autograd of unet.py:86,92,132) fused into the BatchNorm backward of this layer
       const int j = D - 2 - l;
-      const bool add = c->cfg.merge_mode == 1;   // "add": the skip branch receives the merged tensor's gradient as it is
       View dpool{c->GP, nb, level_h(c, l + 1), level_w(c, l + 1), L2.cout, L2.cout};
-      View dskip{c->dcat[j] + (add ? 0 : L2.cout), nb, level_h(c, l), level_w(c, l), L2.cout, (add ? 1 : 2) * L2.cout};
+      View dskip{c->dskip[j], nb, level_h(c, l), level_w(c, l), L2.cout, L2.cout};
       if ((rc = conv_bwd(c->enc2[l], L2.pool_arg, dpool, dskip))) return rc;  // dgrad -> dA of enc1[l]
     } else {
       if ((rc = conv_bwd(c->enc2[l]))) return rc;

@@ -58,6 +58,9 @@ stress)
   echo "bench stress train exit $?"; cat gpurun_out/bench_stress_train.json; tail -3 gpurun_out/bench_stress_train.err
   timeout 600 python bench.py --mode infer --in-ch 6 --size 512 --batch 64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stress_infer.json 2> gpurun_out/bench_stress_infer.err
   echo "bench stress infer exit $?"; cat gpurun_out/bench_stress_infer.json; tail -3 gpurun_out/bench_stress_infer.err ;;
+smoke)
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+  echo "smoke exit $?"; tail -5 gpurun_out/smoke.log ;;
 *) echo "unknown step $what" ;;
 esac
 done
