@@ -606,29 +606,33 @@ __global__ void __launch_bounds__(256) head_ce_fused_kernel(View act, const floa
         t += __shfl_xor_sync(0xffffffffu, t, 4);
         z[k] = t + bias[k];
       }
-      float mx = z[0];
-#pragma unroll
-      for (int k = 1; k < NCLS; ++k) mx = fmaxf(mx, z[k]);
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < NCLS; ++k) sum += expf(z[k] - mx);
-      const float lse = mx + logf(sum);
+      // the softmax / loss of a pixel is computed ONCE, by the first of its 8 threads, and the NCLS logit gradients are
+      // broadcast to the others (7/8 of the expf / logf work of the kernel was redundant)
       const bool use = ok[u] && (y[u] != ignore_index) && y[u] >= 0 && y[u] < NCLS;
-      if (g == 0 && ok[u] && y[u] != ignore_index && !use) la = static_cast<double>(NAN);  // invalid label: see ce_fwd_bwd_kernel
-      float wy = 0.f, zy = 0.f;
-#pragma unroll
-      for (int k = 0; k < NCLS; ++k)
-        if (use && y[u] == k) {
-          wy = wcls[k];
-          zy = z[k];
-        }
-      float dl[NCLS];
-#pragma unroll
-      for (int k = 0; k < NCLS; ++k) dl[k] = wy * (expf(z[k] - lse) - ((use && y[u] == k) ? 1.f : 0.f));
+      float dl[NCLS] = {};
       if (g == 0) {
+        float mx = z[0];
+#pragma unroll
+        for (int k = 1; k < NCLS; ++k) mx = fmaxf(mx, z[k]);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) sum += expf(z[k] - mx);
+        const float lse = mx + logf(sum);
+        if (ok[u] && y[u] != ignore_index && !use) la = static_cast<double>(NAN);  // invalid label: see ce_fwd_bwd_kernel
+        float wy = 0.f, zy = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k)
+          if (use && y[u] == k) {
+            wy = wcls[k];
+            zy = z[k];
+          }
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) dl[k] = wy * (expf(z[k] - lse) - ((use && y[u] == k) ? 1.f : 0.f));
         if (use) la += static_cast<double>(wy) * static_cast<double>(lse - zy);
         lb += wy;
       }
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) dl[k] = __shfl_sync(0xffffffffu, dl[k], lane & ~7);
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
