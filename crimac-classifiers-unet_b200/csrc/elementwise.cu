@@ -762,74 +762,10 @@ __device__ __forceinline__ void block_channel_sums(const float (&acc)[NQ][8], in
   }
 }
 
-// Optional producer of dA for the encoder's second convs: dA = dSkip + unpool(dPool) (autograd of unet.py:86,92,132) is
-// not read from memory but formed on the fly from the concat gradient's skip half, the pooled gradient and the 2-bit
-// arg-max map - the separate pool_bwd_add pass (4.6 bytes per element, written and read back) disappears.
-struct PoolMerge {
-  const uint16_t* arg;  // nullptr: dA comes from `dact`
-  View dpool, dskip;
-  int w_shift, h_shift;  // log2 of W / H when both are powers of two (index math by shifts), else -1
-};
-// incoming gradient of 8 channels of pixel p (linear index over N x H x W of the full-resolution tensor)
-template <bool PM>
-struct DactLoader {
-  uint4 a, b;
-  uint32_t sel;  // PM: window position of this pixel + the arg-max word
-  __device__ __forceinline__ void issue(const View& dact, const PoolMerge& pm, long p, int g, int groups, bool ok) {
-    if (!PM) {
-      a = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
-    } else {
-      a = b = make_uint4(0, 0, 0, 0);
-      sel = 0;
-      if (ok) {
-        const unsigned W = pm.dskip.W, H = pm.dskip.H;
-        const unsigned up = static_cast<unsigned>(p);
-        unsigned x, y, n;
-        if (pm.w_shift >= 0) {
-          x = up & (W - 1);
-          const unsigned t = up >> pm.w_shift;
-          y = t & (H - 1);
-          n = t >> pm.h_shift;
-        } else {
-          x = up % W;
-          const unsigned t = up / W;
-          y = t % H;
-          n = t / H;
-        }
-        const long pp = (static_cast<long>(n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
-        a = __ldcs(reinterpret_cast<const uint4*>(pm.dskip.ptr + p * pm.dskip.pitch + g * 8));
-        b = __ldg(reinterpret_cast<const uint4*>(pm.dpool.ptr + pp * pm.dpool.pitch + g * 8));
-        sel = (static_cast<uint32_t>(((y & 1) << 1) | (x & 1)) << 16) | __ldg(pm.arg + pp * groups + g);
-      }
-    }
-  }
-  __device__ __forceinline__ void get(float (&d)[8]) const {
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const float2 t = unpack_bf16x2(aw[h]);
-      d[2 * h] = t.x;
-      d[2 * h + 1] = t.y;
-    }
-    if (PM) {
-      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-      const uint32_t q = sel >> 16, arg = sel & 0xffffu;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float2 t = unpack_bf16x2(bw[h]);
-        d[2 * h] += (((arg >> (4 * h)) & 3u) == q) ? t.x : 0.f;
-        d[2 * h + 1] += (((arg >> (4 * h + 2)) & 3u) == q) ? t.y : 0.f;
-      }
-    }
-  }
-};
-
 // phase 1: g = dA * (bn(raw) > 0);  partial 0 = sum g, partial 1 = sum g * raw.  (sum g * xhat is derived from the two
 // by the finalize kernel: invstd * (sum g*raw - mean * sum g); the kernel then needs only two per-channel constants
 // in registers, which doubles its occupancy - it is bound by the bytes it keeps in flight.)
-template <bool PM>
-__global__ void __launch_bounds__(256, PM ? 2 : 3) bn_bwd_reduce_kernel(View dact, PoolMerge pm, View raw,
-                                                               const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, View raw, const float* __restrict__ scale,
                                                                const float* __restrict__ shift, float* partials) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
@@ -841,23 +777,91 @@ __global__ void __launch_bounds__(256, PM ? 2 : 3) bn_bwd_reduce_kernel(View dac
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const long stride = static_cast<long>(gridDim.x) * ppb;
-  // pixels per iteration: 2*U (pool-merging variant: 3*U) independent 16-byte loads in flight per thread
-  constexpr int U = 4;
+  constexpr int U = 4;  // pixels per iteration: 2*U independent 16-byte loads in flight per thread
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
-    DactLoader<PM> dl[U];
-    uint4 rv[U];
+    uint4 dv[U], rv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       const bool ok = p < npix;
-      dl[u].issue(dact, pm, p, g, groups, ok);
+      dv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
       rv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      float d[8];
-      dl[u].get(d);
-      const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+      const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w}, rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 d = unpack_bf16x2(dw[h]), r = unpack_bf16x2(rw[h]);
+        const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d.x : 0.f;
+        const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d.y : 0.f;
+        acc[0][2 * h] += g0;
+        acc[0][2 * h + 1] += g1;
+        acc[1][2 * h] = fmaf(g0, r.x, acc[1][2 * h]);
+        acc[1][2 * h + 1] = fmaf(g1, r.y, acc[1][2 * h + 1]);
+      }
+    }
+  }
+  block_channel_sums<2>(acc, C, g, pl, ppb, partials);
+}
+
+// The encoder's second convs: the incoming gradient dA = dSkip + unpool(dPool) (autograd of unet.py:86,92,132) is not
+// read from memory but formed on the fly - the separate pool_bwd_add pass (4.6 bytes per element, written and read back)
+// disappears.  A thread owns one 2x2 pooling WINDOW x 8 channels (the mapping of bn_apply's pooling variant): one load of
+// the pooled gradient and of the 2-bit-per-channel arg-max word serves four pixels, and the window position each
+// channel's gradient routes to is a compile-time constant of the unrolled loop.
+struct PoolWindow {
+  long p00;       // linear pixel index of the window's upper-left pixel
+  uint4 dp;       // pooled gradient, 8 channels
+  uint32_t arg;   // 2 bits per channel: window position (row*2 + col) of the forward's first maximum
+};
+__device__ __forceinline__ PoolWindow load_window(const uint16_t* __restrict__ pool_arg, const View& dpool, int H, int W,
+                                                  unsigned pp, int g, int groups) {
+  const unsigned Wo = W >> 1, Ho = H >> 1;
+  const unsigned q = pp / Wo, xo = pp - q * Wo, n = q / Ho, yo = q - n * Ho;
+  PoolWindow w;
+  w.p00 = (static_cast<long>(n) * H + 2 * yo) * W + 2 * xo;
+  w.dp = __ldg(reinterpret_cast<const uint4*>(dpool.ptr + static_cast<long>(pp) * dpool.pitch + g * 8));
+  w.arg = __ldg(pool_arg + static_cast<long>(pp) * groups + g);
+  return w;
+}
+// d[8] = dSkip values of window pixel `pos` + the pooled gradient of the channels whose maximum was at `pos`
+template <int POS>
+__device__ __forceinline__ void window_grad(const uint4& ds, const PoolWindow& w, float (&d)[8]) {
+  const uint32_t sw[4] = {ds.x, ds.y, ds.z, ds.w}, pw[4] = {w.dp.x, w.dp.y, w.dp.z, w.dp.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float2 s = unpack_bf16x2(sw[h]), t = unpack_bf16x2(pw[h]);
+    d[2 * h] = s.x + ((((w.arg >> (4 * h)) & 3u) == POS) ? t.x : 0.f);
+    d[2 * h + 1] = s.y + ((((w.arg >> (4 * h + 2)) & 3u) == POS) ? t.y : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_pool_kernel(const uint16_t* __restrict__ pool_arg, View dpool,
+                                                                    View dskip, View raw,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift, float* partials) {
+  const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const unsigned npool = static_cast<unsigned>(raw.N) * (raw.H >> 1) * (raw.W >> 1);
+  float sc[8], sh[8];
+  ldg8f(scale + g * 8, sc);
+  ldg8f(shift + g * 8, sh);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const unsigned stride = gridDim.x * ppb;
+  for (unsigned pp = blockIdx.x * ppb + pl; pp < npool; pp += stride) {
+    const PoolWindow w = load_window(pool_arg, dpool, raw.H, raw.W, pp, g, groups);
+    uint4 ds[4], rv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long p = w.p00 + (k >> 1) * raw.W + (k & 1);
+      ds[k] = __ldcs(reinterpret_cast<const uint4*>(dskip.ptr + p * dskip.pitch + g * 8));
+      rv[k] = __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8));
+    }
+    auto one = [&](const float (&d)[8], const uint4& r4) {
+      const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         const float2 r = unpack_bf16x2(rw[h]);
@@ -868,7 +872,12 @@ __global__ void __launch_bounds__(256, PM ? 2 : 3) bn_bwd_reduce_kernel(View dac
         acc[1][2 * h] = fmaf(g0, r.x, acc[1][2 * h]);
         acc[1][2 * h + 1] = fmaf(g1, r.y, acc[1][2 * h + 1]);
       }
-    }
+    };
+    float d[8];
+    window_grad<0>(ds[0], w, d); one(d, rv[0]);
+    window_grad<1>(ds[1], w, d); one(d, rv[1]);
+    window_grad<2>(ds[2], w, d); one(d, rv[2]);
+    window_grad<3>(ds[3], w, d); one(d, rv[3]);
   }
   block_channel_sums<2>(acc, C, g, pl, ppb, partials);
 }
@@ -930,11 +939,44 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
   }
 }
 
-// phase 2 (apply): dRaw = scale * (g - c1 - xhat*c2) = A*g + B*raw + K per channel -> bf16.
+// per-channel constants of phase 2: dRaw = scale * (g - c1 - xhat*c2) = A*g + B*raw + K
+struct BnBwdCoef {
+  float sc[8], sh[8], ca[8], cb[8], ck[8];
+};
+__device__ __forceinline__ void load_bn_bwd_coef(BnBwdCoef& k, int g, const float* scale, const float* shift,
+                                                 const float* mean, const float* invstd, const float* c1,
+                                                 const float* c2, const float* gscale) {
+  float mu[8], is[8], k1[8], k2[8];
+  ldg8f(scale + g * 8, k.sc);
+  ldg8f(shift + g * 8, k.sh);
+  ldg8f(mean + g * 8, mu);
+  ldg8f(invstd + g * 8, is);
+  ldg8f(c1 + g * 8, k1);
+  ldg8f(c2 + g * 8, k2);
+  const float gs = gscale ? *gscale : 1.f;  // the incoming gradient was produced unnormalised (fused head/CE)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    k.ca[j] = k.sc[j] * gs;
+    k.cb[j] = -k.sc[j] * k2[j] * is[j];
+    k.ck[j] = -k.sc[j] * k1[j] - k.cb[j] * mu[j];
+  }
+}
+__device__ __forceinline__ void bn_bwd_pixel(const BnBwdCoef& k, const float (&d)[8], const uint4& r4, float (&o)[8]) {
+  const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float2 r = unpack_bf16x2(rw[h]);
+    const float g0 = fmaf(r.x, k.sc[2 * h], k.sh[2 * h]) > 0.f ? d[2 * h] : 0.f;
+    const float g1 = fmaf(r.y, k.sc[2 * h + 1], k.sh[2 * h + 1]) > 0.f ? d[2 * h + 1] : 0.f;
+    o[2 * h] = fmaf(k.ca[2 * h], g0, fmaf(k.cb[2 * h], r.x, k.ck[2 * h]));
+    o[2 * h + 1] = fmaf(k.ca[2 * h + 1], g1, fmaf(k.cb[2 * h + 1], r.y, k.ck[2 * h + 1]));
+  }
+}
+
+// phase 2 (apply): dRaw = A*g + B*raw + K per channel -> bf16.
 // (The conv-bias gradient sum(dRaw) is EXACTLY zero in exact arithmetic - train-mode BatchNorm removes any bias - and the
 // reference's value is pure cancellation noise ~1e-9; it is written as 0 by the finalize kernel instead of being summed.)
-template <bool PM>
-__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, PoolMerge pm, View raw, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View raw, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd,
@@ -943,54 +985,70 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, PoolMer
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
-  float sc[8], sh[8], cb[8], ck[8], ca[8];
-  {
-    float mu[8], is[8], k1[8], k2[8];
-    ldg8f(scale + g * 8, sc);
-    ldg8f(shift + g * 8, sh);
-    ldg8f(mean + g * 8, mu);
-    ldg8f(invstd + g * 8, is);
-    ldg8f(c1 + g * 8, k1);
-    ldg8f(c2 + g * 8, k2);
-    const float gs = gscale ? *gscale : 1.f;  // the incoming gradient was produced unnormalised (fused head/CE)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ca[j] = sc[j] * gs;
-      cb[j] = -sc[j] * k2[j] * is[j];
-      ck[j] = -sc[j] * k1[j] - cb[j] * mu[j];
-    }
-  }
+  BnBwdCoef k;
+  load_bn_bwd_coef(k, g, scale, shift, mean, invstd, c1, c2, gscale);
   const long stride = static_cast<long>(gridDim.x) * ppb;
   constexpr int U = 4;
   for (long p0 = static_cast<long>(blockIdx.x) * ppb + pl; p0 < npix; p0 += U * stride) {
-    DactLoader<PM> dl[U];
-    uint4 rv[U];
+    uint4 dv[U], rv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       const bool ok = p < npix;
-      dl[u].issue(dact, pm, p, g, groups, ok);
+      dv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(dact.ptr + p * dact.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
       rv[u] = ok ? __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long p = p0 + u * stride;
       if (p < npix) {
-        float d[8];
-        dl[u].get(d);
-        const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
-        float o[8];
+        const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+        float d[8], o[8];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const float2 r = unpack_bf16x2(rw[h]);
-          const float g0 = fmaf(r.x, sc[2 * h], sh[2 * h]) > 0.f ? d[2 * h] : 0.f;
-          const float g1 = fmaf(r.y, sc[2 * h + 1], sh[2 * h + 1]) > 0.f ? d[2 * h + 1] : 0.f;
-          o[2 * h] = fmaf(ca[2 * h], g0, fmaf(cb[2 * h], r.x, ck[2 * h]));
-          o[2 * h + 1] = fmaf(ca[2 * h + 1], g1, fmaf(cb[2 * h + 1], r.y, ck[2 * h + 1]));
+          const float2 t = unpack_bf16x2(dw[h]);
+          d[2 * h] = t.x;
+          d[2 * h + 1] = t.y;
         }
+        bn_bwd_pixel(k, d, rv[u], o);
         store8(draw.ptr + p * draw.pitch + g * 8, o);
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_pool_kernel(const uint16_t* __restrict__ pool_arg, View dpool,
+                                                                   View dskip, View raw, const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd,
+                                                                   const float* __restrict__ c1,
+                                                                   const float* __restrict__ c2, const float* gscale,
+                                                                   View draw) {
+  const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
+  const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
+  const unsigned npool = static_cast<unsigned>(raw.N) * (raw.H >> 1) * (raw.W >> 1);
+  BnBwdCoef k;
+  load_bn_bwd_coef(k, g, scale, shift, mean, invstd, c1, c2, gscale);
+  const unsigned stride = gridDim.x * ppb;
+  for (unsigned pp = blockIdx.x * ppb + pl; pp < npool; pp += stride) {
+    const PoolWindow w = load_window(pool_arg, dpool, raw.H, raw.W, pp, g, groups);
+    uint4 ds[4], rv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long p = w.p00 + (q >> 1) * raw.W + (q & 1);
+      ds[q] = __ldcs(reinterpret_cast<const uint4*>(dskip.ptr + p * dskip.pitch + g * 8));
+      rv[q] = __ldcs(reinterpret_cast<const uint4*>(raw.ptr + p * raw.pitch + g * 8));
+    }
+    float d[8], o[8];
+    window_grad<0>(ds[0], w, d); bn_bwd_pixel(k, d, rv[0], o);
+    store8(draw.ptr + w.p00 * draw.pitch + g * 8, o);
+    window_grad<1>(ds[1], w, d); bn_bwd_pixel(k, d, rv[1], o);
+    store8(draw.ptr + (w.p00 + 1) * draw.pitch + g * 8, o);
+    window_grad<2>(ds[2], w, d); bn_bwd_pixel(k, d, rv[2], o);
+    store8(draw.ptr + (w.p00 + raw.W) * draw.pitch + g * 8, o);
+    window_grad<3>(ds[3], w, d); bn_bwd_pixel(k, d, rv[3], o);
+    store8(draw.ptr + (w.p00 + raw.W + 1) * draw.pitch + g * 8, o);
   }
 }
 
@@ -1413,33 +1471,31 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
   const int grid = reduce_grid(raw);
   // the reduce kernel fits three blocks per SM: one full wave (a 592-block grid would leave a 1/3-occupancy tail wave)
-  const int per_sm = pool_arg != nullptr ? 2 : 3;   // resident blocks per SM of the reduce kernel (register budget)
-  const int grid_r = grid < 148 * per_sm ? grid : 148 * per_sm;
+  int grid_r = grid < 148 * 3 ? grid : 148 * 3;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
-  PoolMerge pm{pool_arg, dpool, dskip, -1, -1};
   if (pool_arg != nullptr) {
-    if ((raw.W & (raw.W - 1)) == 0 && (raw.H & (raw.H - 1)) == 0) {
-      pm.w_shift = pm.h_shift = 0;
-      while ((1 << pm.w_shift) < raw.W) ++pm.w_shift;
-      while ((1 << pm.h_shift) < raw.H) ++pm.h_shift;
-    }
-    // dA = dSkip + unpool(dPool) formed on the fly (32-bit pixel index inside the loader)
+    // dA = dSkip + unpool(dPool) formed on the fly, one thread per pooling window
     if (count > 4.0e9 || dskip.C != C || dpool.C != C || (raw.H & 1) || (raw.W & 1)) return cudaErrorInvalidValue;
-    pm.dskip.N = raw.N;
-    pm.dskip.H = raw.H;
-    pm.dskip.W = raw.W;
-    bn_bwd_reduce_kernel<true><<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, pm, raw, scale, shift, partials);
+    const long windows = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2);
+    long gw = (windows + ppb - 1) / ppb;
+    if (gw > 148 * 2) gw = 148 * 2;   // two resident blocks per SM: one full wave
+    if (gw < 1) gw = 1;
+    grid_r = static_cast<int>(gw);
+    bn_bwd_reduce_pool_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(pool_arg, dpool, dskip, raw, scale, shift, partials);
   } else {
-    bn_bwd_reduce_kernel<false><<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, pm, raw, scale, shift, partials);
+    bn_bwd_reduce_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
   }
   partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid_r, C, count, dbeta,
                                                                 dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd,
                                                                 dbias);
-  if (pool_arg != nullptr)
-    bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dact, pm, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
-  else
-    bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dact, pm, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
+  if (pool_arg != nullptr) {
+    const long windows = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2);
+    bn_bwd_apply_pool_kernel<<<grid_for(windows, ppb), 256, 0, st>>>(pool_arg, dpool, dskip, raw, scale, shift, mean, invstd,
+                                                                     c1c2, c1c2 + C, gscale, draw);
+  } else {
+    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
