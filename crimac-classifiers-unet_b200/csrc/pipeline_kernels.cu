@@ -140,9 +140,43 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float* __restrict__ p
   }
 }
 
+// v = momentum*v + g*gscale ; p -= lr*v  (torch.optim.SGD, dampening 0, pipeline.py:156,178).  16 bytes per parameter of
+// HBM traffic: float4 loads / stores (n4 vectors), the last n % 4 elements by the first threads of block 0.
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, float* __restrict__ v,
                                                   const float* __restrict__ g, size_t n, float lr, float momentum,
                                                   float gscale) {
+  const size_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 gv = __ldcs(g4 + i);
+    float4 vv = v4[i], pv = p4[i];
+    vv.x = momentum * vv.x + gv.x * gscale;
+    vv.y = momentum * vv.y + gv.y * gscale;
+    vv.z = momentum * vv.z + gv.z * gscale;
+    vv.w = momentum * vv.w + gv.w * gscale;
+    pv.x -= lr * vv.x;
+    pv.y -= lr * vv.y;
+    pv.z -= lr * vv.z;
+    pv.w -= lr * vv.w;
+    v4[i] = vv;
+    p4[i] = pv;
+  }
+  if (blockIdx.x == 0) {
+    const size_t i = (n4 << 2) + threadIdx.x;
+    if (i < n) {
+      const float nv = momentum * v[i] + g[i] * gscale;
+      v[i] = nv;
+      p[i] -= lr * nv;
+    }
+  }
+}
+// scalar form for arenas that are not 16-byte aligned
+__global__ void __launch_bounds__(256) sgd_scalar_kernel(float* __restrict__ p, float* __restrict__ v,
+                                                         const float* __restrict__ g, size_t n, float lr, float momentum,
+                                                         float gscale) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float nv = momentum * v[i] + g[i] * gscale;
@@ -201,11 +235,14 @@ extern "C" int crimac_stitch(const float* probs, int n, int n_classes, int ph, i
 extern "C" int crimac_sgd_step(float* params, float* mom, const float* grads, size_t n, float lr, float momentum,
                                float gscale, void* stream) {
   CRIMAC_REQUIRE(params && mom && grads, "NULL tensor");
-  size_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks == 0) return 0;
-  sgd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, mom, grads, n, lr,
-                                                                                      momentum, gscale);
+  if (n == 0) return 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(mom) | reinterpret_cast<uintptr_t>(grads)) & 15) == 0;
+  size_t blocks = ((aligned ? (n >> 2) + 1 : n) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (aligned)
+    sgd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, mom, grads, n, lr, momentum, gscale);
+  else
+    sgd_scalar_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, mom, grads, n, lr, momentum, gscale);
   CRIMAC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
