@@ -113,6 +113,8 @@ struct crimac_ctx {
   // data-parallel gradient exchange over peer memory (crimac_set_comm): buckets are reduced on `comm` while backward runs
   crimac_comm_config comm{};
   bool comm_on = false;
+  crimac_optimizer_config opt{};   // fused SGD(momentum) per gradient bucket (crimac_set_optimizer)
+  bool opt_on = false;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_bk_main[3] = {nullptr, nullptr, nullptr}, ev_bk_side[3] = {nullptr, nullptr, nullptr}, ev_comm = nullptr;
 };
@@ -1013,27 +1015,47 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
       ProfScope ps("wgrad_unpack", 0, 0, us);
       CRIMAC_CHECK_CUDA(launch_wgrad_unpack_all(t, us));
     }
-    if (!c->comm_on) return 0;
+    const bool opt_on = c->opt_on && head_done;   // the optimizer rides only on the fused train step, never on autograd's backward
+    if (!c->comm_on && !opt_on) return 0;
     // arena slice of the bucket, from the gradient table (parameters() order: encoder blocks, decoder blocks, head)
-    const float* base = c->comm.peer_arenas[c->comm.rank];
+    const float* base = c->comm_on ? c->comm.peer_arenas[c->comm.rank] : c->opt.grads;
+    const size_t arena_floats = c->comm_on ? c->comm.arena_floats : (c->opt.n + 3) & ~static_cast<size_t>(3);
     const float* lo = b == 0 ? grads[c->up[0].g_w] : grads[c->conv[c->enc1[b == 1 ? enc_split : 0]].g_w];
-    const float* hi = b == 0 ? base + c->comm.arena_floats
+    const float* hi = b == 0 ? base + arena_floats
                              : (b == 1 ? grads[c->up[0].g_w] : grads[c->conv[c->enc1[enc_split]].g_w]);
     if (hi <= lo) return 0;
-    CRIMAC_REQUIRE(lo >= base && hi <= base + c->comm.arena_floats && (lo - base) % 4 == 0,
-                   "gradient tensors are not views of the symmetric arena given to crimac_set_comm (parameters() order, 16-byte aligned)");
+    CRIMAC_REQUIRE(lo >= base && hi <= base + arena_floats && (lo - base) % 4 == 0,
+                   "gradient tensors are not views of the flat arena given to crimac_set_comm / crimac_set_optimizer (parameters() order, 16-byte aligned)");
+    CRIMAC_REQUIRE(!(c->comm_on && opt_on) || c->opt.grads == base, "crimac_set_optimizer: grads must be the arena of crimac_set_comm");
     size_t count = static_cast<size_t>(hi - lo);
     count = (count + 3) & ~static_cast<size_t>(3);   // the arena is padded to a multiple of 4 floats
+    const size_t off = static_cast<size_t>(lo - base);
     cudaStream_t cs = st;
     if (c->overlap) {
+      // the bucket's gradients are final once the main stream (BatchNorm / bias gradients) and the side stream (weight
+      // gradients, un-pack) have reached this point; exchange and optimizer then run beside the rest of backward
       CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_bk_main[b], st));
       CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_bk_side[b], c->side));
       CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bk_main[b], 0));
       CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_bk_side[b], 0));
       cs = c->comm_stream;
     }
-    return crimac_peer_allreduce(c->comm.peer_arenas, c->comm.peer_pads, c->comm.multicast_arena, c->comm.local_state,
-                                 c->comm.rank, c->comm.world, b, static_cast<size_t>(lo - base), count, c->comm.ctas, cs);
+    if (c->comm_on) {
+      int r = crimac_peer_allreduce(c->comm.peer_arenas, c->comm.peer_pads, c->comm.multicast_arena, c->comm.local_state,
+                                    c->comm.rank, c->comm.world, b, off, count, c->comm.ctas, cs);
+      if (r) return r;
+    }
+    if (opt_on && off < c->opt.n) {
+      // SGD(momentum) on this bucket's slice right behind its exchange: nothing later in this backward reads the fp32
+      // parameters of a closed bucket (the GEMMs use the bf16 operands packed at the start of the step, BatchNorm
+      // backward the scale / shift saved in forward), and the next step's re-pack is ordered behind the final join
+      const size_t n = std::min(count, c->opt.n - off);
+      ProfScope ps("sgd", 0, 16.0 * n, cs);
+      int r = crimac_sgd_step(c->opt.params + off, c->opt.momentum + off, c->opt.grads + off, n, c->opt.lr,
+                              c->opt.momentum_coef, c->opt.gscale, cs);
+      if (r) return r;
+    }
+    return 0;
   };
 
   // head
@@ -1099,7 +1121,7 @@ static int backward_impl(crimac_ctx* c, const void* const* state, const float* x
   if (c->overlap) {
     CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_join, c->side));
     CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
-    if (c->comm_on) {
+    if (c->comm_on || (c->opt_on && head_done)) {
       CRIMAC_CHECK_CUDA(cudaEventRecord(c->ev_comm, c->comm_stream));
       CRIMAC_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_comm, 0));
     }
@@ -1218,5 +1240,25 @@ extern "C" int crimac_preprocess_staged(crimac_ctx* c, const float* sv, int F, i
     return rc;
   }
   c->staged_nb = n;
+  return 0;
+}
+
+// Fused optimizer: from now on every crimac_backward / crimac_train_step on this context also applies
+// v = momentum*v + g*gscale ; p -= lr*v (torch.optim.SGD(momentum), pipeline.py:156,178) to each gradient bucket as soon
+// as it is final (and, data parallel, all-reduced) - on the communication stream, beside the rest of backward.
+// cfg->params / momentum / grads are flat fp32 arrays in parameters() order; the `grads` table of those calls must point
+// into cfg->grads.  gscale = 1/world.  cfg == NULL (or params == NULL) switches it off.  lr is baked into the launch: call
+// again when the schedule changes it (and re-capture a CUDA graph of the step).
+extern "C" int crimac_set_optimizer(crimac_ctx* c, const crimac_optimizer_config* cfg) {
+  CRIMAC_REQUIRE(c != nullptr && c->cfg.train, "train context required");
+  if (cfg == nullptr || cfg->params == nullptr) {
+    c->opt_on = false;
+    return 0;
+  }
+  CRIMAC_REQUIRE(cfg->momentum != nullptr && cfg->grads != nullptr && cfg->n > 0, "NULL array");
+  CRIMAC_REQUIRE(((reinterpret_cast<uintptr_t>(cfg->params) | reinterpret_cast<uintptr_t>(cfg->momentum) |
+                   reinterpret_cast<uintptr_t>(cfg->grads)) & 15) == 0, "arrays must be 16-byte aligned");
+  c->opt = *cfg;
+  c->opt_on = true;
   return 0;
 }

@@ -38,6 +38,18 @@ class _CommConfig(ctypes.Structure):
     ]
 
 
+class _OptConfig(ctypes.Structure):
+    _fields_ = [
+        ("params", ctypes.c_void_p),
+        ("momentum", ctypes.c_void_p),
+        ("grads", ctypes.c_void_p),
+        ("n", ctypes.c_size_t),
+        ("lr", ctypes.c_float),
+        ("momentum_coef", ctypes.c_float),
+        ("gscale", ctypes.c_float),
+    ]
+
+
 AR_PAD_BYTES = 8 * 2 * 16 * 4      # CRIMAC_AR_PAD_BYTES
 AR_STATE_BYTES = 8 * 8             # 8 bytes per bucket, CRIMAC_AR_MAX_BUCKETS = 8
 
@@ -120,6 +132,11 @@ class Context:
         """Switch the bucketed peer-memory gradient all-reduce of this context on (a _CommConfig) or off (None)."""
         self._comm = comm   # keep the structure (and the pointers in it) alive
         _lib.check(self.L.crimac_set_comm(self.handle, ctypes.byref(comm) if comm is not None else None), "crimac_set_comm")
+
+    def set_optimizer(self, opt):
+        """Fuse SGD(momentum) into this context's backward, per gradient bucket (an _OptConfig), or switch it off (None)."""
+        self._opt = opt
+        _lib.check(self.L.crimac_set_optimizer(self.handle, ctypes.byref(opt) if opt is not None else None), "crimac_set_optimizer")
 
     # ---- tables
     def state_table(self, tensors):

@@ -264,6 +264,14 @@ class _NativePlumbing:
             if key[2]:
                 eng.set_comm(comm)
 
+    def _set_native_opt(self, opt):
+        """trainer.Trainer: fuse the SGD(momentum) update into the native backward of every train context of this model
+        (engine._OptConfig; None switches it off).  train_step_fused then ALSO updates the parameters."""
+        self._native_opt = opt
+        for key, eng in _ENGINES.get(self, {}).items():
+            if key[2]:
+                eng.set_optimizer(opt)
+
     def _meta_head_channels(self):
         return 0
 
@@ -312,6 +320,9 @@ class _NativePlumbing:
             comm = getattr(self, "_native_comm", None)
             if train and comm is not None:
                 eng.set_comm(comm)    # data parallel: gradients are exchanged over peer memory inside backward
+            opt = getattr(self, "_native_opt", None)
+            if train and opt is not None:
+                eng.set_optimizer(opt)
         return eng
 
     def _versions(self):

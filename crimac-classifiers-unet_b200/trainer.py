@@ -83,8 +83,12 @@ def reduce_gradients(flat_grads, world):
 
 
 class Trainer:
+    """One optimisation step per call (`step`, `fit_host`, `fit_survey`).  Binding a Trainer to a model fuses the
+    SGD(momentum) update into the model's native train step: `model.train_step_fused(...)` then ALSO updates the
+    parameters (the autograd path `model(x)` / `loss.backward()` never does)."""
+
     def __init__(self, model, lr=0.005, momentum=0.95, lr_reduction=0.5, lr_step=1000, class_weight=(10.0, 300.0, 250.0),
-                 use_cuda_graph=None, exchange=None, exchange_ctas=0):
+                 use_cuda_graph=None, exchange=None, exchange_ctas=0, fused_optimizer=True):
         # defaults: reference configs/config_baseline.yaml:28-31,38 and pipeline.py:135
         self.model = model
         self.lr, self.momentum = float(lr), float(momentum)
@@ -120,10 +124,40 @@ class Trainer:
         if self.world > 1:
             self.exchange = exchange if exchange is not None else ("peer" if dev.type == "cuda" else "nccl")
             if self.exchange == "peer":
-                self.peer = PeerGradientExchange(total, dev, ctas=exchange_ctas)
-                model._grad_arena = self.peer.arena[:total]       # train_step_fused seats every p.grad in here
-                model._set_native_comm(self.peer.comm)
+                # symmetric memory needs peer access between all GPUs of the process group (one NVSwitch node); if the
+                # platform cannot provide it, every rank falls back - loudly, and together - to one ncclAllReduce per step
+                try:
+                    self.peer = PeerGradientExchange(total, dev, ctas=exchange_ctas)
+                    ok = torch.ones(1, device=dev)
+                except Exception as exc:          # noqa: BLE001 - any failure of the symmetric-memory plumbing
+                    import warnings
+                    warnings.warn(f"peer-memory gradient exchange unavailable ({exc!r}); using ncclAllReduce after backward")
+                    self.peer = None
+                    ok = torch.zeros(1, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if ok.item() < 1:
+                    self.peer, self.exchange = None, "nccl"
+                else:
+                    model._grad_arena = self.peer.arena[:total]       # train_step_fused seats every p.grad in here
+                    model._set_native_comm(self.peer.comm)
             self.broadcast_parameters(0)   # DDP semantics: every replica starts from rank 0's weights and buffers
+        # The SGD(momentum) update is fused into the native backward, bucket by bucket (crimac_set_optimizer): a closed
+        # bucket is updated on the communication stream while the rest of backward still runs.  Not with exchange="nccl"
+        # (the all-reduce only happens after backward) and not for holders without the native plumbing (tests).
+        self.fused_optimizer = bool(fused_optimizer) and self.exchange != "nccl" and dev.type == "cuda" and hasattr(model, "_set_native_opt")
+        if self.fused_optimizer:
+            if getattr(model, "_grad_arena", None) is None or model._grad_arena.numel() != total:
+                self._arena_full = torch.zeros((total + 1023) // 1024 * 1024, dtype=torch.float32, device=dev)
+                model._grad_arena = self._arena_full[:total]
+            self._bind_optimizer()
+
+    def _bind_optimizer(self):
+        """(Re-)bind the fused optimizer of the model's native train contexts to the current learning rate."""
+        opt = _engine._OptConfig()
+        opt.params, opt.momentum = self.flat_params.data_ptr(), self.flat_momentum.data_ptr()
+        opt.grads, opt.n = self.model._grad_arena.data_ptr(), self.flat_params.numel()
+        opt.lr, opt.momentum_coef, opt.gscale = self.lr, self.momentum, 1.0 / self.world
+        self.model._set_native_opt(opt)
 
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank `src`'s weights and BN buffers."""
@@ -187,6 +221,8 @@ class Trainer:
         """Optimizer (+ the NCCL gradient exchange in the "nccl" A/B mode; with the peer exchange the gradients were
         already all-reduced inside backward).  A NCCL all-reduce is never captured in a graph (a captured collective
         keeps communicator resources alive and made process-group teardown hang in our runs)."""
+        if self.fused_optimizer:
+            return                                        # applied inside backward, bucket by bucket
         grads = self.model._grad_arena
         if self.exchange == "nccl":
             gscale = reduce_gradients(grads, self.world)  # NCCL over NVLink / NVSwitch
@@ -206,6 +242,8 @@ class Trainer:
         self.iteration += 1
         if self.lr_step > 0 and self.iteration % self.lr_step == 0:
             self.lr *= self.lr_reduction  # ExponentialLR stepped every lr_step iterations (pipeline.py:157,188-189)
+            if self.fused_optimizer:
+                self._bind_optimizer()    # the learning rate is a launch argument of the fused update (graph re-captured)
 
     def step(self, x, labels):
         """One optimisation step on device tensors; returns the replica's loss as a 0-dim device tensor."""

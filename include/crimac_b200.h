@@ -138,6 +138,17 @@ typedef struct crimac_comm_config {
  * or off (NULL); see csrc/net_api.cu.  The gradient pointers of those calls must then be views of peer_arenas[rank]. */
 int crimac_set_comm(crimac_ctx* ctx, const crimac_comm_config* cfg);
 
+typedef struct crimac_optimizer_config {
+  float* params;        /* flat fp32 parameters, parameters() order (the module's tensors are views of it)          */
+  float* momentum;      /* flat fp32 momentum buffer                                                               */
+  const float* grads;   /* flat fp32 gradient arena the `grads` table points into                                  */
+  size_t n;             /* number of parameters                                                                    */
+  float lr, momentum_coef, gscale;   /* v = momentum_coef*v + g*gscale ; p -= lr*v  (gscale = 1/world)            */
+} crimac_optimizer_config;
+/* Fuse optim.SGD(momentum).step() (pipeline.py:156,178) into crimac_backward / crimac_train_step, bucket by bucket,
+ * overlapped with the rest of backward; NULL switches it off.  See csrc/net_api.cu. */
+int crimac_set_optimizer(crimac_ctx* ctx, const crimac_optimizer_config* cfg);
+
 /* Patch gather + sv->dB transform.  sv_dev: fp32 (F, R, P) preloaded pings [frequency][range][ping] whose column 0 is
  * survey ping data_ping0; centres_dev: int32 (n,2) patch centres (y, x) in survey coordinates (batch/samplers/
  * gridded.py:22-54); out_dev: fp32 NCHW (n, F, ph, pw) = clip(10*log10(sv+1e-10), -75, 0) with out-of-data and
