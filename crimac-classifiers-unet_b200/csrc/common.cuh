@@ -89,6 +89,7 @@ struct WgradHaloParams {
   int k_tiles_total;
   int splits;
   int s_tiles, f_tiles;  // Cs/64, Cf/64
+  int nf;                // 64: nine taps per CTA, 64-wide X tiles; 128: 128-wide X tiles, taps split over two CTA kinds
   float* dw;             // scratch [9][Cs][Cf] fp32
   float* slabs;          // deterministic mode: per-split slabs, see WgradParams
   long slab_stride;

@@ -471,6 +471,8 @@ int build(crimac_ctx* c, void* ws, size_t* bytes_out, bool encode_maps) {
         // measured on B200 (profiles/): the 64x64-channel halo tiles win up to Cout*Cin = 256*128, beyond that the
         // 128 x 256 one-tap tiles re-read fewer operand bytes per FLOP
         L.wg_use_halo = static_cast<long>(L.cout) * L.cin <= 256L * 128L;
+        // 128-wide X tiles where Cin allows: 2/3 of the shared-memory traffic per FLOP (the N = 64 tiles are port-bound)
+        w.nf = (L.cin % 128 == 0) ? 128 : 64;
         WgradParams& wt = L.wg_tap;
         wgeom(wt, H, W, L.cout, L.cin, L.bn_wg, 9, 0);
         wt.dw = L.wg_scratch;
@@ -562,7 +564,7 @@ void set_batch(WgradParams& p, int nb) {
 void set_batch(WgradHaloParams& p, int nb) {
   p.NB = nb;
   p.k_tiles_total = nb * p.tiles_x * p.tiles_y;
-  const int tiles = p.s_tiles * p.f_tiles;
+  const int tiles = p.s_tiles * p.f_tiles;   // nf = 128: Cf/128 tiles x 2 CTA kinds = the same count
   int splits = (2 * device_num_sms()) / tiles;
   if (splits > p.k_tiles_total / 8) splits = p.k_tiles_total / 8;
   if (splits < 1) splits = 1;

@@ -161,6 +161,7 @@ extern "C" int crimac_op_wgrad_halo(const void* dy, int dy_pitch, int cout, cons
   p.k_tiles_total = NB * p.tiles_x * p.tiles_y;
   p.s_tiles = cout / 64;
   p.f_tiles = cin / 64;
+  p.nf = (cin % 128 == 0) ? 128 : 64;   // as the network does (net_api.cu)
   if (splits <= 0) {
     const int tiles = p.s_tiles * p.f_tiles;
     splits = (2 * device_num_sms() + tiles - 1) / tiles;

@@ -220,12 +220,13 @@ constexpr int WH_TMEM_COLS = 512;
 // NF = channels of the fixed operand (X) per CTA = MMA N.
 //   NF = 64 : five accumulators (tap pairs (8,7) (6,5) (4,3) (2,1) (1,0); the lower half of the last repeats tap 1 and is
 //             discarded) - 20 MMAs of 128x64x16 per k-step; bound by shared-memory bandwidth (6 KB per 32-cycle MMA).
-//   NF = 128: four accumulators x 128 columns = all of TMEM (tap pairs (8,7) (6,5) (3,2) (1,0)); the centre tap 4 is a
-//             plain GEMM done by wgrad_gemm_kernel (taps = 1).  16 MMAs of 128x128x16 per k-step: 8 KB per 64-cycle MMA,
-//             i.e. the operand traffic per FLOP is 2/3 of the NF = 64 variant and no MMA row is wasted.
+//   NF = 128: (Cin a multiple of 128) 128-wide X tiles: 8 KB per 64-cycle MMA, i.e. 2/3 of the shared-memory traffic per
+//             FLOP.  Five 128-column accumulators do not fit TMEM (512 columns), so the nine taps are split over TWO CTAs
+//             (blockIdx.z): kind 0 owns the pairs (8,7) (6,5) (4,3), kind 1 the pairs (2,1) (1,0) (lower half of the
+//             last discarded, as above).  Both kinds load the same operand tiles; the long kind is launched first.
 template <int NF>
 struct WhCfg {
-  static constexpr int GROUPS = (NF == 64) ? 5 : 4;
+  static constexpr int GROUPS = (NF == 64) ? 5 : 3;   // NF = 128: at most three per CTA kind
   static constexpr int STAGE = WH_HALO_SLOT + (NF / 64) * WH_FIXED_BYTES;
   static constexpr int STAGES = (NF == 64) ? 8 : 6;
   static constexpr int SMEM = STAGES * STAGE + 256 + 1024;
@@ -249,6 +250,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
   const int f_tile = blockIdx.x % f_tiles;
   const int s_tile = blockIdx.x / f_tiles;
   const int split = blockIdx.y;
+  const int kind = (NF == 64) ? 0 : blockIdx.z;        // NF = 128: which subset of the tap pairs this CTA owns
+  const int g_run = (NF == 64) ? 5 : (kind == 0 ? 3 : 2);
   const int kt_per = (p.k_tiles_total + p.splits - 1) / p.splits;
   const int kt_begin = split * kt_per;
   const int kt_end = min(p.k_tiles_total, kt_begin + kt_per);
@@ -277,7 +280,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
 
   // tap pairs (first -> MMA rows 0..63, second -> rows 64..127); halo row offsets grow from first to second
   constexpr int PA5[5] = {8, 6, 4, 2, 1}, PB5[5] = {7, 5, 3, 1, 0};
-  constexpr int PA4[4] = {8, 6, 3, 1}, PB4[4] = {7, 5, 2, 0};
+  constexpr int PA3[2][3] = {{8, 6, 4}, {2, 1, 1}}, PB3[2][3] = {{7, 5, 3}, {1, 0, 0}};   // NF = 128, per CTA kind
+  auto pair_a = [&](int g) { return (NF == 64) ? PA5[g] : PA3[kind][g]; };
+  auto pair_b = [&](int g) { return (NF == 64) ? PB5[g] : PB3[kind][g]; };
 
   if (ksteps > 0) {
     if (warp == 0) {
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
       uint32_t off16[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        const int ta = (NF == 64) ? PA5[g] : PA4[g], tb = (NF == 64) ? PB5[g] : PB4[g];
+        const int ta = pair_a(g), tb = pair_b(g);
         const int oa = ((2 - ta / 3) * WH_HALO_W + (2 - ta % 3)) * 128;
         const int ob = ((2 - tb / 3) * WH_HALO_W + (2 - tb % 3)) * 128;
         dtmpl[g] = ptx::make_smem_desc(0, ob - oa, 1024);
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
           const uint32_t row16 = sh16 + static_cast<uint32_t>(r * WH_HALO_W * 8);  // halo row pitch 18 * 128 B
 #pragma unroll
           for (int g = 0; g < G; ++g)
-            ptx::umma_bf16(tmem_base + g * NF, dtmpl[g] + row16 + off16[g], bdesc, idesc, (ks | r) != 0);
+            if (g < g_run) ptx::umma_bf16(tmem_base + g * NF, dtmpl[g] + row16 + off16[g], bdesc, idesc, (ks | r) != 0);
         }
         ptx::umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::STAGES) {
@@ -351,9 +356,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_halo_kernel(const __grid_constan
       ptx::mbar_wait(acc_bar, 0);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int g = 0; g < G; ++g) {
-        const int tap = (NF == 64) ? (half ? PB5[g] : PA5[g]) : (half ? PB4[g] : PA4[g]);
-        const bool live = !(NF == 64 && g == 4 && half == 0);  // lower half of the fifth group repeats tap 1
+      for (int g = 0; g < g_run; ++g) {
+        const int tap = half ? pair_b(g) : pair_a(g);
+        // the lower half of the last (2,1)/(1,0) chain repeats tap 1: discarded
+        const bool live = !(half == 0 && ((NF == 64 && g == 4) || (NF == 128 && kind == 1 && g == 1)));
         const bool direct = (p.splits == 1) || (p.slabs != nullptr);
         float* row = (p.slabs ? p.slabs + split * p.slab_stride : p.dw) + (static_cast<long>(tap) * p.Cs + co) * p.Cf +
                      f_tile * NF;
@@ -461,15 +467,18 @@ namespace {
 template <int NF>
 cudaError_t launch_wh(const WgradHaloParams& p, cudaStream_t stream) {
   if (cudaError_t e = ensure_dynamic_smem(wgrad_halo_kernel<NF>, WhCfg<NF>::SMEM); e != cudaSuccess) return e;
-  dim3 grid(p.s_tiles * (p.Cf / NF), p.splits);
+  dim3 grid(p.s_tiles * (p.Cf / NF), p.splits, NF == 64 ? 1 : 2);
   wgrad_halo_kernel<NF><<<grid, 256, WhCfg<NF>::SMEM, stream>>>(p);
   return cudaGetLastError();
 }
 }  // namespace
 
-// All nine taps per CTA, 64 x 64 channel tiles.  (A 128-wide eight-tap variant - NF = 128, the template parameter is kept -
-// ran the MMAs at 1235 instead of 967 TFLOP/s but needed a separate, L2-bound centre-tap GEMM: net loss, removed.)
-cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) { return launch_wh<64>(p, stream); }
+// p.nf = 64: all nine taps per CTA, 64 x 64 channel tiles.  p.nf = 128 (Cf % 128 == 0): 64 x 128 channel tiles, the nine
+// taps split over two CTA kinds (see WhCfg).
+cudaError_t launch_wgrad_halo(const WgradHaloParams& p, cudaStream_t stream) {
+  if (p.nf == 128) return (p.Cf % 128 == 0) ? launch_wh<128>(p, stream) : cudaErrorInvalidValue;
+  return launch_wh<64>(p, stream);
+}
 
 cudaError_t launch_wgrad_unpack(const float* scratch, float* dw, int M, int N, int taps, int accumulate,
                                 cudaStream_t stream) {
