@@ -61,6 +61,17 @@ struct ConvParams {
   float* head_out;       // NCHW fp32 (NB, n_classes, H, W): probabilities (softmax=1) or logits
   int n_classes;
   int head_softmax;
+  // EPI_HEAD with on-device overlap stitching (sliding-window inference): instead of writing the probabilities of the
+  // whole patch, every kept pixel's classes st_cls[0..st_k) go straight into the chunk's (K, R, Pc) fp16 output -
+  // fill_out_array (save_predict.py:41-65) with the label masks of crimac_stitch, fused into the last conv's epilogue
+  int head_stitch;
+  const int* st_centres;       // (nb, 2) patch centres (y, x), survey coordinates
+  const uint8_t* st_nan;       // (nb, H, W): 1 where frequency 0 was non-finite (or nullptr)
+  const short* st_labels;      // (R, Pc) chunk labels or nullptr (= all background)
+  const int* st_seabed;        // (Pc) or nullptr
+  int st_seabed_pad, st_overlap, st_ping_start, st_pc, st_r, st_k;
+  int st_cls[4];
+  void* st_out;                // __half (K, R, Pc)
 };
 
 struct WgradParams {

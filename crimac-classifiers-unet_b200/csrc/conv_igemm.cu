@@ -21,6 +21,7 @@
 #include "host_util.h"
 #include "ptx.cuh"
 #include "devfn.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -616,10 +617,42 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k) logit[k] *= inv;
           }
+          if (p.head_stitch) {
+            // fill_out_array + the label masks (overlap frame, outside the chunk, non-finite input, below seabed + pad on
+            // background): the same decisions, in the same order, as stitch_kernel (pipeline_kernels.cu)
+            const int ov = p.st_overlap;
+            bool keep = y >= ov && y < p.H - ov && x >= ov && x < p.W - ov;
+            const int y_upper = p.st_centres[2 * img] - p.H / 2 + 1;
+            const int yd = y_upper + y;
+            const int xl = p.st_centres[2 * img + 1] - p.W / 2 + 1 + x - p.st_ping_start;
+            keep = keep && yd >= 0 && yd < p.st_r && xl >= 0 && xl < p.st_pc;
+            if (keep && p.st_nan != nullptr) keep = p.st_nan[(static_cast<long>(img) * p.H + y) * p.W + x] == 0;
+            if (keep) {
+              const int l0 = p.st_labels ? p.st_labels[static_cast<long>(yd) * p.st_pc + xl] : 0;
+              keep = !(l0 == -100 || l0 == -70 || l0 == -50);
+              if (keep && p.st_seabed != nullptr && l0 == 0) {
+                const int win0 = y_upper > 0 ? y_upper : 0;
+                keep = !(yd - win0 >= p.st_seabed_pad && yd - p.st_seabed_pad >= p.st_seabed[xl]);
+              }
+            }
+            if (keep) {
+              __half* so = static_cast<__half*>(p.st_out);
 #pragma unroll
-          for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
-            if (k < p.n_classes)
-              p.head_out[((static_cast<long>(img) * p.n_classes + k) * p.H + y) * p.W + x] = logit[k];
+              for (int kk = 0; kk < 4; ++kk)
+                if (kk < p.st_k) {
+                  float v = 0.f;
+#pragma unroll
+                  for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+                    if (k == p.st_cls[kk]) v = logit[k];
+                  so[(static_cast<long>(kk) * p.st_r + yd) * p.st_pc + xl] = __float2half(v);
+                }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < CRIMAC_MAX_CLASSES; ++k)
+              if (k < p.n_classes)
+                p.head_out[((static_cast<long>(img) * p.n_classes + k) * p.H + y) * p.W + x] = logit[k];
+          }
         }
       }
     }

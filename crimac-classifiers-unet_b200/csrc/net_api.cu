@@ -749,8 +749,18 @@ extern "C" int crimac_prepare(crimac_ctx* c, const void* const* state, int train
   return 0;
 }
 
+struct StitchArgs {
+  const int* centres;
+  const uint8_t* nan_mask;
+  const short* labels;
+  const int* seabed;
+  int seabed_pad, overlap, ping_start, Pc, R, K;
+  int cls[4];
+  void* out;
+};
+
 static int forward_impl(crimac_ctx* c, const void* const* state, const float* x, int nb, float* out, int softmax,
-                        bool train, cudaStream_t st, bool skip_head = false) {
+                        bool train, cudaStream_t st, bool skip_head = false, const StitchArgs* stitch = nullptr) {
   const int sms = device_num_sms();
   const int D = c->D;
   const int last = c->dec2[D - 2];
@@ -815,6 +825,22 @@ static int forward_impl(crimac_ctx* c, const void* const* state, const float* x,
           p.head_out = out;
           p.n_classes = c->cfg.n_classes;
           p.head_softmax = softmax;
+          if (stitch != nullptr) {
+            p.head_stitch = 1;
+            p.head_softmax = 1;
+            p.st_centres = stitch->centres;
+            p.st_nan = stitch->nan_mask;
+            p.st_labels = stitch->labels;
+            p.st_seabed = stitch->seabed;
+            p.st_seabed_pad = stitch->seabed_pad;
+            p.st_overlap = stitch->overlap;
+            p.st_ping_start = stitch->ping_start;
+            p.st_pc = stitch->Pc;
+            p.st_r = stitch->R;
+            p.st_k = stitch->K;
+            for (int k = 0; k < 4; ++k) p.st_cls[k] = stitch->cls[k];
+            p.st_out = stitch->out;
+          }
           epi = EPI_HEAD;
         } else {
           p.out = L.act.ptr;
@@ -1263,4 +1289,25 @@ extern "C" int crimac_set_optimizer(crimac_ctx* c, const crimac_optimizer_config
   c->opt = *cfg;
   c->opt_on = true;
   return 0;
+}
+
+// Sliding-window inference with the overlap stitching fused into the last conv's epilogue: eval forward + softmax, and
+// every kept pixel's classes cls[0..K) go straight into the chunk's (K, R, Pc) fp16 output (fill_out_array,
+// save_predict.py:41-65, with the label masks of crimac_stitch) - the (nb, n_classes, H, W) probability tensor is never
+// written.  x_dev may be NULL after crimac_preprocess_staged (whose nan_dev output is this call's nan_dev input).
+extern "C" int crimac_forward_infer_stitch(crimac_ctx* c, const void* const* state, const float* x, int nb,
+                                           const int32_t* centres, const uint8_t* nan_mask, const int16_t* labels,
+                                           const int32_t* seabed, int seabed_pad, int overlap, int ping_start, int Pc,
+                                           int R, const int32_t* cls, int K, void* out, void* stream) {
+  int rc = check_call(c, state, nb);
+  if (rc) return rc;
+  CRIMAC_REQUIRE(centres != nullptr && out != nullptr && cls != nullptr, "NULL tensor");
+  CRIMAC_REQUIRE(c->prepared_mode == 0, "call crimac_prepare(ctx, state, train=0) first");
+  CRIMAC_REQUIRE(K >= 1 && K <= 4, "K must be 1..4");
+  for (int k = 0; k < K; ++k) CRIMAC_REQUIRE(cls[k] >= 0 && cls[k] < c->cfg.n_classes, "class index out of range");
+  if (x == nullptr) CRIMAC_REQUIRE(c->staged_nb == nb, "x is NULL but crimac_preprocess_staged has not staged exactly nb patches");
+  c->staged_nb = 0;
+  StitchArgs sa{centres, nan_mask, labels, seabed, seabed_pad, overlap, ping_start, Pc, R, K, {0, 0, 0, 0}, out};
+  for (int k = 0; k < K; ++k) sa.cls[k] = cls[k];
+  return forward_impl(c, state, x, nb, nullptr, 1, false, static_cast<cudaStream_t>(stream), false, &sa);
 }

@@ -177,6 +177,18 @@ class Context:
             "crimac_forward_infer",
         )
 
+    def forward_infer_stitch(self, state, nb, centres, nan_mask, out, ping_start, overlap, labels=None, seabed=None,
+                             seabed_pad=10, classes=(1, 2), x=None):
+        """Eval forward + softmax + overlap stitching in the last conv's epilogue (crimac_forward_infer_stitch)."""
+        K, R, Pc = out.shape
+        cls = (ctypes.c_int32 * len(classes))(*classes)
+        _lib.check(
+            self.L.crimac_forward_infer_stitch(self.handle, state, _lib.ptr(x), nb, _lib.ptr(centres), _lib.ptr(nan_mask),
+                                               _lib.ptr(labels), _lib.ptr(seabed), int(seabed_pad), int(overlap),
+                                               int(ping_start), Pc, R, cls, K, _lib.ptr(out), _lib.stream_ptr()),
+            "crimac_forward_infer_stitch",
+        )
+
     def forward_train(self, state, x, logits):
         _lib.check(
             self.L.crimac_forward_train(self.handle, state, _lib.ptr(x), x.shape[0], _lib.ptr(logits), _lib.stream_ptr()),

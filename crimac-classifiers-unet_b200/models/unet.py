@@ -377,6 +377,37 @@ class _NativePlumbing:
         eng.forward_infer_staged(state, n, out, softmax)
         return out, nan_mask
 
+    @torch.no_grad()
+    def predict_stitch_patches(self, sv, data_ping0, centres, patch_hw, out, ping_start, overlap, labels=None,
+                               seabed=None, seabed_pad=10, classes=(1, 2)):
+        """The whole sliding-window step of one batch of patches in 23 launches: patch gather + dB transform written as the
+        first conv's operand, the eval forward, and - in the last conv's epilogue - softmax plus the overlap stitching of
+        save_predict.py:41-65 (fill_out_array) with the label masks (overlap frame, chunk bounds, non-finite input, below
+        seabed + pad): classes `classes` of every kept pixel go straight into `out` (fp16 (K, R, Pc), written in place).
+        Neither the fp32 patch tensor nor the probability tensor exists in HBM."""
+        if self.training:
+            raise RuntimeError("predict_stitch_patches() is an eval-mode call; use model.eval() first")
+        ph, pw = patch_hw
+        n = centres.shape[0]
+        self._check_supported(torch.empty((0, self.in_channels, ph, pw), device=sv.device))
+        if sv.dim() != 3 or sv.shape[0] != self.in_channels or sv.dtype != torch.float32 or not sv.is_contiguous():
+            raise RuntimeError(f"sv must be a contiguous fp32 (F={self.in_channels}, R, P) CUDA tensor")
+        if centres.dtype != torch.int32 or not centres.is_contiguous() or centres.device != sv.device:
+            raise RuntimeError("centres must be a contiguous int32 (n,2) tensor on the device of sv")
+        if out.dtype != torch.float16 or not out.is_contiguous() or out.dim() != 3 or out.shape[0] != len(classes):
+            raise RuntimeError("out must be a contiguous fp16 (len(classes), R, Pc) tensor")
+        eng = self._engine_for_shape(n, ph, pw, sv.device, train=False)
+        state = eng.state_table(self._state_tensors())
+        key = (self._versions(), self._native_gen)
+        if eng.prepared_key != key:
+            eng.prepare(state, False)
+            eng.prepared_key = key
+        nan_mask = torch.empty((n, ph, pw), dtype=torch.uint8, device=sv.device)
+        eng.preprocess_staged(sv, data_ping0, centres, nan_mask)
+        eng.forward_infer_stitch(state, n, centres, nan_mask, out, ping_start, overlap, labels=labels, seabed=seabed,
+                                 seabed_pad=seabed_pad, classes=classes)
+        return out
+
     def _train_forward(self, x, params):
         x = self._prep_input(x)
         if x.requires_grad:

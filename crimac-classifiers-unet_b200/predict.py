@@ -5,8 +5,9 @@ pipeline_train_predict/save_predict.py:137-220 (save_survey_predictions_zarr) wi
         grid of overlapping patches        (batch/samplers/gridded.py:22-54; host arithmetic only)
         crimac_preprocess_staged           gather + NaN fill + sv->dB + clip, straight from the preloaded pings INTO the
                                            first conv's bf16 hi/lo operand (no fp32 patch tensor in between)
-        UNet_Baseline.predict_proba_patches  the tcgen05 forward with the softmax fused
-        crimac_stitch                      overlap-stitch of classes [SANDEEL, OTHER] into (2, range, pings) fp16
+        crimac_forward_infer_stitch        the tcgen05 forward; the last conv's epilogue does the 1x1 head, the softmax AND
+                                           the overlap-stitch of classes [SANDEEL, OTHER] into (2, range, pings) fp16
+        (UNet_Baseline.predict_stitch_patches; crimac_preprocess / predict_proba / crimac_stitch remain as separate steps)
 
 Zarr reading / writing stays with the caller (out of scope: I/O format), which hands in device or host arrays.
 """
@@ -107,7 +108,7 @@ class SurveyPredictor:
     def __init__(self, model, patch_hw=(256, 256), overlap=20, preload_n_pings=20000, batch_size=93, classes=(1, 2),
                  seabed_pad=10, direct=None):
         # direct: preprocessing writes the first conv's operand (predict_proba_patches); default when the model has it
-        self.direct = hasattr(model, "predict_proba_patches") if direct is None else bool(direct)
+        self.direct = hasattr(model, "predict_stitch_patches") if direct is None else bool(direct)
         self.model, self.patch_hw, self.overlap = model, tuple(patch_hw), int(overlap)
         self.preload_n_pings, self.batch_size = int(preload_n_pings), int(batch_size)
         self.classes, self.seabed_pad = tuple(classes), int(seabed_pad)
@@ -132,10 +133,15 @@ class SurveyPredictor:
         for i in range(0, centres.shape[0], self.batch_size):
             c = centres[i:i + self.batch_size].contiguous()
             if self.direct:
-                probs, nan_mask = self.model.predict_proba_patches(sv, data_ping0, c, self.patch_hw)
-            else:       # two-step form (kept for models without predict_proba_patches and as the A/B of the tests)
-                x, nan_mask = _engine.preprocess(sv, data_ping0, c, self.patch_hw)
-                probs = self.model.predict_proba(x)
+                # one native sequence per batch: gather + dB straight into the first conv's operand, forward, and the
+                # stitch in the last conv's epilogue (no patch tensor, no probability tensor)
+                self.model.predict_stitch_patches(sv, data_ping0, c, self.patch_hw, out, start, self.overlap,
+                                                  labels=labels, seabed=seabed, seabed_pad=self.seabed_pad,
+                                                  classes=self.classes)
+                continue
+            # three-step form (kept as the A/B of the tests): fp32 patches -> probabilities -> crimac_stitch
+            x, nan_mask = _engine.preprocess(sv, data_ping0, c, self.patch_hw)
+            probs = self.model.predict_proba(x)
             _engine.stitch(probs, c, nan_mask, out, start, self.overlap, labels=labels, seabed=seabed,
                            seabed_pad=self.seabed_pad, classes=self.classes)
         return out

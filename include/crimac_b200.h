@@ -79,6 +79,13 @@ int crimac_prepare(crimac_ctx* ctx, const void* const* state, int train, void* s
  * out_dev: fp32 NCHW (nb, n_classes, H, W): class probabilities (softmax != 0) or raw logits. */
 int crimac_forward_infer(crimac_ctx* ctx, const void* const* state, const float* x_dev, int nb, float* out_dev,
                          int softmax, void* stream);
+/* The same eval forward with softmax AND the overlap stitching of crimac_stitch fused into the last conv's epilogue:
+ * classes cls[0..K) of every kept pixel go straight into out_dev (K, R, Pc) fp16; no probability tensor is written.
+ * Arguments as crimac_stitch; x_dev may be NULL after crimac_preprocess_staged. */
+int crimac_forward_infer_stitch(crimac_ctx* ctx, const void* const* state, const float* x_dev, int nb,
+                                const int32_t* centres_dev, const uint8_t* nan_dev, const int16_t* labels_dev,
+                                const int32_t* seabed_dev, int seabed_pad, int overlap, int ping_start, int Pc, int R,
+                                const int32_t* cls, int K, void* out_dev, void* stream);
 /* Train-mode forward (batch statistics, running-stat update, activations kept for backward). logits_dev as above. */
 int crimac_forward_train(crimac_ctx* ctx, const void* const* state, const float* x_dev, int nb, float* logits_dev,
                          void* stream);

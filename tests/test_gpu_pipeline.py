@@ -213,3 +213,36 @@ def test_metadata_channels_kernel_against_reference_golden(E, golden_dir):
         worst = max(worst, ((x[0, F_:] - want).abs() / want.abs().clamp_min(1.0)).max().item())
     print(f"metadata channels: worst relative deviation {worst:.2e}")
     assert worst <= 2e-7                                         # double arithmetic on both sides, one fp32 rounding
+
+
+def test_stitching_in_the_head_epilogue_equals_the_three_step_form(E, pkg):
+    """SurveyPredictor's default path (preprocessing -> first conv operand, forward, stitch in the last conv's epilogue:
+    crimac_preprocess_staged + crimac_forward_infer_stitch) against the three separate steps (crimac_preprocess,
+    predict_proba, crimac_stitch) on a survey with NaNs, a seabed, chunk labels carrying every mask code and patches
+    hanging over all four edges: the stitched fp16 arrays must be bit-identical."""
+    Mm = importlib.import_module("crimac_unet_b200.models.unet")
+    Pr = importlib.import_module("crimac_unet_b200.predict")
+    torch.manual_seed(0)
+    rng = np.random.default_rng(1)
+    Fq, NP, R, patch, ov, preload = 4, 700, 150, (64, 64), 8, 300
+    sv = (10.0 ** rng.uniform(-9, -2, size=(Fq, R, NP))).astype(np.float32)
+    sv[0, 40:44, 90:130] = np.nan
+    seabed = (110 + 15 * np.sin(np.arange(NP) / 30.0)).astype(np.int32)
+    labels = rng.choice(np.array([0, 0, 0, 1, 2, -100, -70, -50], dtype=np.int16), size=(R, NP))
+    m = Mm.UNet_Baseline(3, Fq, depth=3)
+    m.load_state_dict(O.trained_like_state(m.state_dict(), 0, head_gain=2.0))
+    m = m.to(dev).eval()
+    sv_dev, sb_dev, lab_dev = torch.from_numpy(sv).to(dev), torch.from_numpy(seabed).to(dev), torch.from_numpy(labels).to(dev)
+
+    def load(d0, d1, s, e):
+        return sv_dev[:, :, d0:d1].contiguous(), lab_dev[:, s:e].contiguous(), sb_dev[s:e].contiguous()
+
+    outs = {}
+    for direct in (True, False):
+        pred = Pr.SurveyPredictor(m, patch, ov, preload, batch_size=7, direct=direct)
+        outs[direct] = {(s, e): o.clone() for s, e, o in
+                        pred.predict_survey(load, NP, R, seabed_max_of=lambda s, e: int(seabed[s:e].max()))}
+    assert outs[True].keys() == outs[False].keys() and len(outs[True]) == 3
+    for k in outs[True]:
+        assert torch.equal(outs[True][k], outs[False][k])
+        assert (outs[True][k] != 0).float().mean().item() > 0.2
