@@ -246,3 +246,39 @@ def test_stitching_in_the_head_epilogue_equals_the_three_step_form(E, pkg):
     for k in outs[True]:
         assert torch.equal(outs[True][k], outs[False][k])
         assert (outs[True][k] != 0).float().mean().item() > 0.2
+
+
+def test_survey_edge_cases_short_and_shallow(E, pkg):
+    """Ragged surveys (the reference's loop has no special cases for them, save_predict.py:160-171): fewer pings than one
+    patch width, fewer range bins than one patch height, a last chunk shorter than preload_n_pings, no seabed / labels.
+    Product (fused path) against the oracle pipeline: same written-pixel set, values within 2.5e-2."""
+    Mm = importlib.import_module("crimac_unet_b200.models.unet")
+    Pr = importlib.import_module("crimac_unet_b200.predict")
+    torch.manual_seed(0)
+    m = Mm.UNet_Baseline(3, 4, depth=3)
+    m.load_state_dict(O.trained_like_state(m.state_dict(), 0, head_gain=2.0))
+    m = m.to(dev).eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    patch, ov = (64, 64), 8
+    for NP, R, preload in ((50, 40, 100), (230, 70, 100)):
+        rng = np.random.default_rng(NP)
+        sv = (10.0 ** rng.uniform(-9, -2, size=(4, R, NP))).astype(np.float32)
+        sv_dev = torch.from_numpy(sv).to(dev)
+        pred = Pr.SurveyPredictor(m, patch, ov, preload, batch_size=5)
+        got = {(s, e): o.float().cpu().numpy() for s, e, o in
+               pred.predict_survey(lambda d0, d1, s, e: sv_dev[:, :, d0:d1].contiguous(), NP, R)}
+        assert [k for k in got] == [tuple(int(v) for v in r) for r in P.get_data_split([[0, NP]], preload)]
+        for (s, e), o in got.items():
+            grid = P.get_data_grid(s, e, 0, R, patch, ov)
+            d0, d1 = P.preload_extents(grid, NP, patch[1])
+            ref = np.zeros((2, R, e - s))
+            for c in grid:
+                d = P.gather_data(sv[:, :, d0:d1], c, d0, patch)
+                l = P.mask_overlap(P.gather_labels(np.zeros((R, e - s)), c, s, patch), ov)
+                d, l = P.data_transform(d, l)
+                with torch.no_grad():
+                    p = O.softmax_probs(O.unet_forward(sd, torch.from_numpy(d.astype(np.float32))[None])).numpy()[0]
+                P.fill_out_array(ref, p, l.astype(np.int16), c, s)
+            assert np.array_equal(o != 0, ref.astype(np.float16) != 0)
+            assert (o != 0).all()                                     # no seabed, no NaNs: every pixel of the chunk is written
+            assert np.abs(o - ref).max() <= 2.5e-2

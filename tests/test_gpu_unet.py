@@ -750,6 +750,39 @@ def test_decoder_variants_against_reference_golden(M, golden_dir, variant):
     _check_tf_gradients(got, tf_g, variant)
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 32, 96), (3, 80, 48), (1, 16, 32)])
+def test_rectangular_ragged_patches_and_batch_one(M, B, H, W):
+    """Shapes off the beaten path: a single patch per batch, non-square patches whose sides are not multiples of the
+    16 x 8 / 8 x 16 output tiles, the smallest legal patch of depth 5 (one row of two values per channel at the bottom).
+    Eval probabilities, train loss, BatchNorm buffers against the fp32 oracle; every gradient tensor against fp32
+    autograd at the native forward state."""
+    E = importlib.import_module("crimac_unet_b200.engine")
+    torch.manual_seed(B * H + W)
+    m = M.UNet_Baseline(3, 4)
+    x = O.synthetic_echogram(B, 4, H, W, seed=H)
+    _populate_bn(m, x)
+    m = m.to(dev).eval()
+    x = x.to(dev)
+    y = O.synthetic_labels(B, H, W, seed=W, device=dev)
+    with torch.no_grad():
+        ref = O.softmax_probs(O.unet_forward(_state(m), x))
+        got = m.predict_proba(x)
+    assert (got - ref).abs().max().item() <= PROB_TOL
+    m.train()
+    st0 = _state(m)
+    ref_logits, ref_loss, ref_g, ref_stats = O.train_step(st0, x, y)
+    loss = m.train_step_fused(x, y, torch.tensor(O.CLASS_WEIGHTS, device=dev))
+    assert abs(loss.item() - ref_loss.item()) < 3e-3 * abs(ref_loss.item())
+    sd = m.state_dict()
+    for k, v in ref_stats.items():
+        if "num_batches" not in k:
+            assert _rel(sd[k], v) < 2e-2, k
+    got_g = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    m.load_state_dict(st0)
+    tf_loss, tf_g = _teacher_forced_gradients(m, m._engine_for(x, train=True), E, x, y, B)
+    _check_tf_gradients(got_g, tf_g, f"{B}x4x{H}x{W}")
+
+
 def test_deterministic_mode_is_bit_reproducible(M):
     """The reference's fix_seeds (utils/general.py:120-128) sets torch.backends.cudnn.deterministic = True.  The native
     path honours the same switch: split-K weight-gradient partial tiles are stored per split and summed in a fixed order
