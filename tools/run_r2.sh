@@ -46,7 +46,11 @@ ncu_elem)
   $CMD > gpurun_out/plain4.log 2>&1 && \
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:bn_bwd|bn_apply|bn_finalize|head_ce|first_conv|partial_sum|view_colsum|unpack|pack_|sgd" -c 60 -s 330 -o gpurun_out/prof_elem $CMD > gpurun_out/ncu_elem.log 2>&1
   echo "ncu elem exit $?"
-  python tools/ncu_summary.py report gpurun_out/prof_elem.ncu-rep gpurun_out/ncu_elem_train.csv; rm -f gpurun_out/prof_elem.ncu-rep ;;
+  python tools/ncu_summary.py report gpurun_out/prof_elem.ncu-rep gpurun_out/ncu_elem_train.csv; rm -f gpurun_out/prof_elem.ncu-rep
+  $CMD > gpurun_out/plain6.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:pool_kernel|head_ce_fused|sgd_kernel|upsample|wgrad_unpack" -c 16 -s 32 -o gpurun_out/prof_elem2 $CMD > gpurun_out/ncu_elem2.log 2>&1
+  echo "ncu elem2 exit $?"
+  python tools/ncu_summary.py report gpurun_out/prof_elem2.ncu-rep gpurun_out/ncu_elem2_train.csv; rm -f gpurun_out/prof_elem2.ncu-rep ;;
 ncu_infer)
   CMD="python bench.py --mode infer --steps 1 --warmup 3 --no-cpu-baseline"
   $CMD > gpurun_out/plain5.log 2>&1 && \
