@@ -94,7 +94,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  ptx::pdl_trigger();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.a_map[0]);
     ptx::prefetch_tmap(&p.b_map);
@@ -122,9 +121,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const __gri
   if (HAS_STATS && warp >= 4) {
     for (int i = threadIdx.x - 128; i < 2 * p.n_tiles * BLOCK_N; i += EPI_THREADS) s_acc[i] = 0.f;
   }
-  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail; nothing before
-  // this line reads or writes global memory
-  ptx::pdl_wait();
   if (EPI == EPI_HEAD && warp >= 4) {
     const int e = threadIdx.x - 128;
     for (int i = e; i < p.n_classes * 64; i += EPI_THREADS) s_head[i] = p.head_w[i];
@@ -712,9 +708,11 @@ cudaError_t launch_one(const ConvParams& p, int num_sms, cudaStream_t stream) {
     ConvParams q = p;
     q.resident = 0;
     if (p.n_tiles == 1 && wbytes <= Cfg::RES_MAX_B) q.resident = (wbytes + 3 * HALO_SLOT <= Cfg::OPERAND_BYTES) ? 3 : 2;
-    return launch_chained(kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM_BYTES, stream, q);
+    kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(q);
+    return cudaGetLastError();
   }
-  return launch_chained(kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM_BYTES, stream, p);
+  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
 }
 
 }  // namespace

@@ -6,7 +6,6 @@
 // All activation tensors are NHWC bf16 "views" (pointer, pitch) so that concat buffers are written/read in place.
 #include "host_util.h"
 #include "devfn.cuh"
-#include "ptx.cuh"
 #include <cstdlib>
 
 namespace {
@@ -158,8 +157,6 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
   double s1 = 0.0, s2 = 0.0;
-  ptx::pdl_trigger();
-  ptx::pdl_wait();
   if (c < C) {
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains; partial rows are few and O(1e4) each
     int t = tl;
@@ -219,12 +216,10 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 template <bool POOL>
 __global__ void __launch_bounds__(256) bn_apply_kernel(View raw, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, View act, View pool,
-                                                       uint16_t* __restrict__ pool_arg, int trig) {
+                                                       uint16_t* __restrict__ pool_arg) {
   const int groups = raw.C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   float sc[8], sh[8];
-  if (trig) ptx::pdl_trigger();
-  ptx::pdl_wait();
   ldg8f(scale + g * 8, sc);
   ldg8f(shift + g * 8, sh);
   const unsigned stride = gridDim.x * ppb;
@@ -781,8 +776,6 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(View dact, View r
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
   float sc[8], sh[8];
-  ptx::pdl_trigger();
-  ptx::pdl_wait();
   ldg8f(scale + g * 8, sc);
   ldg8f(shift + g * 8, sh);
   float acc[2][8];
@@ -857,8 +850,6 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_pool_kernel(const uint16
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const unsigned npool = static_cast<unsigned>(raw.N) * (raw.H >> 1) * (raw.W >> 1);
   float sc[8], sh[8];
-  ptx::pdl_trigger();
-  ptx::pdl_wait();
   ldg8f(scale + g * 8, sc);
   ldg8f(shift + g * 8, sh);
   float acc[2][8];
@@ -906,8 +897,6 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
                                                                    const float* invstd, float* zero_out) {
   // block = 8 channels x 32 part-lanes (short dependent load chains)
   __shared__ double sh[NQ][32][8];
-  ptx::pdl_trigger();
-  ptx::pdl_wait();
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
   double a[NQ];
@@ -997,12 +986,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dact, View ra
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd,
                                                               const float* __restrict__ c1, const float* __restrict__ c2,
-                                                              const float* gscale, View draw, int trig) {
+                                                              const float* gscale, View draw) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const long npix = static_cast<long>(raw.N) * raw.H * raw.W;
-  if (trig) ptx::pdl_trigger();
-  ptx::pdl_wait();
   BnBwdCoef k;
   load_bn_bwd_coef(k, g, scale, shift, mean, invstd, c1, c2, gscale);
   const long stride = static_cast<long>(gridDim.x) * ppb;
@@ -1042,12 +1029,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_pool_kernel(const uint16_
                                                                    const float* __restrict__ invstd,
                                                                    const float* __restrict__ c1,
                                                                    const float* __restrict__ c2, const float* gscale,
-                                                                   View draw, int trig) {
+                                                                   View draw) {
   const int C = raw.C, groups = C >> 3, ppb = blockDim.x / groups;
   const int g = threadIdx.x % groups, pl = threadIdx.x / groups;
   const unsigned npool = static_cast<unsigned>(raw.N) * (raw.H >> 1) * (raw.W >> 1);
-  if (trig) ptx::pdl_trigger();
-  ptx::pdl_wait();
   BnBwdCoef k;
   load_bn_bwd_coef(k, g, scale, shift, mean, invstd, c1, c2, gscale);
   const unsigned stride = gridDim.x * ppb;
@@ -1321,11 +1306,6 @@ __global__ void __launch_bounds__(256) pack_convt_all_kernel(const __grid_consta
   }
 }
 
-// experiment switch: CRIMAC_PDL_LATE=1 keeps the kernels in front of a conv from triggering it early
-inline int early_trigger() {
-  static const int v = getenv("CRIMAC_PDL_LATE") != nullptr ? 0 : 1;
-  return v;
-}
 inline int grid_for(long work_items, int threads) {
   long b = (work_items + threads - 1) / threads;
   if (b > kMaxBlocks) b = kMaxBlocks;
@@ -1390,8 +1370,9 @@ cudaError_t launch_first_conv_wgrad(const float* x, const bf16* xs, View draw, i
 cudaError_t launch_bn_finalize(const float* partials, int m_tiles, int C, double count, const float* gamma,
                                const float* beta, float* rm, float* rv, long long* nbt, float momentum, float eps,
                                float* scale, float* shift, float* save_mean, float* save_invstd, cudaStream_t st) {
-  return launch_chained(bn_finalize_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partials, m_tiles, C, count, gamma,
-                        beta, rm, rv, nbt, momentum, eps, scale, shift, save_mean, save_invstd);
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, m_tiles, C, count, gamma, beta, rm, rv, nbt, momentum,
+                                                    eps, scale, shift, save_mean, save_invstd);
+  return cudaGetLastError();
 }
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                                 const float* conv_bias, float eps, int C, float* scale, float* shift,
@@ -1406,12 +1387,12 @@ cudaError_t launch_bn_apply(View raw, const float* scale, const float* shift, Vi
   const int ppb = 256 / (raw.C / 8);
   if (pool.ptr != nullptr) {
     const long items = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2);
-    return launch_chained(bn_apply_kernel<true>, dim3(grid_for(items, ppb)), dim3(256), 0, st, raw, scale, shift, act,
-                          pool, pool_arg, early_trigger());
+    bn_apply_kernel<true><<<grid_for(items, ppb), 256, 0, st>>>(raw, scale, shift, act, pool, pool_arg);
+  } else {
+    const long items = static_cast<long>(raw.N) * raw.H * raw.W;
+    bn_apply_kernel<false><<<grid_for((items + 3) / 4, ppb), 256, 0, st>>>(raw, scale, shift, act, pool, nullptr);
   }
-  const long items = static_cast<long>(raw.N) * raw.H * raw.W;
-  return launch_chained(bn_apply_kernel<false>, dim3(grid_for((items + 3) / 4, ppb)), dim3(256), 0, st, raw, scale,
-                        shift, act, pool, static_cast<uint16_t*>(nullptr), early_trigger());
+  return cudaGetLastError();
 }
 cudaError_t launch_head_fwd(View act, const float* hw, const float* hb, int ncls, float* logits, cudaStream_t st) {
   const long px = static_cast<long>(act.N) * act.H * act.W;
@@ -1498,8 +1479,6 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
   int grid_r = grid < 148 * 3 ? grid : 148 * 3;
   const int ppb = 256 / (C / 8);
   const double count = static_cast<double>(raw.N) * raw.H * raw.W;
-  const size_t red_smem = static_cast<size_t>(ppb) * 2 * C * sizeof(float);
-  cudaError_t e;
   if (pool_arg != nullptr) {
     // dA = dSkip + unpool(dPool) formed on the fly, one thread per pooling window
     if (count > 4.0e9 || dskip.C != C || dpool.C != C || (raw.H & 1) || (raw.W & 1)) return cudaErrorInvalidValue;
@@ -1508,22 +1487,21 @@ cudaError_t launch_bn_bwd(View dact, View raw, const float* scale, const float* 
     if (gw > 148 * 2) gw = 148 * 2;   // two resident blocks per SM: one full wave
     if (gw < 1) gw = 1;
     grid_r = static_cast<int>(gw);
-    e = launch_chained(bn_bwd_reduce_pool_kernel, dim3(grid_r), dim3(256), red_smem, st, pool_arg, dpool, dskip, raw,
-                       scale, shift, partials);
+    bn_bwd_reduce_pool_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(pool_arg, dpool, dskip, raw, scale, shift, partials);
   } else {
-    e = launch_chained(bn_bwd_reduce_kernel, dim3(grid_r), dim3(256), red_smem, st, dact, raw, scale, shift, partials);
+    bn_bwd_reduce_kernel<<<grid_r, 256, ppb * 2 * C * sizeof(float), st>>>(dact, raw, scale, shift, partials);
   }
-  if (e != cudaSuccess) return e;
-  e = launch_chained(partial_sum_finalize_kernel<2>, dim3((C + 7) / 8), dim3(256), 0, st, partials, grid_r, C, count,
-                     dbeta, dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd, dbias);
-  if (e != cudaSuccess) return e;
+  partial_sum_finalize_kernel<2><<<(C + 7) / 8, 256, 0, st>>>(partials, grid_r, C, count, dbeta,
+                                                                dgamma, accumulate, c1c2, c1c2 + C, gscale, mean, invstd,
+                                                                dbias);
   if (pool_arg != nullptr) {
     const long windows = static_cast<long>(raw.N) * (raw.H / 2) * (raw.W / 2);
-    return launch_chained(bn_bwd_apply_pool_kernel, dim3(grid_for(windows, ppb)), dim3(256), 0, st, pool_arg, dpool,
-                          dskip, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw, early_trigger());
+    bn_bwd_apply_pool_kernel<<<grid_for(windows, ppb), 256, 0, st>>>(pool_arg, dpool, dskip, raw, scale, shift, mean, invstd,
+                                                                     c1c2, c1c2 + C, gscale, draw);
+  } else {
+    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(dact, raw, scale, shift, mean, invstd, c1c2, c1c2 + C, gscale, draw);
   }
-  return launch_chained(bn_bwd_apply_kernel, dim3(grid), dim3(256), 0, st, dact, raw, scale, shift, mean, invstd, c1c2,
-                        c1c2 + C, gscale, draw, early_trigger());
+  return cudaGetLastError();
 }
 cudaError_t launch_view_colsum(View v, float* partials, float* out, int accumulate, cudaStream_t st) {
   const int C = v.C;

@@ -1,5 +1,4 @@
 #include "host_util.h"
-#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <cudaTypedefs.h>
@@ -121,14 +120,6 @@ cudaError_t ensure_dynamic_smem_impl(const void* kern, int bytes) {
     done[kern] |= bit;
   }
   return e;
-}
-
-bool crimac_chained_launches() {
-  static const bool on = [] {
-    const char* e = std::getenv("CRIMAC_NO_PDL");
-    return !(e != nullptr && e[0] == '1');
-  }();
-  return on;
 }
 
 int device_num_sms() {

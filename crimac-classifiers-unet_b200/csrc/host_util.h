@@ -63,25 +63,6 @@ template <typename Kern>
 inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
   return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), bytes);
 }
-// Launch `kern` as a programmatic dependent of the previous kernel of `st` (ptx::pdl_trigger / ptx::pdl_wait in the
-// kernels): its CTAs may be scheduled, set up barriers / TMEM and then block in pdl_wait() while the predecessor's last
-// CTAs drain.  Only for kernels that call ptx::pdl_wait() before touching global memory.
-bool crimac_chained_launches();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                  Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = crimac_chained_launches() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
 bool crimac_profiling();  // per-launch event timing is on: kernels are then kept on ONE stream so that times are isolated
 
 // ---- launch accounting + optional per-launch CUDA-event timing (crimac_profile_* in the C-ABI).

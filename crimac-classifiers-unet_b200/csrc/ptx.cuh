@@ -170,11 +170,4 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
   return d;
 }
 
-// Programmatic dependent launch (launch_chained() in host_util.h sets the stream-serialisation attribute): a kernel
-// calls pdl_trigger() at its top so that the next kernel of the stream may be scheduled while this one drains, and
-// pdl_wait() before its first access to global memory another kernel produces.  pdl_wait() returns when every grid
-// this one depends on has COMPLETED and its writes are visible; without the launch attribute both are no-ops.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 }  // namespace ptx

@@ -62,14 +62,6 @@ stress)
   echo "bench stress train exit $?"; cat gpurun_out/bench_stress_train.json; tail -3 gpurun_out/bench_stress_train.err
   timeout 600 python bench.py --mode infer --in-ch 6 --size 512 --batch 64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_stress_infer.json 2> gpurun_out/bench_stress_infer.err
   echo "bench stress infer exit $?"; cat gpurun_out/bench_stress_infer.json; tail -3 gpurun_out/bench_stress_infer.err ;;
-pdl_ab)
-  # programmatic dependent launch A/B: off / on / on without early trigger in front of the convs; train + inference
-  for v in off on late on off; do
-    case $v in off) export CRIMAC_NO_PDL=1; unset CRIMAC_PDL_LATE ;; on) unset CRIMAC_NO_PDL CRIMAC_PDL_LATE ;; late) unset CRIMAC_NO_PDL; export CRIMAC_PDL_LATE=1 ;; esac
-    timeout 300 python bench.py --steps 30 --warmup 5 --quick --no-cpu-baseline 2> gpurun_out/pdl_$v.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('train $v', d['ms_per_step'], d['value'], d['clocks'])"
-    timeout 300 python bench.py --mode infer --steps 30 --warmup 5 --no-cpu-baseline 2>> gpurun_out/pdl_$v.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('infer $v', d['ms_per_step'], d['value'])"
-  done
-  unset CRIMAC_NO_PDL CRIMAC_PDL_LATE ;;
 smoke)
   timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
   echo "smoke exit $?"; tail -5 gpurun_out/smoke.log ;;
