@@ -330,6 +330,47 @@ def survey_subrecord(model, dev, rank, world, E, n_pings=1_000_000, n_range=256,
             "workload": "configs[3]: ONE survey of %d pings x %d range bins, %d-ping chunks, sharded by ping range over %d GPU(s)" % (n_pings, n_range, preload, world)}
 
 
+def reference_loop_subrecord(M, S, dev, B, C, size, steps):
+    """The reference's training loop, statement for statement (pipeline.py:156-181: torch.optim.SGD, ExponentialLR,
+    nn.CrossEntropyLoss(weight), model(inputs), loss.backward(), optimizer.step(), loss.item()), on the native module:
+    what a user gets who swaps the model class and changes nothing else.  Host batches, as a DataLoader hands them over."""
+    import torch
+    from torch import nn, optim
+    torch.manual_seed(1)
+    model = M.UNet_Baseline(3, C).to(dev)
+    optimizer = optim.SGD(model.parameters(), lr=0.005, momentum=0.95)
+    scheduler = optim.lr_scheduler.ExponentialLR(optimizer, gamma=0.5)
+    criterion = nn.CrossEntropyLoss(weight=torch.tensor([10.0, 300.0, 250.0], device=dev), ignore_index=-100)
+    batch = {"data": S.synthetic_echogram(B, C, size, size, seed=300).pin_memory(),
+             "labels": S.synthetic_labels(B, size, size, seed=301).pin_memory()}
+
+    def run(k):
+        for i in range(k):
+            inputs_train = batch["data"].float().to(dev)
+            labels_train = batch["labels"].long().to(dev)
+            model.train()
+            optimizer.zero_grad()
+            outputs_train = model(inputs_train)
+            loss_train = criterion(outputs_train, labels_train)
+            loss_train.backward()
+            optimizer.step()
+            loss_train.item()
+            if (i + 1) % 1000 == 0:
+                scheduler.step()
+
+    run(3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms, "steps": steps,
+            "api": "pipeline.py:156-181 verbatim on crimac_unet_b200 UNet_Baseline: autograd Function over the C-ABI (eager "
+                   "launches), torch CrossEntropyLoss and torch.optim.SGD outside the library; host batch -> device, loss.item() per step"}
+
+
 def parity_subrecord(M, Trainer, S, dev, steps=60):
     """parity printed with the bench line.  A trained-like net (the native trainer runs `steps`
     optimisation steps on a structured workload; there is no checkpoint to download) is copied into the reference's
@@ -583,6 +624,7 @@ def run_b200(args):
                         + f": train step (forward, weighted CE, backward, SGD), fp32 torch CPU, batch 8 (of 32), 1 warm-up + 2 timed steps, {dt:.2f} s/step"}
         if args.mode == "train" and not args.quick:
             parity = parity_subrecord(M, Trainer, O, dev)
+            extra["reference_loop"] = reference_loop_subrecord(M, O, dev, B, C, S, args.steps)
 
     if rank == 0:
         line = {
