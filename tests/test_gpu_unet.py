@@ -182,6 +182,25 @@ def test_fp32_validation_mode_matches_oracle_to_1e4(M, depth, B, H, W, in_ch):
     assert (fast - got).abs().max().item() <= PROB_TOL      # the production path against the validation mode
 
 
+def test_oracle_noise_floor_cpu_against_cuda_fp32(M):
+    """no reference test pins results at this boundary, so the oracle's own noise is bounded instead - the
+    same fp32 restatement evaluated by torch on the host cores (oneDNN) and on the device (cuDNN, TF32 off) on the same
+    seeded input.  The 1e-4 budget of the fp32 validation mode must sit well above this floor."""
+    torch.manual_seed(0)
+    m = M.UNet_Baseline(3, 4)
+    x = O.synthetic_echogram(2, 4, 128, 128, seed=2)
+    _populate_bn(m, x)
+    m.eval()
+    with torch.no_grad():
+        cpu_logits = O.unet_forward(_state(m), x)
+        m = m.to(dev)
+        gpu_logits = O.unet_forward(_state(m), x.to(dev)).cpu()
+    dp = (O.softmax_probs(cpu_logits) - O.softmax_probs(gpu_logits)).abs().max().item()
+    dl = (cpu_logits - gpu_logits).abs().max().item()
+    print(f"oracle noise floor, torch CPU fp32 vs torch CUDA fp32: max|dp|={dp:.2e} max|dlogit|={dl:.2e}")
+    assert dp <= 2e-5 and dl <= 2e-4
+
+
 def test_inference_is_per_patch_and_deterministic(M):
     torch.manual_seed(1)
     m = M.UNet_Baseline(3, 4).to(dev).eval()
