@@ -146,54 +146,92 @@ __global__ void __launch_bounds__(64) first_conv_kernel(const float* __restrict_
 
 // ============================================================================ BN statistics -> scale/shift
 // partials [m_tiles][2][C] (sum, sum of squares) -> batch mean / biased var; running stats (momentum, unbiased var).
+// Row-lane `tl` (of 32) sums rows tl, tl+32, ... of partials[row][NQ][C] for channel c: eight rows per round, all loads
+// of a round in flight before the first add (a round is one L2 round trip instead of one per row).
+template <int NQ>
+__device__ __forceinline__ void column_partial_sums(const float* __restrict__ partials, int nparts, int C, int c, int tl,
+                                                    double& q0, double& q1) {
+  float f[NQ][2];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) f[q][0] = f[q][1] = 0.f;
+  for (int i0 = tl; i0 < nparts; i0 += 8 * 32) {
+    float v[8][NQ];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * 32;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) v[u][q] = i < nparts ? partials[(static_cast<long>(i) * NQ + q) * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) f[q][u & 1] += v[u][q];
+  }
+  q0 = static_cast<double>(f[0][0]) + static_cast<double>(f[0][1]);
+  q1 = NQ > 1 ? static_cast<double>(f[NQ - 1][0]) + static_cast<double>(f[NQ - 1][1]) : 0.0;
+}
+// Sum over the 32 row-lanes of a (8 channels x 32 row-lanes) block; threads with tl == 0 receive the totals.
+// A warp holds 4 row-lanes x 8 channels: two shuffles, then 8 per-warp values per channel through shared memory.
+__device__ __forceinline__ void block_lane_sum8x32(double (&sh)[2][8][8], double& a, double& b) {
+  a += __shfl_xor_sync(0xffffffffu, a, 8);
+  b += __shfl_xor_sync(0xffffffffu, b, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 16);
+  b += __shfl_xor_sync(0xffffffffu, b, 16);
+  const int cl = threadIdx.x & 7, w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) < 8) {
+    sh[0][w][cl] = a;
+    sh[1][w][cl] = b;
+  }
+  __syncthreads();
+  if ((threadIdx.x >> 3) == 0) {
+    a = sh[0][0][cl];
+    b = sh[1][0][cl];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) {
+      a += sh[0][t][cl];
+      b += sh[1][t][cl];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int m_tiles, int C,
                                                           double count, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* running_mean,
                                                           float* running_var, long long* num_batches_tracked,
                                                           float momentum, float eps, float* scale, float* shift,
                                                           float* save_mean, float* save_invstd) {
-  // block = 8 channels x 32 row-lanes: short dependent load chains (the kernel is pure latency)
-  __shared__ double sh[2][32][8];
+  // block = 8 channels x 32 row-lanes.  The kernel is pure latency: every load a thread needs is issued before the
+  // first use (eight partial rows per round; gamma / beta / running statistics up front by the threads that finish).
+  __shared__ double sh[2][8][8];
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
-  double s1 = 0.0, s2 = 0.0;
-  if (c < C) {
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains; partial rows are few and O(1e4) each
-    int t = tl;
-    for (; t + 32 < m_tiles; t += 64) {
-      a0 += partials[static_cast<long>(t) * 2 * C + c];
-      b0 += partials[static_cast<long>(t) * 2 * C + C + c];
-      a1 += partials[static_cast<long>(t + 32) * 2 * C + c];
-      b1 += partials[static_cast<long>(t + 32) * 2 * C + C + c];
+  const bool fin = tl == 0 && c < C;
+  float g = 0.f, b = 0.f, rm = 0.f, rv = 0.f;
+  if (fin) {
+    g = gamma[c];
+    b = beta[c];
+    if (running_mean != nullptr) {
+      rm = running_mean[c];
+      rv = running_var[c];
     }
-    if (t < m_tiles) {
-      a0 += partials[static_cast<long>(t) * 2 * C + c];
-      b0 += partials[static_cast<long>(t) * 2 * C + C + c];
-    }
-    s1 = static_cast<double>(a0) + static_cast<double>(a1);
-    s2 = static_cast<double>(b0) + static_cast<double>(b1);
   }
-  sh[0][tl][cl] = s1;
-  sh[1][tl][cl] = s2;
-  __syncthreads();
-  if (tl == 0 && c < C) {
-    for (int t = 1; t < 32; ++t) {
-      s1 += sh[0][t][cl];
-      s2 += sh[1][t][cl];
-    }
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C) column_partial_sums<2>(partials, m_tiles, C, c, tl, s1, s2);
+  block_lane_sum8x32(sh, s1, s2);
+  if (fin) {
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = gamma[c] * invstd;
+    const float sc = g * invstd;
     scale[c] = sc;
-    shift[c] = beta[c] - static_cast<float>(mean) * sc;
+    shift[c] = b - static_cast<float>(mean) * sc;
     save_mean[c] = static_cast<float>(mean);
     save_invstd[c] = invstd;
     if (running_mean != nullptr) {
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+      running_mean[c] = (1.f - momentum) * rm + momentum * static_cast<float>(mean);
+      running_var[c] = (1.f - momentum) * rv + momentum * static_cast<float>(unbiased);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
@@ -895,51 +933,38 @@ __global__ void __launch_bounds__(256) partial_sum_finalize_kernel(const float* 
                                                                    int accumulate, float* c1, float* c2,
                                                                    const float* gscale, const float* mean,
                                                                    const float* invstd, float* zero_out) {
-  // block = 8 channels x 32 part-lanes (short dependent load chains)
-  __shared__ double sh[NQ][32][8];
+  // block = 8 channels x 32 part-lanes; see column_partial_sums / block_lane_sum8x32
+  __shared__ double sh[2][8][8];
   const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + cl;
-  double a[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) a[q] = 0.0;
-  if (c < C) {
-    float f0[NQ], f1[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) f0[q] = f1[q] = 0.f;
-    int i = tl;
-    for (; i + 32 < nparts; i += 64) {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        f0[q] += partials[(static_cast<long>(i) * NQ + q) * C + c];
-        f1[q] += partials[(static_cast<long>(i + 32) * NQ + q) * C + c];
-      }
+  const bool fin = tl == 0 && c < C;
+  double mu = 0.0, is = 0.0, gs = 1.0;
+  float prev0 = 0.f, prev1 = 0.f;
+  if (fin) {   // everything the finishing threads need, issued before the partial rows
+    if (gscale) gs = static_cast<double>(*gscale);  // incoming gradient was produced unnormalised
+    if (NQ == 2 && mean != nullptr) {
+      mu = static_cast<double>(mean[c]);
+      is = static_cast<double>(invstd[c]);
     }
-    if (i < nparts) {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) f0[q] += partials[(static_cast<long>(i) * NQ + q) * C + c];
+    if (accumulate) {
+      prev0 = out0[c];
+      if (NQ == 2) prev1 = out1[c];
     }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) a[q] = static_cast<double>(f0[q]) + static_cast<double>(f1[q]);
   }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) sh[q][tl][cl] = a[q];
-  __syncthreads();
-  if (tl == 0 && c < C) {
-    const double gs = gscale ? static_cast<double>(*gscale) : 1.0;  // incoming gradient was produced unnormalised
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      for (int t = 1; t < 32; ++t) a[q] += sh[q][t][cl];
-      a[q] *= gs;
-    }
+  double a[2] = {0.0, 0.0};
+  if (c < C) column_partial_sums<NQ>(partials, nparts, C, c, tl, a[0], a[1]);
+  block_lane_sum8x32(sh, a[0], a[1]);
+  if (fin) {
+    a[0] *= gs;
+    a[1] *= gs;
     // BN backward: the second partial is sum g*raw; sum g*xhat = invstd * (sum g*raw - mean * sum g)
-    if (NQ == 2 && mean != nullptr)
-      a[NQ - 1] = static_cast<double>(invstd[c]) * (a[NQ - 1] - static_cast<double>(mean[c]) * a[0]);
-    out0[c] = accumulate ? out0[c] + static_cast<float>(a[0]) : static_cast<float>(a[0]);
+    if (NQ == 2 && mean != nullptr) a[1] = is * (a[1] - mu * a[0]);
+    out0[c] = prev0 + static_cast<float>(a[0]);
     if (zero_out != nullptr && !accumulate) zero_out[c] = 0.f;
     if (NQ == 2) {
-      out1[c] = accumulate ? out1[c] + static_cast<float>(a[NQ - 1]) : static_cast<float>(a[NQ - 1]);
+      out1[c] = prev1 + static_cast<float>(a[1]);
       c1[c] = static_cast<float>(a[0] / count);
-      c2[c] = static_cast<float>(a[NQ - 1] / count);
+      c2[c] = static_cast<float>(a[1] / count);
     }
   }
 }
