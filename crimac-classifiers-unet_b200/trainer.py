@@ -1,9 +1,10 @@
 """Data-parallel training loop body for the native U-Net (reference pipeline_train_predict/pipeline.py:144-203:
 SGD(lr, momentum) + ExponentialLR, one optimizer step per batch).
 
-One process per GPU.  Parameters and gradients live in two flat fp32 arenas so that the gradient exchange is ONE
-NCCL all-reduce over NVLink (the path has no other collective: BatchNorm statistics stay per replica, as in the
-reference which has no SyncBN) and the optimizer is one fused kernel.  Semantics = DistributedDataParallel: the
+One process per GPU.  Parameters and gradients live in two flat fp32 arenas.  The gradient exchange is the library's own
+NVLink peer-memory all-reduce (csrc/peer_allreduce.cu), launched per gradient bucket inside backward and followed by the
+fused SGD update of that bucket; `exchange="nccl"` keeps one ncclAllReduce of the whole arena after backward as the A/B
+baseline.  The path has no other collective: BatchNorm statistics stay per replica, as in the reference (no SyncBN).  Semantics = DistributedDataParallel: the
 update uses the mean over replicas of the per-replica (weighted-mean) loss gradients.  Like DDP, constructing a
 Trainer inside an initialised process group broadcasts rank 0's parameters AND BatchNorm buffers to every replica.
 Unlike DDP (broadcast_buffers=True) the BatchNorm running statistics are NOT re-synchronised on every forward: each
