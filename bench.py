@@ -628,7 +628,8 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC if args.mode == "train" else "U-Net 256x256 patches/s, inference (softmax probabilities)",
+            "metric": (METRIC if standard and B == 32 else f"U-Net {S}x{S} patches/s, train fwd+bwd (class-weighted CE), batch {B} per B200") if args.mode == "train"
+                      else f"U-Net {S}x{S} patches/s, inference (softmax probabilities)",
             "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 (fp32 accumulate; first conv, BN statistics, head, loss in fp32)", "data": "synthetic",
